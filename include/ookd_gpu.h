@@ -1,0 +1,254 @@
+/*
+ * ookd_gpu.h -- C ABI of the B200 (sm_100a) OOKiedokie receive path.
+ *
+ * libookd_gpu.so replaces the loop body of the reference's ookiedokie_rx()
+ * (reference src/ookiedokie.c:238-290; prototype src/ookiedokie.h:49-51):
+ *
+ *     sdr_rx -> sc16q11_to_complexf          src/sdr/bladeRF_file.c:97-126, src/complexf.h:68-77
+ *     fir_filter_and_decimate                src/fir.h:69-81,  src/fir.c:302-395
+ *     threshold                              src/ookiedokie.c:171-179
+ *     record_dig (edge list)                 src/ookiedokie.c:146-169
+ *     device_process -> sm_process           src/device.c:634-658, src/state_machine.c:421-556
+ *
+ * Conventions follow the reference's: opaque heap handles from *_create,
+ * int status (0 = ok, negative = error), result buffers owned by the handle
+ * and valid until the next call on it or its destruction (cf. device_process,
+ * src/device.c:634-658).  Plain pointers and sizes only; no CUDA or torch
+ * types appear in any signature.  There is NO CPU fallback: every entry point
+ * that computes fails with OOKD_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Threading: a handle may be used from one thread at a time (the reference is
+ * single threaded); different handles are independent.  The library installs
+ * no signal handlers.
+ */
+#ifndef OOKD_GPU_H
+#define OOKD_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OOKD_MAX_STAGES   8      /* FIR stages per filter                           */
+#define OOKD_MAX_TAPS     1024   /* taps per stage                                  */
+#define OOKD_MSG_BYTES    32     /* message payload capacity => num_bits <= 256     */
+
+/* status codes */
+#define OOKD_OK             0
+#define OOKD_ERR_ARG       (-1)  /* invalid argument / descriptor                   */
+#define OOKD_ERR_CUDA      (-2)  /* CUDA runtime error or no usable sm_100 device   */
+#define OOKD_ERR_NOMEM     (-3)
+#define OOKD_ERR_STATE     (-4)  /* call not valid in the handle's current state    */
+#define OOKD_ERR_OVERFLOW  (-5)  /* internal capacity exceeded after retries        */
+
+/* ---- filter: what fir_init() extracts from a filter JSON (src/fir.c:118-226) ---- */
+struct ookd_filter_desc {
+    uint32_t num_stages;                     /* 0 => no filter (ookiedokie.c:261-264) */
+    uint32_t decimation[OOKD_MAX_STAGES];    /* >= 1                                   */
+    uint32_t num_taps[OOKD_MAX_STAGES];      /* >= 1                                   */
+    const float *taps[OOKD_MAX_STAGES];      /* (float) json_number_value(), fir.c:224 */
+};
+
+/* ---- device state machine in the reference's own (microsecond) terms ----
+ * Mirrors the arguments of sm_init / sm_add_state / sm_add_state_trigger
+ * (src/state_machine.h:85-140).  State 0 is RESET (src/state_machine.c:52).
+ * cond / action carry the values of enum sm_trigger_cond / sm_trigger_action
+ * (src/state_machine.h:33-50). */
+enum ookd_cond   { OOKD_COND_ALWAYS = 1, OOKD_COND_PULSE_START, OOKD_COND_PULSE_END,
+                   OOKD_COND_TIMEOUT, OOKD_COND_MSG_COMPLETE };
+enum ookd_action { OOKD_ACT_NONE = 1, OOKD_ACT_APPEND_0, OOKD_ACT_APPEND_1, OOKD_ACT_OUTPUT_DATA };
+
+struct ookd_sm_trigger_us {
+    int32_t  cond;
+    int32_t  action;
+    uint32_t next_state;
+    uint32_t reserved;
+    uint64_t duration_us;                    /* 0 => any                               */
+};
+
+struct ookd_sm_state_us {
+    uint64_t duration_us;                    /* 0 => any                               */
+    uint64_t timeout_us;                     /* 0 => never                             */
+    uint32_t first_trigger;                  /* index into triggers[]                  */
+    uint32_t num_triggers;
+};
+
+struct ookd_sm_desc {
+    uint32_t num_states;
+    uint32_t num_triggers;
+    const struct ookd_sm_state_us   *states;
+    const struct ookd_sm_trigger_us *triggers;
+    uint32_t max_bits;                       /* device "num_bits", 1..256              */
+    uint32_t sample_rate;                    /* samplerate / total decimation, integer
+                                                division as in src/main.c:674-683       */
+};
+
+/* ---- the same machine compiled to integer sample counts (what the GPU runs) ----
+ * The reference accumulates elapsed_us += (1.0/fs)*1e6 per non-firing
+ * evaluation (src/state_machine.c:78-82,:514) and compares it with float
+ * windows d -/+ 0.15 d (:100-133).  ookd_sm_compile() replays that
+ * accumulation once and records, for every window, the first and last count k
+ * of consecutive non-firing evaluations for which the comparison holds. */
+#define OOKD_K_INF 0xFFFFFFFFu
+
+struct ookd_sm_trigger_k {
+    int32_t  cond;
+    int32_t  action;
+    uint32_t next_state;
+    uint32_t kmin, kmax;                     /* fires only for kmin <= k <= kmax       */
+};
+
+struct ookd_sm_state_k {
+    uint32_t first_trigger, num_triggers;
+    uint32_t dmin, dmax;                     /* state-duration window (edge triggers)  */
+    uint32_t ktimeout;                       /* OOKD_K_INF => never                    */
+};
+
+struct ookd_sm_compiled {
+    uint32_t num_states, num_triggers;
+    struct ookd_sm_state_k   *states;        /* malloc'd by ookd_sm_compile            */
+    struct ookd_sm_trigger_k *triggers;
+    uint32_t max_bits;
+    uint32_t k_sat;                          /* counts saturate here: > every finite bound */
+};
+
+int  ookd_sm_compile(const struct ookd_sm_desc *desc, struct ookd_sm_compiled *out);
+void ookd_sm_compiled_free(struct ookd_sm_compiled *c);
+
+/* Smallest float p with sqrtf(p) >= thr, so that (re*re+im*im >= p) is the
+ * reference's (sqrtf(re*re+im*im) >= thr), src/ookiedokie.c:177. */
+float ookd_power_threshold(float thr);
+
+/* ---- results ---- */
+struct ookd_msg {
+    uint64_t out_sample;                     /* post-decimation index of the sample that
+                                                raised SM_PROCESS_RESULT_OUTPUT_READY   */
+    uint64_t buffer_idx;                     /* samples_per_buffer buffer it belongs to:
+                                                the reference prints one group per buffer
+                                                (src/ookiedokie.c:283-287)              */
+    uint32_t num_bits;
+    uint32_t reserved;
+    uint8_t  data[OOKD_MSG_BYTES];           /* LSB-first within bytes, state_machine.c:365-385 */
+};
+
+/* State-machine state between two post-decimation samples.  Used to stitch
+ * time shards (one per GPU) and successive ookd_gpu_decode_shard calls. */
+struct ookd_sm_carry {
+    uint32_t state;
+    uint32_t k;                              /* consecutive non-firing evaluations, saturated */
+    uint32_t num_bits;
+    uint32_t prev_bit;                       /* sm->prev_bit; may be stale after a dropped buffer */
+    uint8_t  data[OOKD_MSG_BYTES];
+};
+
+struct ookd_gpu_config {
+    const struct ookd_filter_desc *filter;   /* NULL or num_stages==0 => no filter     */
+    const struct ookd_sm_desc *sm;           /* NULL => thresholds/edges only          */
+    float    threshold;                      /* cfg->rx_threshold                      */
+    uint32_t samples_per_buffer;             /* cfg->samples_per_buffer (semantic!)    */
+    int32_t  device_id;                      /* CUDA ordinal; -1 => current device     */
+    uint32_t flags;                          /* OOKD_FLAG_*                            */
+    uint32_t sm_chunk_buffers;               /* buffers per state-machine work item; 0 => default */
+};
+
+#define OOKD_FLAG_FORCE_GENERIC  1u          /* always use the shape-agnostic FIR kernels       */
+#define OOKD_FLAG_NO_SCREEN      2u          /* disable the reduced-precision screen (exact MACs
+                                                for every sample)                                */
+
+struct ookd_gpu_result {
+    uint64_t n_in;                           /* input samples consumed incl. EOF zero padding   */
+    uint64_t n_out;                          /* post-decimation samples                          */
+    uint64_t n_buffers;
+    uint64_t n_edges;
+    uint64_t n_msgs;
+    const struct ookd_msg *msgs;             /* host memory owned by the handle                  */
+    uint32_t first_bit;                      /* threshold decision of output sample 0            */
+    uint32_t sm_rounds;                      /* speculation rounds the stitcher needed           */
+    float    kernel_ms;                      /* device time of the last call (CUDA events)       */
+    float    fir_ms;                         /* ... of the FIR/threshold kernel(s) alone         */
+    uint32_t gpu_launches;                   /* kernels launched by the last call                */
+    uint32_t refined_tiles;                  /* tiles that needed the exact path (screen mode)   */
+};
+
+typedef struct ookd_gpu ookd_gpu;
+
+int  ookd_gpu_device_count(void);
+const char *ookd_gpu_strerror(int status);
+const char *ookd_gpu_last_error(const ookd_gpu *h);     /* detail text for the last failure */
+
+int  ookd_gpu_create(ookd_gpu **h, const struct ookd_gpu_config *cfg);
+void ookd_gpu_destroy(ookd_gpu *h);
+
+/* Whole-capture decode == running ookiedokie_rx() over a file holding
+ * n_samples SC16Q11 samples (interleaved little-endian int16 I,Q): the tail is
+ * zero padded to a multiple of samples_per_buffer exactly like
+ * sdr_bladerf_file_rx (src/sdr/bladeRF_file.c:106-123).
+ * iq may be host memory (pinned recommended; copied in pipelined pieces) or,
+ * with iq_is_device_ptr != 0, memory on the handle's device. */
+int  ookd_gpu_decode(ookd_gpu *h, const int16_t *iq, uint64_t n_samples,
+                     int iq_is_device_ptr, struct ookd_gpu_result *res);
+
+/* Time-shard decode (multi-GPU / streaming).  The shard covers input samples
+ * [first_sample, first_sample + n_samples) of a longer capture; first_sample
+ * must be a multiple of lcm(samples_per_buffer, total decimation).  iq points
+ * at sample first_sample - halo, where halo = ookd_gpu_halo(h) samples of
+ * history (fewer only when first_sample < halo: then iq points at sample 0).
+ * `last` != 0 applies the EOF zero padding.  entry == NULL starts the state
+ * machine in RESET (capture start); otherwise it resumes from *entry, which
+ * may be a guess: ookd_gpu_resolve() re-runs only the state machine stage from
+ * a corrected entry without touching the samples again.  exit_ receives the
+ * state after the shard's last sample. */
+int  ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr,
+                           uint64_t first_sample, uint64_t n_samples, int last,
+                           const struct ookd_sm_carry *entry, struct ookd_sm_carry *exit_,
+                           struct ookd_gpu_result *res);
+int  ookd_gpu_resolve(ookd_gpu *h, const struct ookd_sm_carry *entry,
+                      struct ookd_sm_carry *exit_, struct ookd_gpu_result *res);
+uint32_t ookd_gpu_halo(const ookd_gpu *h);               /* input samples of FIR history  */
+uint32_t ookd_gpu_total_decimation(const ookd_gpu *h);
+void ookd_gpu_initial_carry(const ookd_gpu *h, struct ookd_sm_carry *c);  /* RESET, k=0 */
+
+/* Edge list of the last decode (the information --rx-rec-dig serialises,
+ * src/ookiedokie.c:146-169): positions i >= 1 (global post-decimation index)
+ * with bit[i] != bit[i-1]; polarity alternates starting from !first_bit. */
+int  ookd_gpu_edges(ookd_gpu *h, const uint64_t **edges, uint64_t *n_edges, uint32_t *first_bit);
+
+/* Threshold decisions of the last decode, one byte per output sample. */
+int  ookd_gpu_bits(ookd_gpu *h, uint8_t *bits_out, uint64_t max_out, uint64_t *n_out);
+
+/* Filtered + decimated samples (interleaved float re,im) computed with the
+ * reference's exact in-order fp32 arithmetic (src/fir.c:313-318); the parity
+ * dump for fir_filter_and_decimate.  Runs its own kernels; does not disturb
+ * the last decode's results. */
+int  ookd_gpu_filtered(ookd_gpu *h, const int16_t *iq, uint64_t n_samples, int iq_is_device_ptr,
+                       float *out_iq_host, uint64_t max_out, uint64_t *n_out);
+
+/* Same arithmetic on caller-supplied complex float input (what fir_test feeds
+ * fir_filter_and_decimate, src/test/fir_test.c:246-275). */
+int  ookd_gpu_filter_cf(ookd_gpu *h, const float *in_iq_host, uint64_t n_samples,
+                        float *out_iq_host, uint64_t max_out, uint64_t *n_out);
+
+/* Device-side synthetic SC16Q11 capture (benchmark/test input; integer-only
+ * recipe shared with oracle/ookd_oracle.c:ookd_oracle_synth).  Writes
+ * n_samples samples starting at global index first_sample to dst, which is
+ * device memory if dst_is_device_ptr else host memory. */
+int  ookd_gpu_synth(int32_t device_id, int16_t *dst, int dst_is_device_ptr,
+                    uint64_t first_sample, uint64_t n_samples,
+                    const uint64_t *toggles_host, uint64_t n_toggles,
+                    int32_t i_on, int32_t q_on, int32_t noise_scale, uint64_t seed);
+
+/* Pinned host memory for captures handed to ookd_gpu_decode. */
+void *ookd_gpu_host_alloc(size_t bytes);
+void  ookd_gpu_host_free(void *p);
+/* Raw device buffers (so a C host can keep a capture resident without CUDA headers). */
+void *ookd_gpu_dev_alloc(int32_t device_id, size_t bytes);
+void  ookd_gpu_dev_free(int32_t device_id, void *p);
+int   ookd_gpu_memcpy_h2d(int32_t device_id, void *dst_dev, const void *src_host, size_t bytes);
+int   ookd_gpu_memcpy_d2h(int32_t device_id, void *dst_host, const void *src_dev, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OOKD_GPU_H */

@@ -1,0 +1,390 @@
+"""ctypes view of the C ABI in include/ookd_gpu.h (libookd_gpu.so).
+
+This module is glue for tests, bench.py and scripting; the product is the
+shared library.  It contains no arithmetic of its own and no fallback: if the
+library is missing it is built, and if there is no sm_100 device every compute
+call raises OokdError.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libookd_gpu.so")
+
+MAX_STAGES = 8
+MSG_BYTES = 32
+K_INF = 0xFFFFFFFF
+
+FLAG_FORCE_GENERIC = 1
+FLAG_NO_SCREEN = 2
+
+# every symbol include/ookd_gpu.h declares
+EXPORTS = [
+    "ookd_sm_compile", "ookd_sm_compiled_free", "ookd_power_threshold",
+    "ookd_gpu_device_count", "ookd_gpu_strerror", "ookd_gpu_last_error",
+    "ookd_gpu_create", "ookd_gpu_destroy", "ookd_gpu_decode", "ookd_gpu_decode_shard",
+    "ookd_gpu_resolve", "ookd_gpu_halo", "ookd_gpu_total_decimation", "ookd_gpu_initial_carry",
+    "ookd_gpu_edges", "ookd_gpu_bits", "ookd_gpu_filtered", "ookd_gpu_filter_cf", "ookd_gpu_synth",
+    "ookd_gpu_host_alloc", "ookd_gpu_host_free", "ookd_gpu_dev_alloc", "ookd_gpu_dev_free",
+    "ookd_gpu_memcpy_h2d", "ookd_gpu_memcpy_d2h",
+]
+
+
+class OokdError(RuntimeError):
+    pass
+
+
+class FilterDesc(C.Structure):
+    _fields_ = [("num_stages", C.c_uint32),
+                ("decimation", C.c_uint32 * MAX_STAGES),
+                ("num_taps", C.c_uint32 * MAX_STAGES),
+                ("taps", C.POINTER(C.c_float) * MAX_STAGES)]
+
+
+class SmTriggerUs(C.Structure):
+    _fields_ = [("cond", C.c_int32), ("action", C.c_int32), ("next_state", C.c_uint32),
+                ("reserved", C.c_uint32), ("duration_us", C.c_uint64)]
+
+
+class SmStateUs(C.Structure):
+    _fields_ = [("duration_us", C.c_uint64), ("timeout_us", C.c_uint64),
+                ("first_trigger", C.c_uint32), ("num_triggers", C.c_uint32)]
+
+
+class SmDesc(C.Structure):
+    _fields_ = [("num_states", C.c_uint32), ("num_triggers", C.c_uint32),
+                ("states", C.POINTER(SmStateUs)), ("triggers", C.POINTER(SmTriggerUs)),
+                ("max_bits", C.c_uint32), ("sample_rate", C.c_uint32)]
+
+
+class SmTriggerK(C.Structure):
+    _fields_ = [("cond", C.c_int32), ("action", C.c_int32), ("next_state", C.c_uint32),
+                ("kmin", C.c_uint32), ("kmax", C.c_uint32)]
+
+
+class SmStateK(C.Structure):
+    _fields_ = [("first_trigger", C.c_uint32), ("num_triggers", C.c_uint32),
+                ("dmin", C.c_uint32), ("dmax", C.c_uint32), ("ktimeout", C.c_uint32)]
+
+
+class SmCompiled(C.Structure):
+    _fields_ = [("num_states", C.c_uint32), ("num_triggers", C.c_uint32),
+                ("states", C.POINTER(SmStateK)), ("triggers", C.POINTER(SmTriggerK)),
+                ("max_bits", C.c_uint32), ("k_sat", C.c_uint32)]
+
+
+class Msg(C.Structure):
+    _fields_ = [("out_sample", C.c_uint64), ("buffer_idx", C.c_uint64), ("num_bits", C.c_uint32),
+                ("reserved", C.c_uint32), ("data", C.c_uint8 * MSG_BYTES)]
+
+
+class SmCarry(C.Structure):
+    _fields_ = [("state", C.c_uint32), ("k", C.c_uint32), ("num_bits", C.c_uint32),
+                ("prev_bit", C.c_uint32), ("data", C.c_uint8 * MSG_BYTES)]
+
+    def astuple(self):
+        return (self.state, self.k, self.num_bits, self.prev_bit, bytes(self.data))
+
+    @classmethod
+    def fromtuple(cls, t):
+        c = cls()
+        c.state, c.k, c.num_bits, c.prev_bit = t[:4]
+        C.memmove(c.data, t[4], MSG_BYTES)
+        return c
+
+
+class GpuConfig(C.Structure):
+    _fields_ = [("filter", C.POINTER(FilterDesc)), ("sm", C.POINTER(SmDesc)), ("threshold", C.c_float),
+                ("samples_per_buffer", C.c_uint32), ("device_id", C.c_int32), ("flags", C.c_uint32),
+                ("sm_chunk_buffers", C.c_uint32)]
+
+
+class GpuResult(C.Structure):
+    _fields_ = [("n_in", C.c_uint64), ("n_out", C.c_uint64), ("n_buffers", C.c_uint64),
+                ("n_edges", C.c_uint64), ("n_msgs", C.c_uint64), ("msgs", C.POINTER(Msg)),
+                ("first_bit", C.c_uint32), ("sm_rounds", C.c_uint32), ("kernel_ms", C.c_float),
+                ("fir_ms", C.c_float), ("gpu_launches", C.c_uint32), ("refined_tiles", C.c_uint32)]
+
+
+def build_library():
+    subprocess.run(["make", "-s", "-C", os.path.join(_HERE, "csrc")], check=True)
+
+
+_lib = None
+
+
+def lib():
+    """Load libookd_gpu.so (building it first if absent).  Never falls back to anything else."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build_library()
+        L = C.CDLL(LIB_PATH)
+        L.ookd_sm_compile.restype = C.c_int
+        L.ookd_sm_compile.argtypes = [C.POINTER(SmDesc), C.POINTER(SmCompiled)]
+        L.ookd_sm_compiled_free.argtypes = [C.POINTER(SmCompiled)]
+        L.ookd_power_threshold.restype = C.c_float
+        L.ookd_power_threshold.argtypes = [C.c_float]
+        L.ookd_gpu_device_count.restype = C.c_int
+        L.ookd_gpu_strerror.restype = C.c_char_p
+        L.ookd_gpu_strerror.argtypes = [C.c_int]
+        L.ookd_gpu_last_error.restype = C.c_char_p
+        L.ookd_gpu_last_error.argtypes = [C.c_void_p]
+        L.ookd_gpu_create.restype = C.c_int
+        L.ookd_gpu_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GpuConfig)]
+        L.ookd_gpu_destroy.argtypes = [C.c_void_p]
+        L.ookd_gpu_decode.restype = C.c_int
+        L.ookd_gpu_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(GpuResult)]
+        L.ookd_gpu_decode_shard.restype = C.c_int
+        L.ookd_gpu_decode_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int,
+                                            C.POINTER(SmCarry), C.POINTER(SmCarry), C.POINTER(GpuResult)]
+        L.ookd_gpu_resolve.restype = C.c_int
+        L.ookd_gpu_resolve.argtypes = [C.c_void_p, C.POINTER(SmCarry), C.POINTER(SmCarry), C.POINTER(GpuResult)]
+        L.ookd_gpu_halo.restype = C.c_uint32
+        L.ookd_gpu_halo.argtypes = [C.c_void_p]
+        L.ookd_gpu_total_decimation.restype = C.c_uint32
+        L.ookd_gpu_total_decimation.argtypes = [C.c_void_p]
+        L.ookd_gpu_initial_carry.argtypes = [C.c_void_p, C.POINTER(SmCarry)]
+        L.ookd_gpu_edges.restype = C.c_int
+        L.ookd_gpu_edges.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64),
+                                     C.POINTER(C.c_uint32)]
+        L.ookd_gpu_bits.restype = C.c_int
+        L.ookd_gpu_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.ookd_gpu_filtered.restype = C.c_int
+        L.ookd_gpu_filtered.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64,
+                                        C.POINTER(C.c_uint64)]
+        L.ookd_gpu_filter_cf.restype = C.c_int
+        L.ookd_gpu_filter_cf.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                         C.POINTER(C.c_uint64)]
+        L.ookd_gpu_synth.restype = C.c_int
+        L.ookd_gpu_synth.argtypes = [C.c_int32, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p,
+                                     C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
+        L.ookd_gpu_host_alloc.restype = C.c_void_p
+        L.ookd_gpu_host_alloc.argtypes = [C.c_size_t]
+        L.ookd_gpu_host_free.argtypes = [C.c_void_p]
+        L.ookd_gpu_dev_alloc.restype = C.c_void_p
+        L.ookd_gpu_dev_alloc.argtypes = [C.c_int32, C.c_size_t]
+        L.ookd_gpu_dev_free.argtypes = [C.c_int32, C.c_void_p]
+        L.ookd_gpu_memcpy_h2d.restype = C.c_int
+        L.ookd_gpu_memcpy_h2d.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.ookd_gpu_memcpy_d2h.restype = C.c_int
+        L.ookd_gpu_memcpy_d2h.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def make_filter_desc(stages):
+    """stages: [(decimation, float32 taps)] -> (FilterDesc, keepalive)."""
+    fd = FilterDesc()
+    keep = []
+    fd.num_stages = len(stages)
+    for i, (dec, taps) in enumerate(stages):
+        t = np.ascontiguousarray(taps, dtype=np.float32)
+        keep.append(t)
+        fd.decimation[i] = int(dec)
+        fd.num_taps[i] = len(t)
+        fd.taps[i] = t.ctypes.data_as(C.POINTER(C.c_float))
+    return fd, keep
+
+
+def make_sm_desc(states, num_bits, sample_rate):
+    """states: [dict(duration_us, timeout_us, triggers=[dict(cond, action, next, duration_us)])]
+    (state 0 = RESET) -> (SmDesc, keepalive)."""
+    nt = sum(len(s["triggers"]) for s in states)
+    st = (SmStateUs * len(states))()
+    tr = (SmTriggerUs * max(nt, 1))()
+    q = 0
+    for i, s in enumerate(states):
+        st[i].duration_us = int(s["duration_us"])
+        st[i].timeout_us = int(s["timeout_us"])
+        st[i].first_trigger = q
+        st[i].num_triggers = len(s["triggers"])
+        for t in s["triggers"]:
+            tr[q].cond = int(t["cond"])
+            tr[q].action = int(t["action"])
+            tr[q].next_state = int(t["next"])
+            tr[q].duration_us = int(t["duration_us"])
+            q += 1
+    d = SmDesc()
+    d.num_states = len(states)
+    d.num_triggers = nt
+    d.states = C.cast(st, C.POINTER(SmStateUs))
+    d.triggers = C.cast(tr, C.POINTER(SmTriggerUs))
+    d.max_bits = int(num_bits)
+    d.sample_rate = int(sample_rate)
+    return d, (st, tr)
+
+
+def sm_compile(states, num_bits, sample_rate):
+    """Host-only: integer windows the GPU will use.  -> dict(states=[...], triggers=[...], k_sat)."""
+    d, keep = make_sm_desc(states, num_bits, sample_rate)
+    out = SmCompiled()
+    rc = lib().ookd_sm_compile(C.byref(d), C.byref(out))
+    if rc != 0:
+        raise OokdError(f"ookd_sm_compile: {lib().ookd_gpu_strerror(rc).decode()}")
+    res = dict(k_sat=out.k_sat, max_bits=out.max_bits,
+               states=[dict(first_trigger=out.states[i].first_trigger, num_triggers=out.states[i].num_triggers,
+                            dmin=out.states[i].dmin, dmax=out.states[i].dmax, ktimeout=out.states[i].ktimeout)
+                       for i in range(out.num_states)],
+               triggers=[dict(cond=out.triggers[i].cond, action=out.triggers[i].action,
+                              next=out.triggers[i].next_state, kmin=out.triggers[i].kmin, kmax=out.triggers[i].kmax)
+                         for i in range(out.num_triggers)])
+    lib().ookd_sm_compiled_free(C.byref(out))
+    return res
+
+
+def power_threshold(thr):
+    return float(lib().ookd_power_threshold(C.c_float(thr)))
+
+
+def device_count():
+    return int(lib().ookd_gpu_device_count())
+
+
+def _as_ptr(iq):
+    """numpy int16 array -> (pointer, n_samples, is_device=0, keepalive); (int ptr, n) tuples pass through as device."""
+    if isinstance(iq, tuple):
+        return C.c_void_p(int(iq[0])), int(iq[1]), 1, None
+    a = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+    return C.c_void_p(a.ctypes.data), a.size // 2, 0, a
+
+
+class Gpu:
+    """One ookd_gpu handle."""
+
+    def __init__(self, filter_stages=None, sm=None, threshold=0.1, samples_per_buffer=8192, device_id=-1,
+                 flags=0, sm_chunk_buffers=0):
+        L = lib()
+        cfg = GpuConfig()
+        self._keep = []
+        if filter_stages:
+            fd, k = make_filter_desc(filter_stages)
+            self._keep += [fd, k]
+            cfg.filter = C.pointer(fd)
+        if sm is not None:
+            sd, k = make_sm_desc(sm["states"], sm["num_bits"], sm["sample_rate"])
+            self._keep += [sd, k]
+            cfg.sm = C.pointer(sd)
+            self.msg_bytes = (sm["num_bits"] + 7) // 8
+        else:
+            self.msg_bytes = 0
+        cfg.threshold = threshold
+        cfg.samples_per_buffer = samples_per_buffer
+        cfg.device_id = device_id
+        cfg.flags = flags
+        cfg.sm_chunk_buffers = sm_chunk_buffers
+        self.h = C.c_void_p()
+        rc = L.ookd_gpu_create(C.byref(self.h), C.byref(cfg))
+        if rc != 0:
+            self.h = None
+            raise OokdError(f"ookd_gpu_create: {L.ookd_gpu_strerror(rc).decode()}")
+        self.device_id = device_id
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().ookd_gpu_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise OokdError(f"{what}: {lib().ookd_gpu_strerror(rc).decode()} ({lib().ookd_gpu_last_error(self.h).decode()})")
+
+    def _result(self, res):
+        msgs = [(int(res.msgs[i].out_sample), int(res.msgs[i].buffer_idx), int(res.msgs[i].num_bits),
+                 bytes(res.msgs[i].data[:self.msg_bytes])) for i in range(res.n_msgs)]
+        return dict(n_in=int(res.n_in), n_out=int(res.n_out), n_buffers=int(res.n_buffers),
+                    n_edges=int(res.n_edges), msgs=msgs, first_bit=int(res.first_bit),
+                    sm_rounds=int(res.sm_rounds), kernel_ms=float(res.kernel_ms), fir_ms=float(res.fir_ms),
+                    gpu_launches=int(res.gpu_launches), refined_tiles=int(res.refined_tiles))
+
+    @property
+    def halo(self):
+        return int(lib().ookd_gpu_halo(self.h))
+
+    @property
+    def total_decimation(self):
+        return int(lib().ookd_gpu_total_decimation(self.h))
+
+    def decode(self, iq):
+        """iq: numpy int16 (host) or (device_ptr, n_samples)."""
+        p, n, is_dev, keep = _as_ptr(iq)
+        res = GpuResult()
+        self._check(lib().ookd_gpu_decode(self.h, p, n, is_dev, C.byref(res)), "ookd_gpu_decode")
+        return self._result(res)
+
+    def decode_shard(self, iq, first_sample, n_samples, last, entry=None):
+        """iq points at sample first_sample - min(halo, first_sample).  -> (result, exit carry tuple)."""
+        if isinstance(iq, tuple):
+            p, is_dev, keep = C.c_void_p(int(iq[0])), 1, None
+        else:
+            keep = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+            p, is_dev = C.c_void_p(keep.ctypes.data), 0
+        res = GpuResult()
+        ex = SmCarry()
+        en = SmCarry.fromtuple(entry) if entry is not None else None
+        self._check(lib().ookd_gpu_decode_shard(self.h, p, is_dev, first_sample, n_samples, int(last),
+                                                C.byref(en) if en is not None else None, C.byref(ex),
+                                                C.byref(res)), "ookd_gpu_decode_shard")
+        return self._result(res), ex.astuple()
+
+    def resolve(self, entry):
+        res = GpuResult()
+        ex = SmCarry()
+        en = SmCarry.fromtuple(entry)
+        self._check(lib().ookd_gpu_resolve(self.h, C.byref(en), C.byref(ex), C.byref(res)), "ookd_gpu_resolve")
+        return self._result(res), ex.astuple()
+
+    def edges(self):
+        p = C.POINTER(C.c_uint64)()
+        n = C.c_uint64()
+        fb = C.c_uint32()
+        self._check(lib().ookd_gpu_edges(self.h, C.byref(p), C.byref(n), C.byref(fb)), "ookd_gpu_edges")
+        e = np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint64)
+        return int(fb.value), e
+
+    def bits(self):
+        n = C.c_uint64()
+        self._check(lib().ookd_gpu_bits(self.h, None, 0, C.byref(n)), "ookd_gpu_bits")
+        out = np.empty(n.value, dtype=np.uint8)
+        self._check(lib().ookd_gpu_bits(self.h, out.ctypes.data, n.value, C.byref(n)), "ookd_gpu_bits")
+        return out
+
+    def filtered(self, iq):
+        p, n, is_dev, keep = _as_ptr(iq)
+        m = C.c_uint64()
+        self._check(lib().ookd_gpu_filtered(self.h, p, n, is_dev, None, 0, C.byref(m)), "ookd_gpu_filtered")
+        out = np.empty((m.value, 2), dtype=np.float32)
+        self._check(lib().ookd_gpu_filtered(self.h, p, n, is_dev, out.ctypes.data, m.value, C.byref(m)),
+                    "ookd_gpu_filtered")
+        return out
+
+    def filter_cf(self, iq_f32):
+        x = np.ascontiguousarray(iq_f32, dtype=np.float32).reshape(-1, 2)
+        m = C.c_uint64()
+        self._check(lib().ookd_gpu_filter_cf(self.h, x.ctypes.data, x.shape[0], None, 0, C.byref(m)),
+                    "ookd_gpu_filter_cf")
+        out = np.empty((m.value, 2), dtype=np.float32)
+        self._check(lib().ookd_gpu_filter_cf(self.h, x.ctypes.data, x.shape[0], out.ctypes.data, m.value,
+                                             C.byref(m)), "ookd_gpu_filter_cf")
+        return out
+
+
+def synth(n_samples, toggles, i_on, q_on, noise_scale, seed, first_sample=0, device_id=-1, device_ptr=None):
+    """Synthetic capture on the GPU.  Returns numpy (n,2) int16, or fills device_ptr when given."""
+    tg = np.ascontiguousarray(toggles, dtype=np.uint64)
+    if device_ptr is not None:
+        rc = lib().ookd_gpu_synth(device_id, C.c_void_p(int(device_ptr)), 1, first_sample, n_samples,
+                                  tg.ctypes.data, len(tg), int(i_on), int(q_on), int(noise_scale), int(seed))
+        out = None
+    else:
+        out = np.empty((n_samples, 2), dtype=np.int16)
+        rc = lib().ookd_gpu_synth(device_id, out.ctypes.data, 0, first_sample, n_samples, tg.ctypes.data, len(tg),
+                                  int(i_on), int(q_on), int(noise_scale), int(seed))
+    if rc != 0:
+        raise OokdError(f"ookd_gpu_synth: {lib().ookd_gpu_strerror(rc).decode()}")
+    return out

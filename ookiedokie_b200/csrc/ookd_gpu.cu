@@ -1,0 +1,860 @@
+// ookd_gpu.cu -- C ABI of the sm_100a receive path (include/ookd_gpu.h).
+//
+// One handle = one CUDA device + two streams (copy, compute) + grow-only workspaces.
+// A decode is:  [H2D pieces ->] FIR/threshold kernel(s) -> edge count / scan / write ->
+// state-machine rounds -> message gather -> D2H of the (tiny) message list.
+// There is no CPU fallback anywhere in this file: without a usable device every compute
+// entry point returns OOKD_ERR_CUDA.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ookd_common.cuh"
+#include "fir_kernels.cuh"
+#include "edge_kernels.cuh"
+#include "sm_kernels.cuh"
+#include "synth_kernel.cuh"
+
+using namespace ookd;
+
+namespace {
+
+struct DevBuf {
+    void  *p = nullptr;
+    size_t cap = 0;
+};
+
+struct Stage {
+    uint32_t T = 0, D = 1;
+    std::vector<float> taps;
+    float *d_taps = nullptr;
+};
+
+enum FirPath { FIR_GENERIC = 0, FIR_TILED_1STAGE_32 };
+
+}  // namespace
+
+struct ookd_gpu {
+    int device = 0;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr;
+    std::vector<cudaEvent_t> ev_piece;
+
+    std::vector<Stage> stages;        // empty => no filter (treated as the 1-tap unity stage)
+    uint32_t total_dec = 1;
+    uint32_t halo_fir = 0;            // input samples of history the FIR chain needs
+    uint32_t halo = 0;                // what callers must provide in front of a shard
+    FirPath path = FIR_GENERIC;
+    float threshold = 0.1f, pstar = 0.0f;
+    uint32_t spb = 8192;
+    uint32_t chunk_buffers = 64;
+    uint32_t flags = 0;
+
+    bool have_sm = false;
+    ookd_sm_compiled smc{};
+    SmTable *d_tab = nullptr;
+
+    // workspaces
+    DevBuf in, bits, inter[2], block_counts, edges, scalars, chunk_exit[2], chunk_ran, slots, slot_count,
+           slot_off, msgs_dev;
+    uint32_t slot_cap = 8;
+    void *h_scalars = nullptr;        // pinned, 256 B
+    std::vector<ookd_msg> h_msgs;
+    std::vector<SmMsg> h_msgs_raw;
+    std::vector<u64> h_edges;
+    bool h_edges_valid = false;
+
+    // geometry of the last decode (needed by resolve / edges / bits)
+    bool have_last = false;
+    i64 out_lo = 0, out_hi = 0, bit_base = 0;
+    uint32_t pre = 0;
+    u64 n_edges = 0, first_buffer = 0, n_buffers = 0, n_in = 0;
+    uint32_t n_chunks = 0, base_bit = 0;
+    int exit_idx = 0;
+    uint32_t launches = 0;
+
+    char err[256] = {0};
+};
+
+namespace {
+
+int fail(ookd_gpu *h, int code, const char *fmt, ...)
+{
+    if (h) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(h->err, sizeof(h->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(h, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            return fail(h, OOKD_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,             \
+                        cudaGetErrorString(e_));                                                 \
+        }                                                                                        \
+    } while (0)
+
+int ensure(ookd_gpu *h, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return OOKD_OK;
+    if (b.p) {
+        CU(h, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        want = bytes;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(h, OOKD_ERR_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return OOKD_OK;
+}
+
+void release(DevBuf &b)
+{
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+u64 gcd64(u64 a, u64 b) { while (b) { u64 t = a % b; a = b; b = t; } return a; }
+
+void carry_to_dev(const ookd_sm_carry &c, SmCarry &d)
+{
+    d.state = c.state; d.k = c.k; d.num_bits = c.num_bits; d.prev = c.prev_bit;
+    memcpy(d.data, c.data, 32);
+}
+
+void carry_from_dev(const SmCarry &d, ookd_sm_carry &c)
+{
+    c.state = d.state; c.k = d.k; c.num_bits = d.num_bits; c.prev_bit = d.prev;
+    memcpy(c.data, d.data, 32);
+}
+
+// ---- FIR/threshold over outputs [o_begin, o_end) of the shard (tile-aligned by the caller) ----
+int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end, i64 o_begin, i64 o_end)
+{
+    if (o_end <= o_begin) return OOKD_OK;
+    if (h->path == FIR_TILED_1STAGE_32) {
+        constexpr int R = 8, L = 256 * R;
+        TiledArgs a{};
+        a.in = d_in; a.in_base = in_base; a.in_valid_end = in_valid_end;
+        a.out_lo = o_begin; a.out_hi = o_end;
+        a.out_bits = (uint8_t *) h->bits.p; a.bit_base = h->bit_base; a.pstar = h->pstar;
+        a.tile_list = nullptr; a.tile_count = nullptr;
+        TapsParam<32> tp;
+        memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
+        const u64 tiles = (u64) (o_end - o_begin + L - 1) / L;
+        fir1_exact_tiled_kernel<32, R><<<(unsigned) tiles, 256, 0, h->s_compute>>>(a, tp);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        return OOKD_OK;
+    }
+    return fail(h, OOKD_ERR_STATE, "launch_fir: no tiled path");
+}
+
+// ---- shape-agnostic chain: one launch per stage, intermediates in HBM ----
+// Computes final outputs [o_lo, o_hi); writes decisions (bits != null) and/or the final
+// stage's samples (out_cf != null, out_cf[0] <-> o_lo).  `in` is int16x2 (in_is_i16) or float2.
+int run_generic_chain(ookd_gpu *h, const void *d_in, bool in_is_i16, i64 in_base, i64 in_valid_end,
+                      i64 o_lo, i64 o_hi, float2 *out_cf, uint32_t *bits, i64 bit_base)
+{
+    if (o_hi <= o_lo) return OOKD_OK;
+    const size_t ns = h->stages.size();
+    // required output range per stage, walking backwards
+    std::vector<i64> lo(ns), hi(ns);
+    i64 need_lo = o_lo, need_hi = o_hi;
+    for (size_t s = ns; s-- > 0;) {
+        lo[s] = need_lo; hi[s] = need_hi;
+        const Stage &st = h->stages[s];
+        // stage s output j reads stage s-1 outputs (j+1)*D-1-(T-1) .. (j+1)*D-1
+        need_hi = need_hi * (i64) st.D;                                   // exclusive
+        need_lo = (need_lo + 1) * (i64) st.D - 1 - (i64) (st.T - 1);
+        if (need_lo < 0) need_lo = 0;
+    }
+    const void *src = d_in;
+    bool src_i16 = in_is_i16;
+    i64 src_base = in_base, src_end = in_valid_end;
+    for (size_t s = 0; s < ns; s++) {
+        const Stage &st = h->stages[s];
+        const bool last = (s + 1 == ns);
+        GenericStageArgs a{};
+        a.in = src; a.in_base = src_base; a.in_valid_end = src_end;
+        a.taps = st.d_taps; a.T = st.T; a.D = st.D;
+        a.out_lo = lo[s]; a.out_hi = hi[s];
+        a.pstar = h->pstar;
+        if (last) {
+            a.out_cf = out_cf; a.out_bits = bits; a.bit_base = bit_base;
+        } else {
+            DevBuf &ib = h->inter[s & 1];
+            const int rc = ensure(h, ib, (size_t) (hi[s] - lo[s]) * sizeof(float2));
+            if (rc) return rc;
+            a.out_cf = (float2 *) ib.p; a.out_bits = nullptr; a.bit_base = 0;
+        }
+        const u64 n = (u64) (hi[s] - lo[s]);
+        const unsigned grid = (unsigned) ((n + 255) / 256);
+        const size_t smem = st.T * sizeof(float);
+        if (src_i16) {
+            fir_stage_generic_kernel<true><<<grid, 256, smem, h->s_compute>>>(a);
+        } else {
+            fir_stage_generic_kernel<false><<<grid, 256, smem, h->s_compute>>>(a);
+        }
+        h->launches++;
+        CU(h, cudaGetLastError());
+        src = a.out_cf; src_i16 = false; src_base = lo[s]; src_end = hi[s];
+    }
+    return OOKD_OK;
+}
+
+// ---- state machine stage + message gather; fills res ----
+int run_state_machine(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *exit_, ookd_gpu_result *res)
+{
+    h->h_msgs.clear();
+    uint32_t rounds = 0;
+    if (!h->have_sm || h->out_hi <= h->out_lo) {
+        if (exit_) {
+            ookd_sm_carry c{};
+            carry_from_dev(entry0, c);
+            *exit_ = c;
+        }
+        if (res) { res->n_msgs = 0; res->msgs = nullptr; res->sm_rounds = 0; }
+        return OOKD_OK;
+    }
+    const uint32_t nc = h->n_chunks;
+    int rc;
+    if ((rc = ensure(h, h->chunk_exit[0], sizeof(SmCarry) * nc))) return rc;
+    if ((rc = ensure(h, h->chunk_exit[1], sizeof(SmCarry) * nc))) return rc;
+    if ((rc = ensure(h, h->chunk_ran, sizeof(SmCarry) * nc))) return rc;
+    if ((rc = ensure(h, h->slot_count, sizeof(uint32_t) * (nc + 1)))) return rc;
+    if ((rc = ensure(h, h->slot_off, sizeof(uint32_t) * (nc + 1)))) return rc;
+
+    uint32_t *d_nran = (uint32_t *) ((char *) h->scalars.p + 64);      // [32] per-burst round counters
+    uint32_t *d_overflow = (uint32_t *) ((char *) h->scalars.p + 32);
+    const uint32_t *h_nran = (const uint32_t *) ((const char *) h->h_scalars + 64);
+    const uint32_t *h_overflow = (const uint32_t *) ((const char *) h->h_scalars + 32);
+
+    for (int attempt = 0; attempt < 12; attempt++) {
+        if ((rc = ensure(h, h->slots, sizeof(SmMsg) * (size_t) nc * h->slot_cap))) return rc;
+        CU(h, cudaMemsetAsync(d_overflow, 0, 4, h->s_compute));
+        SmArgs a{};
+        a.tab = h->d_tab;
+        a.edges = (const u64 *) h->edges.p;
+        a.n_edges = h->n_edges;
+        a.base_bit = h->base_bit;
+        a.out_lo = h->out_lo; a.out_hi = h->out_hi;
+        a.spb = h->spb; a.dec = h->total_dec;
+        a.first_buffer = h->first_buffer;
+        a.chunk_buffers = h->chunk_buffers;
+        a.n_chunks = nc;
+        a.entry0 = entry0;
+        a.ran_with = (SmCarry *) h->chunk_ran.p;
+        a.slots = (SmMsg *) h->slots.p;
+        a.slot_cap = h->slot_cap;
+        a.slot_count = (uint32_t *) h->slot_count.p;
+        a.n_ran = d_nran;
+        a.overflow = d_overflow;
+
+        int cur = 0;
+        rounds = 0;
+        const unsigned grid = (nc + 31) / 32;
+        for (;;) {
+            // a short burst of rounds, then one look at the last round's re-run counter
+            const uint32_t burst = (rounds == 0) ? 3 : 2;
+            CU(h, cudaMemsetAsync(d_nran, 0, 128, h->s_compute));
+            for (uint32_t r = 0; r < burst; r++) {
+                a.round = rounds;
+                a.counter_idx = r;
+                a.exit_prev = (const SmCarry *) h->chunk_exit[cur].p;
+                a.exit_cur = (SmCarry *) h->chunk_exit[cur ^ 1].p;
+                sm_round_kernel<<<grid, 32, 0, h->s_compute>>>(a);
+                h->launches++;
+                CU(h, cudaGetLastError());
+                cur ^= 1;
+                rounds++;
+            }
+            CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
+            CU(h, cudaStreamSynchronize(h->s_compute));
+            if (h_nran[burst - 1] == 0) break;          // a round that re-ran nothing: fixed point
+            if (rounds > nc + 8) return fail(h, OOKD_ERR_STATE, "state machine stitch did not converge");
+        }
+        h->exit_idx = cur;
+        if (*h_overflow != 0) {
+            h->slot_cap *= 4;
+            continue;
+        }
+        // gather
+        CU(h, cudaMemcpyAsync(h->slot_off.p, h->slot_count.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice,
+                              h->s_compute));
+        scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
+        h->launches++;
+        CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaStreamSynchronize(h->s_compute));
+        const u64 n_msgs = ((const u64 *) h->h_scalars)[1];
+        if (n_msgs) {
+            if ((rc = ensure(h, h->msgs_dev, sizeof(SmMsg) * n_msgs))) return rc;
+            sm_gather_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(
+                (const SmMsg *) h->slots.p, h->slot_cap, (const uint32_t *) h->slot_count.p,
+                (const uint32_t *) h->slot_off.p, nc, (SmMsg *) h->msgs_dev.p);
+            h->launches++;
+            h->h_msgs_raw.resize(n_msgs);
+            CU(h, cudaMemcpyAsync(h->h_msgs_raw.data(), h->msgs_dev.p, sizeof(SmMsg) * n_msgs,
+                                  cudaMemcpyDeviceToHost, h->s_compute));
+        }
+        SmCarry last{};
+        CU(h, cudaMemcpyAsync(&last, (SmCarry *) h->chunk_exit[cur].p + (nc - 1), sizeof(SmCarry),
+                              cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaStreamSynchronize(h->s_compute));
+        h->h_msgs.resize(n_msgs);
+        for (u64 i = 0; i < n_msgs; i++) {
+            const SmMsg &m = h->h_msgs_raw[i];
+            ookd_msg &o = h->h_msgs[i];
+            memset(&o, 0, sizeof(o));
+            o.out_sample = m.out_sample;
+            o.buffer_idx = ((m.out_sample + 1) * (u64) h->total_dec - 1) / h->spb;
+            o.num_bits = m.num_bits;
+            const uint32_t nbytes = (h->smc.max_bits + 7) / 8;
+            memcpy(o.data, m.data, nbytes);
+        }
+        if (exit_) carry_from_dev(last, *exit_);
+        if (res) {
+            res->n_msgs = n_msgs;
+            res->msgs = n_msgs ? h->h_msgs.data() : nullptr;
+            res->sm_rounds = rounds;
+        }
+        return OOKD_OK;
+    }
+    return fail(h, OOKD_ERR_OVERFLOW, "message slots overflowed after retries");
+}
+
+}  // namespace
+
+// =======================================================================================
+extern "C" {
+
+int ookd_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *ookd_gpu_strerror(int status)
+{
+    switch (status) {
+        case OOKD_OK: return "ok";
+        case OOKD_ERR_ARG: return "invalid argument";
+        case OOKD_ERR_CUDA: return "CUDA error / no usable sm_100 device";
+        case OOKD_ERR_NOMEM: return "out of memory";
+        case OOKD_ERR_STATE: return "invalid state for this call";
+        case OOKD_ERR_OVERFLOW: return "internal capacity exceeded";
+        default: return "unknown error";
+    }
+}
+
+const char *ookd_gpu_last_error(const ookd_gpu *h)
+{
+    return h ? h->err : "null handle";
+}
+
+void ookd_gpu_destroy(ookd_gpu *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->s_compute) cudaStreamSynchronize(h->s_compute);
+    if (h->s_copy) cudaStreamSynchronize(h->s_copy);
+    for (auto &st : h->stages) if (st.d_taps) cudaFree(st.d_taps);
+    if (h->d_tab) cudaFree(h->d_tab);
+    DevBuf *all[] = {&h->in, &h->bits, &h->inter[0], &h->inter[1], &h->block_counts, &h->edges, &h->scalars,
+                     &h->chunk_exit[0], &h->chunk_exit[1], &h->chunk_ran, &h->slots, &h->slot_count,
+                     &h->slot_off, &h->msgs_dev};
+    for (DevBuf *b : all) release(*b);
+    if (h->h_scalars) cudaFreeHost(h->h_scalars);
+    for (auto e : h->ev_piece) cudaEventDestroy(e);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->ev_f0) cudaEventDestroy(h->ev_f0);
+    if (h->ev_f1) cudaEventDestroy(h->ev_f1);
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    ookd_sm_compiled_free(&h->smc);
+    delete h;
+}
+
+int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
+{
+    if (!out || !cfg || cfg->samples_per_buffer == 0) return OOKD_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return OOKD_ERR_CUDA;
+    int dev = cfg->device_id;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) return OOKD_ERR_CUDA;
+    }
+    if (dev >= ndev) return OOKD_ERR_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return OOKD_ERR_CUDA;
+    if (prop.major != 10) return OOKD_ERR_CUDA;      // kernels are built for sm_100a only
+
+    ookd_gpu *h = new ookd_gpu();
+    h->device = dev;
+    h->threshold = cfg->threshold;
+    h->pstar = ookd_power_threshold(cfg->threshold);
+    h->spb = cfg->samples_per_buffer;
+    h->flags = cfg->flags;
+    h->chunk_buffers = cfg->sm_chunk_buffers ? cfg->sm_chunk_buffers : 64;
+
+#define CREATE_FAIL(code)                                                                        \
+    do { ookd_gpu_destroy(h); return (code); } while (0)
+#define CUC(call)                                                                                \
+    do { if ((call) != cudaSuccess) { CREATE_FAIL(OOKD_ERR_CUDA); } } while (0)
+
+    CUC(cudaSetDevice(dev));
+    CUC(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&h->ev_t0));
+    CUC(cudaEventCreate(&h->ev_t1));
+    CUC(cudaEventCreate(&h->ev_f0));
+    CUC(cudaEventCreate(&h->ev_f1));
+    CUC(cudaHostAlloc(&h->h_scalars, 256, cudaHostAllocDefault));
+    if (ensure(h, h->scalars, 256) != OOKD_OK) CREATE_FAIL(OOKD_ERR_NOMEM);
+
+    // ---- filter ----
+    const ookd_filter_desc *f = cfg->filter;
+    if (f && f->num_stages > 0) {
+        if (f->num_stages > OOKD_MAX_STAGES) CREATE_FAIL(OOKD_ERR_ARG);
+        for (uint32_t s = 0; s < f->num_stages; s++) {
+            if (f->decimation[s] == 0 || f->num_taps[s] == 0 || f->num_taps[s] > OOKD_MAX_TAPS || !f->taps[s]) {
+                CREATE_FAIL(OOKD_ERR_ARG);
+            }
+            Stage st;
+            st.T = f->num_taps[s];
+            st.D = f->decimation[s];
+            st.taps.assign(f->taps[s], f->taps[s] + st.T);
+            h->stages.push_back(st);
+        }
+    } else {
+        // no filter: thresholds are taken on the converted samples themselves
+        // (src/ookiedokie.c:261-264).  0 + 1.0f*x == x exactly, so a unity tap is identical.
+        Stage st;
+        st.T = 1; st.D = 1; st.taps.assign(1, 1.0f);
+        h->stages.push_back(st);
+    }
+    u64 dec = 1, halo = 0;
+    for (auto &st : h->stages) {
+        halo += (u64) (st.T - 1) * dec;       // H = (T1-1) + (T2-1)*D1 + ...
+        dec *= st.D;
+        if (dec > 0xFFFFFFFFull) CREATE_FAIL(OOKD_ERR_ARG);
+        CUC(cudaMalloc(&st.d_taps, st.T * sizeof(float)));
+        CUC(cudaMemcpy(st.d_taps, st.taps.data(), st.T * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    h->total_dec = (uint32_t) dec;
+    h->halo_fir = (uint32_t) halo;
+    // one extra byte of decisions in front of a shard gives the edge detector its predecessor
+    h->halo = (uint32_t) ((halo + 8 * dec + 3) & ~3ull);
+
+    h->path = FIR_GENERIC;
+    if (!(h->flags & OOKD_FLAG_FORCE_GENERIC)) {
+        if (h->stages.size() == 1 && h->stages[0].T == 32 && h->stages[0].D == 1) {
+            h->path = FIR_TILED_1STAGE_32;
+        }
+    }
+
+    // ---- state machine ----
+    if (cfg->sm) {
+        if (cfg->sm->num_states > OOKD_SM_MAX_STATES || cfg->sm->num_triggers > OOKD_SM_MAX_TRIGGERS) {
+            CREATE_FAIL(OOKD_ERR_ARG);
+        }
+        const int rc = ookd_sm_compile(cfg->sm, &h->smc);
+        if (rc != OOKD_OK) CREATE_FAIL(rc);
+        SmTable *tab = new SmTable();
+        memset(tab, 0, sizeof(*tab));
+        tab->num_states = h->smc.num_states;
+        tab->num_triggers = h->smc.num_triggers;
+        tab->max_bits = h->smc.max_bits;
+        tab->k_sat = h->smc.k_sat;
+        memcpy(tab->states, h->smc.states, sizeof(ookd_sm_state_k) * h->smc.num_states);
+        memcpy(tab->triggers, h->smc.triggers, sizeof(ookd_sm_trigger_k) * h->smc.num_triggers);
+        cudaError_t e = cudaMalloc(&h->d_tab, sizeof(SmTable));
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_tab, tab, sizeof(SmTable), cudaMemcpyHostToDevice);
+        delete tab;
+        if (e != cudaSuccess) CREATE_FAIL(OOKD_ERR_CUDA);
+        h->have_sm = true;
+    }
+#undef CUC
+#undef CREATE_FAIL
+    *out = h;
+    return OOKD_OK;
+}
+
+uint32_t ookd_gpu_halo(const ookd_gpu *h) { return h ? h->halo : 0; }
+uint32_t ookd_gpu_total_decimation(const ookd_gpu *h) { return h ? h->total_dec : 0; }
+
+void ookd_gpu_initial_carry(const ookd_gpu *h, struct ookd_sm_carry *c)
+{
+    (void) h;
+    memset(c, 0, sizeof(*c));
+}
+
+int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, uint64_t first_sample,
+                          uint64_t n_samples, int last, const struct ookd_sm_carry *entry,
+                          struct ookd_sm_carry *exit_, struct ookd_gpu_result *res)
+{
+    if (!h) return OOKD_ERR_ARG;
+    if (!iq && n_samples) return fail(h, OOKD_ERR_ARG, "null input");
+    CU(h, cudaSetDevice(h->device));
+    h->have_last = false;
+    h->h_edges_valid = false;
+    h->launches = 0;
+    if (res) memset(res, 0, sizeof(*res));
+
+    const u64 D = h->total_dec, spb = h->spb;
+    const u64 align = spb / gcd64(spb, D) * D;                 // lcm(spb, D)
+    if (first_sample % align) return fail(h, OOKD_ERR_ARG, "first_sample must be a multiple of lcm(spb, decimation)");
+    if (!last && (n_samples % align)) return fail(h, OOKD_ERR_ARG, "non-final shard length must be a multiple of lcm(spb, decimation)");
+
+    // EOF semantics of sdr_bladerf_file_rx: a short final read is zero padded to a full buffer
+    const u64 n_eff = last ? (n_samples + spb - 1) / spb * spb : n_samples;
+    const u64 halo_avail = first_sample < h->halo ? first_sample : h->halo;
+    const i64 in_base = (i64) (first_sample - halo_avail);
+    const i64 in_valid_end = (i64) (first_sample + n_samples);
+    h->out_lo = (i64) (first_sample / D);
+    h->out_hi = (i64) ((first_sample + n_eff) / D);
+    h->pre = (h->out_lo > 0) ? 8 : 0;
+    h->bit_base = h->out_lo - h->pre;
+    h->first_buffer = first_sample / spb;
+    h->n_buffers = n_eff / spb;
+    h->n_in = n_eff;
+    const u64 n_bits = (u64) (h->out_hi - h->bit_base);
+    const u64 n_out = (u64) (h->out_hi - h->out_lo);
+    h->n_chunks = (uint32_t) ((h->n_buffers + h->chunk_buffers - 1) / h->chunk_buffers);
+    if (h->n_chunks == 0) h->n_chunks = 1;
+
+    int rc;
+    if ((rc = ensure(h, h->bits, (n_bits / 8 + 64 + 8) & ~7ull))) return rc;
+
+    CU(h, cudaEventRecord(h->ev_t0, h->s_compute));
+
+    // ---- input staging + FIR/threshold ----
+    const u64 n_have = halo_avail + n_samples;                 // samples present at iq
+    const uint32_t *d_in = (const uint32_t *) iq;
+    constexpr u64 TILE = 256 * 8;                              // outputs per tile of the tiled path
+    CU(h, cudaEventRecord(h->ev_f0, h->s_compute));
+    if (!iq_is_device_ptr) {
+        if ((rc = ensure(h, h->in, n_have * 4 + 16))) return rc;
+        d_in = (const uint32_t *) h->in.p;
+        const u64 piece = 16ull << 20;                         // 16 Mi samples = 64 MiB per copy
+        const u64 n_pieces = n_have ? (n_have + piece - 1) / piece : 0;
+        while (h->ev_piece.size() < n_pieces) {
+            cudaEvent_t e;
+            CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            h->ev_piece.push_back(e);
+        }
+        i64 o_done = h->bit_base;
+        for (u64 p = 0; p < n_pieces; p++) {
+            const u64 s0 = p * piece, s1 = (s0 + piece < n_have) ? s0 + piece : n_have;
+            CU(h, cudaMemcpyAsync((uint32_t *) h->in.p + s0, (const uint32_t *) iq + s0, (s1 - s0) * 4,
+                                  cudaMemcpyHostToDevice, h->s_copy));
+            CU(h, cudaEventRecord(h->ev_piece[p], h->s_copy));
+            if (h->path != FIR_GENERIC) {
+                CU(h, cudaStreamWaitEvent(h->s_compute, h->ev_piece[p], 0));
+                // outputs whose newest input has arrived, rounded down to whole tiles
+                i64 o_avail;
+                if (p + 1 == n_pieces) {
+                    o_avail = h->out_hi;
+                } else {
+                    const u64 g_end = (u64) in_base + s1;      // global samples present: [.., g_end)
+                    o_avail = (i64) (g_end / D);
+                    o_avail = h->bit_base + (i64) (((u64) (o_avail - h->bit_base)) / TILE * TILE);
+                    if (o_avail > h->out_hi) o_avail = h->out_hi;
+                }
+                if (o_avail > o_done) {
+                    if ((rc = launch_fir(h, d_in, in_base, in_valid_end, o_done, o_avail))) return rc;
+                    o_done = o_avail;
+                }
+            }
+        }
+        if (n_pieces == 0 && h->path != FIR_GENERIC) {
+            if ((rc = launch_fir(h, d_in, in_base, in_valid_end, h->bit_base, h->out_hi))) return rc;
+        }
+        if (h->path == FIR_GENERIC) {
+            if (n_pieces) CU(h, cudaStreamWaitEvent(h->s_compute, h->ev_piece[n_pieces - 1], 0));
+            if ((rc = run_generic_chain(h, d_in, true, in_base, in_valid_end, h->bit_base, h->out_hi, nullptr,
+                                        (uint32_t *) h->bits.p, h->bit_base))) return rc;
+        }
+    } else {
+        if (h->path != FIR_GENERIC) {
+            if ((rc = launch_fir(h, d_in, in_base, in_valid_end, h->bit_base, h->out_hi))) return rc;
+        } else {
+            if ((rc = run_generic_chain(h, d_in, true, in_base, in_valid_end, h->bit_base, h->out_hi, nullptr,
+                                        (uint32_t *) h->bits.p, h->bit_base))) return rc;
+        }
+    }
+    CU(h, cudaEventRecord(h->ev_f1, h->s_compute));
+
+    // ---- edges ----
+    h->n_edges = 0;
+    h->base_bit = 0;
+    if (n_bits > 0) {
+        EdgeArgs ea{};
+        ea.words = (const u64 *) h->bits.p;
+        ea.bit_base = h->bit_base;
+        ea.start_bit = h->pre;
+        ea.n_bits = (i64) n_bits;
+        const u64 n_words = (n_bits + 63) / 64;
+        const unsigned eg = (unsigned) ((n_words + EDGE_WPB - 1) / EDGE_WPB);
+        if ((rc = ensure(h, h->block_counts, sizeof(uint32_t) * (eg + 1)))) return rc;
+        ea.block_counts = (uint32_t *) h->block_counts.p;
+        edge_count_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(ea);
+        scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>(ea.block_counts, eg, (u64 *) h->scalars.p);
+        h->launches += 2;
+        CU(h, cudaGetLastError());
+        // scalars[0] = total edges; also fetch the first word of decisions for first_bit/base_bit
+        CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 8, h->bits.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaStreamSynchronize(h->s_compute));
+        h->n_edges = ((const u64 *) h->h_scalars)[0];
+        const u64 w0 = ((const u64 *) h->h_scalars)[1];
+        // decision preceding the shard (or decision 0 itself at the capture start)
+        h->base_bit = (uint32_t) ((w0 >> (h->pre ? h->pre - 1 : 0)) & 1);
+        if (res) res->first_bit = (uint32_t) ((w0 >> h->pre) & 1);
+        if ((rc = ensure(h, h->edges, sizeof(u64) * (h->n_edges + 2)))) return rc;
+        if (h->n_edges) {
+            ea.edges = (u64 *) h->edges.p;
+            edge_write_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(ea);
+            h->launches++;
+            CU(h, cudaGetLastError());
+        }
+    } else {
+        if ((rc = ensure(h, h->edges, 16))) return rc;
+    }
+
+    // ---- state machine ----
+    SmCarry e0{};
+    if (entry) carry_to_dev(*entry, e0);
+    h->have_last = true;
+    rc = run_state_machine(h, e0, exit_, res);
+    if (rc) return rc;
+
+    CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
+    CU(h, cudaEventSynchronize(h->ev_t1));
+    if (res) {
+        res->n_in = n_eff;
+        res->n_out = n_out;
+        res->n_buffers = h->n_buffers;
+        res->n_edges = h->n_edges;
+        res->gpu_launches = h->launches;
+        cudaEventElapsedTime(&res->kernel_ms, h->ev_t0, h->ev_t1);
+        cudaEventElapsedTime(&res->fir_ms, h->ev_f0, h->ev_f1);
+    }
+    return OOKD_OK;
+}
+
+int ookd_gpu_decode(ookd_gpu *h, const int16_t *iq, uint64_t n_samples, int iq_is_device_ptr,
+                    struct ookd_gpu_result *res)
+{
+    return ookd_gpu_decode_shard(h, iq, iq_is_device_ptr, 0, n_samples, 1, nullptr, nullptr, res);
+}
+
+int ookd_gpu_resolve(ookd_gpu *h, const struct ookd_sm_carry *entry, struct ookd_sm_carry *exit_,
+                     struct ookd_gpu_result *res)
+{
+    if (!h || !entry) return OOKD_ERR_ARG;
+    if (!h->have_last) return fail(h, OOKD_ERR_STATE, "resolve without a preceding decode");
+    CU(h, cudaSetDevice(h->device));
+    SmCarry e0{};
+    carry_to_dev(*entry, e0);
+    h->launches = 0;
+    CU(h, cudaEventRecord(h->ev_t0, h->s_compute));
+    const int rc = run_state_machine(h, e0, exit_, res);
+    if (rc) return rc;
+    CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
+    CU(h, cudaEventSynchronize(h->ev_t1));
+    if (res) {
+        res->n_in = h->n_in;
+        res->n_out = (u64) (h->out_hi - h->out_lo);
+        res->n_buffers = h->n_buffers;
+        res->n_edges = h->n_edges;
+        res->gpu_launches = h->launches;
+        cudaEventElapsedTime(&res->kernel_ms, h->ev_t0, h->ev_t1);
+    }
+    return OOKD_OK;
+}
+
+int ookd_gpu_edges(ookd_gpu *h, const uint64_t **edges, uint64_t *n_edges, uint32_t *first_bit)
+{
+    if (!h || !edges || !n_edges) return OOKD_ERR_ARG;
+    if (!h->have_last) return fail(h, OOKD_ERR_STATE, "no decode yet");
+    CU(h, cudaSetDevice(h->device));
+    if (!h->h_edges_valid) {
+        h->h_edges.resize(h->n_edges);
+        if (h->n_edges) {
+            CU(h, cudaMemcpyAsync(h->h_edges.data(), h->edges.p, sizeof(u64) * h->n_edges, cudaMemcpyDeviceToHost,
+                                  h->s_compute));
+            CU(h, cudaStreamSynchronize(h->s_compute));
+        }
+        h->h_edges_valid = true;
+    }
+    *edges = (const uint64_t *) h->h_edges.data();
+    *n_edges = h->n_edges;
+    if (first_bit) {
+        // decision of the shard's first output
+        u64 w0 = 0;
+        if (h->out_hi > h->bit_base) {
+            CU(h, cudaMemcpy(&w0, h->bits.p, 8, cudaMemcpyDeviceToHost));
+        }
+        *first_bit = (uint32_t) ((w0 >> h->pre) & 1);
+    }
+    return OOKD_OK;
+}
+
+int ookd_gpu_bits(ookd_gpu *h, uint8_t *bits_out, uint64_t max_out, uint64_t *n_out)
+{
+    if (!h || !n_out) return OOKD_ERR_ARG;
+    if (!h->have_last) return fail(h, OOKD_ERR_STATE, "no decode yet");
+    CU(h, cudaSetDevice(h->device));
+    const u64 n = (u64) (h->out_hi - h->out_lo);
+    *n_out = n;
+    if (!bits_out) return OOKD_OK;
+    const u64 n_bits = (u64) (h->out_hi - h->bit_base);
+    std::vector<uint8_t> packed((n_bits + 7) / 8);
+    if (!packed.empty()) {
+        CU(h, cudaMemcpy(packed.data(), h->bits.p, packed.size(), cudaMemcpyDeviceToHost));
+    }
+    const u64 lim = n < max_out ? n : max_out;
+    for (u64 i = 0; i < lim; i++) {
+        const u64 b = i + h->pre;
+        bits_out[i] = (packed[b >> 3] >> (b & 7)) & 1;
+    }
+    return OOKD_OK;
+}
+
+static int filtered_common(ookd_gpu *h, const void *in, bool in_i16, bool in_dev, uint64_t n_samples, bool pad_spb,
+                           float *out_iq_host, uint64_t max_out, uint64_t *n_out)
+{
+    if (!h || !n_out) return OOKD_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    const u64 D = h->total_dec;
+    const u64 n_eff = pad_spb ? (n_samples + h->spb - 1) / h->spb * h->spb : n_samples;
+    const u64 n = n_eff / D;
+    *n_out = n;
+    if (!out_iq_host || n == 0) return OOKD_OK;
+    const u64 lim = n < max_out ? n : max_out;
+    int rc;
+    DevBuf tmp_in, tmp_out;
+    const void *d_in = in;
+    const size_t esz = in_i16 ? 4 : 8;
+    if (!in_dev) {
+        if ((rc = ensure(h, tmp_in, n_samples * esz + 16))) return rc;
+        if (n_samples) {
+            CU(h, cudaMemcpyAsync(tmp_in.p, in, n_samples * esz, cudaMemcpyHostToDevice, h->s_compute));
+        }
+        d_in = tmp_in.p;
+    }
+    rc = ensure(h, tmp_out, lim * sizeof(float2));
+    if (!rc) rc = run_generic_chain(h, d_in, in_i16, 0, (i64) n_samples, 0, (i64) lim, (float2 *) tmp_out.p, nullptr, 0);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(out_iq_host, tmp_out.p, lim * sizeof(float2), cudaMemcpyDeviceToHost, h->s_compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_compute);
+        if (e != cudaSuccess) rc = fail(h, OOKD_ERR_CUDA, "filtered: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(h->s_compute);
+    release(tmp_in);
+    release(tmp_out);
+    return rc;
+}
+
+int ookd_gpu_filtered(ookd_gpu *h, const int16_t *iq, uint64_t n_samples, int iq_is_device_ptr, float *out_iq_host,
+                      uint64_t max_out, uint64_t *n_out)
+{
+    return filtered_common(h, iq, true, iq_is_device_ptr != 0, n_samples, true, out_iq_host, max_out, n_out);
+}
+
+int ookd_gpu_filter_cf(ookd_gpu *h, const float *in_iq_host, uint64_t n_samples, float *out_iq_host, uint64_t max_out,
+                       uint64_t *n_out)
+{
+    return filtered_common(h, in_iq_host, false, false, n_samples, false, out_iq_host, max_out, n_out);
+}
+
+int ookd_gpu_synth(int32_t device_id, int16_t *dst, int dst_is_device_ptr, uint64_t first_sample, uint64_t n_samples,
+                   const uint64_t *toggles_host, uint64_t n_toggles, int32_t i_on, int32_t q_on, int32_t noise_scale,
+                   uint64_t seed)
+{
+    if (!dst && n_samples) return OOKD_ERR_ARG;
+    if (device_id >= 0 && cudaSetDevice(device_id) != cudaSuccess) return OOKD_ERR_CUDA;
+    if (n_samples == 0) return OOKD_OK;
+    u64 *d_tog = nullptr;
+    uint32_t *d_dst = (uint32_t *) dst;
+    int rc = OOKD_OK;
+    if (cudaMalloc(&d_tog, sizeof(u64) * (n_toggles + 1)) != cudaSuccess) return OOKD_ERR_NOMEM;
+    if (n_toggles && cudaMemcpy(d_tog, toggles_host, sizeof(u64) * n_toggles, cudaMemcpyHostToDevice) != cudaSuccess) {
+        rc = OOKD_ERR_CUDA;
+    }
+    if (!rc && !dst_is_device_ptr) {
+        if (cudaMalloc(&d_dst, n_samples * 4) != cudaSuccess) rc = OOKD_ERR_NOMEM;
+    }
+    if (!rc) {
+        const u64 threads = (n_samples + SYNTH_SPT - 1) / SYNTH_SPT;
+        const unsigned grid = (unsigned) ((threads + 255) / 256);
+        synth_kernel<<<grid, 256>>>(d_dst, first_sample, n_samples, d_tog, n_toggles, i_on, q_on, noise_scale,
+                                    synth_mix64(seed));
+        if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) rc = OOKD_ERR_CUDA;
+    }
+    if (!rc && !dst_is_device_ptr) {
+        if (cudaMemcpy(dst, d_dst, n_samples * 4, cudaMemcpyDeviceToHost) != cudaSuccess) rc = OOKD_ERR_CUDA;
+    }
+    if (!dst_is_device_ptr && d_dst) cudaFree(d_dst);
+    cudaFree(d_tog);
+    return rc;
+}
+
+void *ookd_gpu_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void ookd_gpu_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+void *ookd_gpu_dev_alloc(int32_t device_id, size_t bytes)
+{
+    void *p = nullptr;
+    if (device_id >= 0 && cudaSetDevice(device_id) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void ookd_gpu_dev_free(int32_t device_id, void *p)
+{
+    if (device_id >= 0) cudaSetDevice(device_id);
+    if (p) cudaFree(p);
+}
+
+int ookd_gpu_memcpy_h2d(int32_t device_id, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (device_id >= 0 && cudaSetDevice(device_id) != cudaSuccess) return OOKD_ERR_CUDA;
+    return cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? OOKD_OK : OOKD_ERR_CUDA;
+}
+
+int ookd_gpu_memcpy_d2h(int32_t device_id, void *dst_host, const void *src_dev, size_t bytes)
+{
+    if (device_id >= 0 && cudaSetDevice(device_id) != cudaSuccess) return OOKD_ERR_CUDA;
+    return cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? OOKD_OK : OOKD_ERR_CUDA;
+}
+
+}  // extern "C"

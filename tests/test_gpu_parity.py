@@ -1,0 +1,91 @@
+"""GPU parity: every result of the C ABI against the CPU oracle on identical inputs (bit-exact)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from ookiedokie_b200 import binding as B
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+FILTERS = ["fs32_fs4", "fs128_fs16_dec4", "fs64_fs8", "unity1", "unity16", None]
+
+
+def _gpu(filt, device=None, **kw):
+    stages = O.load_filter(filt) if filt else None
+    sm = util.sm_spec(device, stages) if device else None
+    return B.Gpu(filter_stages=stages, sm=sm, **kw), stages
+
+
+def test_synth_matches_oracle():
+    dev = O.load_device("p3l-nexa2012")
+    msgs = [O.message_bytes(dev, util.nexa_fields(i)) for i in range(2)]
+    tog, total = O.toggles_from_messages(dev, msgs, util.FS, 12000)
+    for scale, seed in [(0, 0), (O.noise_scale_for_sigma(0.02), 7), (O.noise_scale_for_sigma(0.3), 0xC0FFEE)]:
+        ref = O.synth(total, tog, 1376, 1375, scale, seed)
+        got = B.synth(total, tog, 1376, 1375, scale, seed)
+        assert np.array_equal(ref, got)
+    # offset window
+    ref = O.synth(5000, tog, 1945, 0, O.noise_scale_for_sigma(0.05), 3, first_sample=11000)
+    got = B.synth(5000, tog, 1945, 0, O.noise_scale_for_sigma(0.05), 3, first_sample=11000)
+    assert np.array_equal(ref, got)
+
+
+@pytest.mark.parametrize("filt", FILTERS)
+def test_filtered_samples_bit_exact(filt):
+    rng = np.random.default_rng(5)
+    iq = rng.integers(-2048, 2048, size=(70001, 2), dtype=np.int16)
+    iq[:100] = 0
+    iq[50] = (2047, -2048)          # impulse-ish start (gen_samples.m: impulse at sample 50)
+    g, stages = _gpu(filt, samples_per_buffer=1024)
+    got = g.filtered(iq)
+    ref = O.rx(iq, stages, None, samples_per_buffer=1024, want_filtered=True)["filtered"]
+    assert got.shape == ref.shape
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))     # bit-exact, stronger than 1e-5
+
+
+@pytest.mark.parametrize("filt", ["fs32_fs4", "fs128_fs16_dec4", "unity16"])
+def test_filter_cf_matches_fir_semantics(filt):
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((5000, 2)).astype(np.float32)
+    g, stages = _gpu(filt)
+    got = g.filter_cf(x)
+    ref = O.Fir(stages).run(x)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+CASES = [
+    # device, filter, n_msgs, sigma, amp, spb, flags
+    ("p3l-nexa2012", "fs32_fs4", 3, 0.0, 0.95, 8192, 0),
+    ("p3l-nexa2012", "fs32_fs4", 3, 0.02, 0.95, 8192, 0),
+    ("p3l-nexa2012", "fs32_fs4", 3, 0.02, 0.95, 8192, B.FLAG_FORCE_GENERIC),
+    ("p3l-nexa2012", "fs32_fs4", 4, 0.03, 0.95, 8192, 0),
+    ("p3l-nexa2012", "fs32_fs4", 3, 0.02, 0.95, 1024, 0),
+    ("p3l-nexa2012", "fs32_fs4", 3, 0.02, 0.95, 65536, 0),
+    ("p3l-nexa2012", "fs32_fs4", 2, 0.02, 0.95, 5000, 0),
+    ("p3l-nexa2012", "fs128_fs16_dec4", 3, 0.02, 0.95, 8192, 0),
+    ("p3l-nexa2012", None, 2, 0.0, 0.95, 8192, 0),
+    ("p3l-nexa2012", "fs64_fs8", 3, 0.05, 0.95, 8192, 0),
+    ("unknown-remote1", "fs128_fs16_dec4", 10, 0.10, 0.30, 8192, 0),
+    ("unknown-remote1", "fs128_fs16_dec4", 6, 0.05, 0.30, 8192, 0),
+    ("unknown-remote1", "fs32_fs4", 4, 0.02, 0.5, 4096, 0),
+    ("unknown-remote1", "fs128_fs16_dec4", 4, 0.05, 0.30, 1001, 0),     # spb not a multiple of the decimation
+]
+
+
+@pytest.mark.parametrize("devname,filt,n_msgs,sigma,amp,spb,flags", CASES)
+def test_decode_matches_oracle(devname, filt, n_msgs, sigma, amp, spb, flags):
+    dev = O.load_device(devname)
+    fields = util.nexa_fields if "nexa" in devname else util.remote_fields
+    iq, msgs, _ = util.capture(dev, n_msgs, sigma=sigma, amplitude=amp, phase=0.7, seed=n_msgs * 31 + spb, fields=fields)
+    g, stages = _gpu(filt, dev, samples_per_buffer=spb, flags=flags, sm_chunk_buffers=7)
+    ref = O.rx(iq, stages, dev, samples_per_buffer=spb, want_bits=True)
+    got = g.decode(iq)
+    assert got["n_out"] == ref["n_out"] and got["n_buffers"] == ref["n_buffers"]
+    assert np.array_equal(g.bits(), ref["bits"])
+    fb, edges = g.edges()
+    assert fb == ref["first_bit"]
+    assert np.array_equal(edges, ref["edges"])
+    assert got["msgs"] == ref["msgs"]
+    if sigma <= 0.02 and amp > 0.9:
+        assert [m[3] for m in got["msgs"]] == msgs      # clean enough: every transmitted message decodes
