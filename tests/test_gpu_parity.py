@@ -4,7 +4,7 @@ import pytest
 
 from oracle import oracle as O
 from ookiedokie_b200 import binding as B
-from tests import util
+import ookd_testutil as util
 
 pytestmark = pytest.mark.gpu
 
