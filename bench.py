@@ -1,0 +1,374 @@
+#!/usr/bin/env python3
+"""bench.py -- IQ Msamples/s decoded (SC16Q11 -> OOK messages) on 1..8 B200, % of HBM roofline.
+
+Workload (BASELINE.json configs[1], named in config.workload): p3l-nexa2012 bursts through
+filters/fs32_fs4.json on a 4 GiB (2^30 samples) synthetic SC16Q11 capture per GPU (amplitude 0.95,
+carrier phase 0.7 rad, integer AWGN sigma 0.02, per-message field variation, seed 0x00C0FFEE).  With
+N > 1 the ranks decode consecutive 4 GiB time shards of ONE continuous N*4 GiB capture (FIR halo
+reads + state-machine carry stitch, ookiedokie_b200/shard.py): weak scaling, no collective on the
+data path; only the 48-byte carries and the message lists cross ranks.
+
+    value : whole-job Msamples/s with the shard already resident in HBM
+    e2e   : same through the C ABI with the shard in pinned HOST memory (H2D inside the timed region,
+            message list read back every step)
+    --impl reference : the unmodified reference binary (oracle/_ref/ookiedokie, single threaded as the
+            reference is) on a bounded prefix of the same capture, on the box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEVICE_NAME = "p3l-nexa2012"
+FILTER_NAME = "fs32_fs4"
+FS = 3000000
+SPB = 8192
+THR = 0.1
+AMP, PHASE, SIGMA, SEED = 0.95, 0.7, 0.02, 0x00C0FFEE
+LEAD = 12000
+METRIC = "IQ Msamples/s decoded (SC16Q11->OOK msgs)"
+UNIT = "Msamples/s"
+
+
+def workload_name(samples):
+    return (f"{DEVICE_NAME} + {FILTER_NAME}, {samples * 4 / 2**30:.3g} GiB synthetic SC16Q11 capture per GPU "
+            f"(amp {AMP}, sigma {SIGMA}, thr {THR}, spb {SPB}, fs {FS})")
+
+
+def message_params(i):
+    return {"Channel": str(1 + i % 3), "Temperature (C)": f"{-20.0 + 0.1 * ((i * 37) % 900):.1f}"}
+
+
+def build_toggles(dev, total_samples):
+    """Messages tiled back to back until they cover total_samples.  -> (toggles, n_messages)."""
+    import numpy as np
+    est = total_samples // 380000 + 8
+    msgs = [dev.message(message_params(i)) for i in range(est)]
+    tog, total = dev.toggles(msgs, LEAD)
+    while total < total_samples:
+        est *= 2
+        msgs = [dev.message(message_params(i)) for i in range(est)]
+        tog, total = dev.toggles(msgs, LEAD)
+    return np.ascontiguousarray(tog), len(msgs)
+
+
+def on_level():
+    import math
+    return int(round(AMP * 2048.0 * math.cos(PHASE))), int(round(AMP * 2048.0 * math.sin(PHASE)))
+
+
+def noise_scale():
+    ih4_std = (4.0 * (65536.0 ** 2 - 1.0) / 12.0) ** 0.5       # std of the sum of four 16-bit uniforms
+    return int(round(SIGMA * 2048.0 / ih4_std * (1 << 24)))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        busy = [c for c in sm if c > 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    return None
+
+
+def reference_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "ookiedokie")
+    return p if os.path.exists(p) else None
+
+
+def run_reference_cpu(iq_prefix, repeats=1):
+    """Times the unmodified reference binary on a capture prefix.  -> (Msamples/s, n_rows)."""
+    ref = reference_binary()
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    with tempfile.TemporaryDirectory(dir=tmpdir) as td:
+        cap = os.path.join(td, "cap.sc16q11")
+        iq_prefix.tofile(cap)
+        n = iq_prefix.size // 2
+        best, rows = None, 0
+        env = dict(os.environ, OOKD_DATA_DIR=os.path.join(ROOT, "ookiedokie_b200", "data") + "/")
+        dev_path = os.path.join(ROOT, "ookiedokie_b200", "data", "devices", DEVICE_NAME + ".json")
+        filt_path = os.path.join(ROOT, "ookiedokie_b200", "data", "filters", FILTER_NAME + ".json")
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            out = subprocess.run([ref, "--rx", "bladerf_file", "-A", cap, "-d", dev_path, "-F", filt_path, "--rx-fmt",
+                                  "csv", "--samples-per-buffer", str(SPB), "-T", str(THR), "-s", str(FS)],
+                                 capture_output=True, text=True, env=env, check=True)
+            dt = time.perf_counter() - t0
+            rows = max(len(out.stdout.strip().splitlines()) - 1, 0)
+            best = dt if best is None else min(best, dt)
+    return n / best / 1e6, rows
+
+
+def impl_reference(args, rank, world):
+    if rank != 0:
+        return
+    import numpy as np
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic"}
+    if reference_binary() is None:
+        line.update({"unavailable": "oracle/_ref/ookiedokie not built (needs /root/reference at build time)"})
+        print(json.dumps(line))
+        return
+    from oracle import oracle as O
+    dev = O.load_device(DEVICE_NAME)
+    n = args.ref_samples
+    n_msgs = n // 380000 + 4
+    msgs = [O.message_bytes(dev, message_params(i)) for i in range(n_msgs)]
+    tog, _ = O.toggles_from_messages(dev, msgs, FS, LEAD)
+    i_on, q_on = on_level()
+    iq = O.synth(n, tog, i_on, q_on, noise_scale(), SEED)
+    for _ in range(args.warmup):
+        run_reference_cpu(iq)
+    vals = []
+    t0 = time.perf_counter()
+    rows = 0
+    for _ in range(args.steps):
+        v, rows = run_reference_cpu(iq)
+        vals.append(v)
+    total = time.perf_counter() - t0
+    value = statistics.mean(vals)
+    sample = f"first {n} samples ({n * 4 / 2**20:.0f} MiB) of the same synthetic capture, {rows} messages decoded"
+    line.update({"value": value, "ms_per_step": 1e3 * total / max(args.steps, 1),
+                 "config": {"workload": workload_name(args.samples), "sample": sample},
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
+                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--samples", type=int, default=1 << 30, help="samples per GPU (default 2^30 = 4 GiB)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-samples", type=int, default=1 << 27, help="prefix timed on the CPU baseline (N=1)")
+    ap.add_argument("--ref-samples", type=int, default=1 << 25, help="prefix per step of --impl reference")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--chunk-buffers", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        impl_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ookiedokie_b200 import binding as B
+    from ookiedokie_b200 import host as H
+    from ookiedokie_b200 import shard as S
+
+    if not torch.cuda.is_available() or B.device_count() == 0:
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the receive path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fir = H.Fir(FILTER_NAME)
+    dev = H.Device(DEVICE_NAME, FS // fir.total_decimation)
+    gpu = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
+                flags=args.flags, sm_chunk_buffers=args.chunk_buffers)
+    n = args.samples
+    halo = gpu.halo
+    first = rank * n
+    halo_avail = min(halo, first)
+    last = (rank == world - 1)
+    tog, n_tx_msgs = build_toggles(dev, world * n)
+    i_on, q_on = on_level()
+
+    # ---- shard resident in HBM (synthesised on the device; identical bytes to the CPU recipe) ----
+    d_iq = torch.empty(((halo_avail + n) * 2,), dtype=torch.int16, device="cuda")
+    B.synth(halo_avail + n, tog, i_on, q_on, noise_scale(), SEED, first_sample=first - halo_avail, device_id=local_rank,
+            device_ptr=d_iq.data_ptr())
+    torch.cuda.synchronize()
+
+    def one_step(iq_arg):
+        runner = S.GpuShardRunner(gpu, iq_arg, first, n, last)
+        res, exit_c, rounds = S.stitch(runner, rank, world)
+        msgs = S.gather_messages(res["msgs"], rank, world, dev.nbytes)
+        return res, msgs, runner
+
+    dev_arg = (d_iq.data_ptr(), halo_avail + n)
+    for _ in range(args.warmup):
+        one_step(dev_arg)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    launches = 0
+    fir_ms = 0.0
+    kernel_ms = 0.0
+    for _ in range(args.steps):
+        res, msgs, runner = one_step(dev_arg)
+        launches += runner.launches
+        fir_ms += runner.fir_ms
+        kernel_ms += runner.kernel_ms
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t = torch.tensor([dt, fir_ms, kernel_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt, fir_ms_max, kernel_ms_max = [float(x) for x in t.cpu()]
+    ms_per_step = 1e3 * dt / args.steps
+    value = world * n / (dt / args.steps) / 1e6
+    n_msgs = len(msgs) if msgs is not None else 0
+    n_edges = res["n_edges"]
+    sm_rounds = res["sm_rounds"]
+
+    # ---- end to end: shard in pinned host memory, H2D inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        nbytes = (halo_avail + n) * 4
+        hptr = B.lib().ookd_gpu_host_alloc(nbytes)
+        if not hptr:
+            raise SystemExit("pinned host allocation failed")
+        rc = B.lib().ookd_gpu_memcpy_d2h(local_rank, hptr, d_iq.data_ptr(), nbytes)
+        assert rc == 0
+        import ctypes
+        h_iq = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_int16)), shape=((halo_avail + n) * 2,))
+        one_step(h_iq)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            res_e, msgs_e, _ = one_step(h_iq)
+        barrier()
+        dte = time.perf_counter() - t0
+        te = torch.tensor([dte], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dte = float(te.item())
+        d2h = len(res_e["msgs"]) * 56 + 3 * 256 + 48
+        e2e = {"value": world * n / (dte / args.e2e_steps) / 1e6, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps}
+        if rank == 0 and msgs is not None and msgs_e is not None:
+            assert msgs_e == msgs, "host-input decode differs from device-input decode"
+        cpu_prefix = h_iq[halo_avail * 2: (halo_avail + min(n, args.cpu_samples)) * 2].copy() if rank == 0 else None
+        B.lib().ookd_gpu_host_free(hptr)
+    else:
+        cpu_prefix = d_iq[halo_avail * 2: (halo_avail + min(n, args.cpu_samples)) * 2].cpu().numpy() if rank == 0 else None
+
+    # ---- CPU baseline (rank 0, N = 1 only): the unmodified reference binary on a bounded prefix ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nc = cpu_prefix.size // 2
+        if reference_binary() is not None:
+            v, rows = run_reference_cpu(cpu_prefix)
+            n_gpu_rows = sum(1 for m in msgs if (m[0] + 1) <= (nc // SPB) * SPB) if msgs else 0
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "host_cores_available": os.cpu_count(),
+                   "sample": f"first {nc} samples ({nc * 4 / 2**20:.0f} MiB) of the same capture; "
+                             f"{rows} messages (GPU decoded {n_gpu_rows} in the same span)"}
+        else:
+            from oracle import oracle as O
+            odev = O.load_device(DEVICE_NAME)
+            t0 = time.perf_counter()
+            r = O.rx(cpu_prefix, O.load_filter(FILTER_NAME), odev, threshold_=THR, samples_per_buffer=SPB, samplerate=FS)
+            v = nc / (time.perf_counter() - t0) / 1e6
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
+                   "sample": f"first {nc} samples of the same capture; {len(r['msgs'])} messages"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        fir_ms_per_launch = fir_ms_max / args.steps
+        achieved = 4.0 * n / (fir_ms_per_launch * 1e-3) / 1e9 if fir_ms_per_launch > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(n), "samples_per_gpu": n, "device": DEVICE_NAME, "filter": FILTER_NAME,
+                       "parallelism": f"time-shards x{world}" if world > 1 else "single shard",
+                       "l2": "input shard (4 B/sample) larger than L2; no flush needed",
+                       "messages_decoded": n_msgs, "messages_transmitted_upper_bound": n_tx_msgs,
+                       "edges_last_rank": n_edges, "sm_rounds": sm_rounds},
+            "device_ms_per_step": kernel_ms_max / args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
+                         "peak_source": peak_src, "kernel": "FIR/threshold (fir1_*), 4 B/sample algorithmic",
+                         "kernel_ms_per_launch": fir_ms_per_launch},
+            "clocks": clocks, "gpu_launches": launches,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

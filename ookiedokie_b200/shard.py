@@ -1,0 +1,128 @@
+"""Time-sharded decode across ranks: one process per GPU, no collective on the data path.
+
+Rank r owns input samples [r*S, (r+1)*S) of one continuous capture and reads `halo` samples of
+history in front of its shard (FIR halo + one byte of decisions for the edge detector).  The only
+exchange is the state-machine carry at each shard boundary (struct ookd_sm_carry, 48 bytes):
+
+    1. every rank decodes its shard from a guessed entry state (rank 0: the true initial state);
+    2. exits are all-gathered; a rank whose predecessor's exit differs from the entry it used
+       re-runs ONLY its state-machine stage from the corrected entry (ookd_gpu_resolve; samples,
+       decisions and edges are untouched);
+    3. repeat until no rank changed -- at most world_size rounds, because rank 0's entry is exact
+       and each pass fixes at least the first still-wrong boundary.
+
+The fixed point equals the sequential decode (each shard is a deterministic function of its entry).
+`runner` is anything with decode(entry) / resolve(entry) -> (result, exit_carry_tuple), so the
+protocol itself is testable on CPU with gloo and a stand-in runner.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+CARRY_BYTES = 16 + 32
+MSG_REC = 8 + 8 + 4 + 32        # out_sample, buffer_idx, num_bits, data
+
+
+def carry_to_bytes(c):
+    state, k, num_bits, prev, data = c
+    return np.array([state, k, num_bits, prev], dtype=np.uint32).tobytes() + bytes(data).ljust(32, b"\0")[:32]
+
+
+def carry_from_bytes(b):
+    b = bytes(b)
+    s = np.frombuffer(b[:16], dtype=np.uint32)
+    return (int(s[0]), int(s[1]), int(s[2]), int(s[3]), b[16:48])
+
+
+INITIAL_CARRY = (0, 0, 0, 0, bytes(32))
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def stitch(runner, rank, world, guess=None):
+    """Run the protocol above.  Returns (result, exit, rounds)."""
+    entry_used = None if rank == 0 else (guess if guess is not None else INITIAL_CARRY)
+    res, exit_c = runner.decode(entry_used)
+    if world == 1:
+        return res, exit_c, 1
+    if entry_used is None:
+        entry_used = INITIAL_CARRY
+    dev = _dev()
+    rounds = 1
+    while True:
+        mine = torch.frombuffer(bytearray(carry_to_bytes(exit_c)), dtype=torch.uint8).to(dev)
+        gathered = [torch.empty(CARRY_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        changed = False
+        true_entry = entry_used
+        if rank > 0:
+            true_entry = carry_from_bytes(gathered[rank - 1].cpu().numpy().tobytes())
+            changed = true_entry != entry_used
+        flag = torch.tensor([1 if changed else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()) == 0:
+            return res, exit_c, rounds
+        if changed:
+            res, exit_c = runner.resolve(true_entry)
+            entry_used = true_entry
+        rounds += 1
+        if rounds > world + 2:
+            raise RuntimeError("shard stitch did not converge")
+
+
+def gather_messages(msgs, rank, world, nbytes):
+    """msgs: [(out_sample, buffer_idx, num_bits, data)] per rank -> full ordered list on rank 0 (None elsewhere)."""
+    if world == 1:
+        return list(msgs)
+    dev = _dev()
+    cnt = torch.tensor([len(msgs)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    buf = np.zeros((cap, MSG_REC), dtype=np.uint8)
+    for i, (o, b, nb, data) in enumerate(msgs):
+        buf[i, 0:8] = np.frombuffer(np.uint64(o).tobytes(), dtype=np.uint8)
+        buf[i, 8:16] = np.frombuffer(np.uint64(b).tobytes(), dtype=np.uint8)
+        buf[i, 16:20] = np.frombuffer(np.uint32(nb).tobytes(), dtype=np.uint8)
+        buf[i, 20:20 + len(data)] = np.frombuffer(bytes(data), dtype=np.uint8)
+    mine = torch.from_numpy(buf).to(dev)
+    allb = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allb, mine)
+    if rank != 0:
+        return None
+    out = []
+    for r in range(world):
+        a = allb[r].cpu().numpy()
+        for i in range(counts[r]):
+            rec = a[i].tobytes()
+            out.append((int(np.frombuffer(rec[0:8], dtype=np.uint64)[0]), int(np.frombuffer(rec[8:16], dtype=np.uint64)[0]),
+                        int(np.frombuffer(rec[16:20], dtype=np.uint32)[0]), rec[20:20 + nbytes]))
+    return out
+
+
+class GpuShardRunner:
+    """runner over one ookiedokie_b200.binding.Gpu handle and a resident (device or pinned host) shard."""
+
+    def __init__(self, gpu, iq, first_sample, n_samples, last):
+        self.gpu, self.iq, self.first, self.n, self.last = gpu, iq, first_sample, n_samples, last
+        self.launches = 0
+        self.fir_ms = 0.0
+        self.kernel_ms = 0.0
+
+    def _acc(self, res):
+        self.launches += res["gpu_launches"]
+        self.fir_ms += res["fir_ms"]
+        self.kernel_ms += res["kernel_ms"]
+
+    def decode(self, entry):
+        res, ex = self.gpu.decode_shard(self.iq, self.first, self.n, self.last, entry)
+        self._acc(res)
+        return res, ex
+
+    def resolve(self, entry):
+        res, ex = self.gpu.resolve(entry)
+        self._acc(res)
+        return res, ex
