@@ -104,6 +104,8 @@ struct ookd_sm_state_k {
     uint32_t first_trigger, num_triggers;
     uint32_t dmin, dmax;                     /* state-duration window (edge triggers)  */
     uint32_t ktimeout;                       /* OOKD_K_INF => never                    */
+    uint32_t ksat;                           /* counts saturate here while in this state:
+                                                1 + largest finite bound the state compares k with */
 };
 
 struct ookd_sm_compiled {

@@ -67,7 +67,7 @@ class SmTriggerK(C.Structure):
 
 class SmStateK(C.Structure):
     _fields_ = [("first_trigger", C.c_uint32), ("num_triggers", C.c_uint32),
-                ("dmin", C.c_uint32), ("dmax", C.c_uint32), ("ktimeout", C.c_uint32)]
+                ("dmin", C.c_uint32), ("dmax", C.c_uint32), ("ktimeout", C.c_uint32), ("ksat", C.c_uint32)]
 
 
 class SmCompiled(C.Structure):
@@ -227,7 +227,8 @@ def sm_compile(states, num_bits, sample_rate):
         raise OokdError(f"ookd_sm_compile: {lib().ookd_gpu_strerror(rc).decode()}")
     res = dict(k_sat=out.k_sat, max_bits=out.max_bits,
                states=[dict(first_trigger=out.states[i].first_trigger, num_triggers=out.states[i].num_triggers,
-                            dmin=out.states[i].dmin, dmax=out.states[i].dmax, ktimeout=out.states[i].ktimeout)
+                            dmin=out.states[i].dmin, dmax=out.states[i].dmax, ktimeout=out.states[i].ktimeout,
+                            ksat=out.states[i].ksat)
                        for i in range(out.num_states)],
                triggers=[dict(cond=out.triggers[i].cond, action=out.triggers[i].action,
                               next=out.triggers[i].next_state, kmin=out.triggers[i].kmin, kmax=out.triggers[i].kmax)

@@ -58,7 +58,7 @@ struct ookd_gpu {
 
     // workspaces
     DevBuf in, bits, inter[2], block_counts, edges, scalars, chunk_exit[2], chunk_ran, slots, slot_count,
-           slot_off, msgs_dev;
+           slot_off, msgs_dev, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
     uint32_t slot_cap = 8;
     void *h_scalars = nullptr;        // pinned, 256 B
     std::vector<ookd_msg> h_msgs;
@@ -219,60 +219,79 @@ int run_generic_chain(ookd_gpu *h, const void *d_in, bool in_is_i16, i64 in_base
 }
 
 // ---- state machine stage + message gather; fills res ----
-int run_state_machine(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *exit_, ookd_gpu_result *res)
+constexpr uint32_t TAB_K = 8;
+
+// scalars layout (device + pinned host mirror, 256 B):
+//   [0]  u64 edge total      [8]  u64 message total   [32] u32 overflow flag
+//   [40] u32 walk resolved   [44] u32 walk complete   [64..192) u32 round counters   [192..240) final exit carry
+int finish_messages(ookd_gpu *h, const SmMsg *raw, u64 n_msgs, const SmCarry &last, uint32_t rounds,
+                    ookd_sm_carry *exit_, ookd_gpu_result *res)
 {
-    h->h_msgs.clear();
-    uint32_t rounds = 0;
-    if (!h->have_sm || h->out_hi <= h->out_lo) {
-        if (exit_) {
-            ookd_sm_carry c{};
-            carry_from_dev(entry0, c);
-            *exit_ = c;
-        }
-        if (res) { res->n_msgs = 0; res->msgs = nullptr; res->sm_rounds = 0; }
-        return OOKD_OK;
+    h->h_msgs.resize(n_msgs);
+    const uint32_t nbytes = (h->smc.max_bits + 7) / 8;
+    for (u64 i = 0; i < n_msgs; i++) {
+        const SmMsg &m = raw[i];
+        ookd_msg &o = h->h_msgs[i];
+        memset(&o, 0, sizeof(o));
+        o.out_sample = m.out_sample;
+        o.buffer_idx = ((m.out_sample + 1) * (u64) h->total_dec - 1) / h->spb;
+        o.num_bits = m.num_bits;
+        memcpy(o.data, m.data, nbytes);
     }
+    if (exit_) carry_from_dev(last, *exit_);
+    if (res) {
+        res->n_msgs = n_msgs;
+        res->msgs = n_msgs ? h->h_msgs.data() : nullptr;
+        res->sm_rounds = rounds;
+    }
+    return OOKD_OK;
+}
+
+SmArgs base_sm_args(ookd_gpu *h, const SmCarry &entry0)
+{
+    SmArgs a{};
+    a.tab = h->d_tab;
+    a.edges = (const u64 *) h->edges.p;
+    a.n_edges = h->n_edges;
+    a.base_bit = h->base_bit;
+    a.out_lo = h->out_lo; a.out_hi = h->out_hi;
+    a.spb = h->spb; a.dec = h->total_dec;
+    a.first_buffer = h->first_buffer;
+    a.chunk_buffers = h->chunk_buffers;
+    a.n_chunks = h->n_chunks;
+    a.entry0 = entry0;
+    a.slots = (SmMsg *) h->slots.p;
+    a.slot_cap = h->slot_cap;
+    a.n_ran = (uint32_t *) ((char *) h->scalars.p + 64);
+    a.overflow = (uint32_t *) ((char *) h->scalars.p + 32);
+    return a;
+}
+
+// Fallback: Jacobi relaxation (always terminates within n_chunks rounds).
+int run_state_machine_jacobi(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *exit_, ookd_gpu_result *res,
+                             uint32_t rounds_before)
+{
     const uint32_t nc = h->n_chunks;
     int rc;
     if ((rc = ensure(h, h->chunk_exit[0], sizeof(SmCarry) * nc))) return rc;
     if ((rc = ensure(h, h->chunk_exit[1], sizeof(SmCarry) * nc))) return rc;
     if ((rc = ensure(h, h->chunk_ran, sizeof(SmCarry) * nc))) return rc;
-    if ((rc = ensure(h, h->slot_count, sizeof(uint32_t) * (nc + 1)))) return rc;
-    if ((rc = ensure(h, h->slot_off, sizeof(uint32_t) * (nc + 1)))) return rc;
-
-    uint32_t *d_nran = (uint32_t *) ((char *) h->scalars.p + 64);      // [32] per-burst round counters
-    uint32_t *d_overflow = (uint32_t *) ((char *) h->scalars.p + 32);
     const uint32_t *h_nran = (const uint32_t *) ((const char *) h->h_scalars + 64);
     const uint32_t *h_overflow = (const uint32_t *) ((const char *) h->h_scalars + 32);
+    uint32_t rounds = 0;
 
     for (int attempt = 0; attempt < 12; attempt++) {
-        if ((rc = ensure(h, h->slots, sizeof(SmMsg) * (size_t) nc * h->slot_cap))) return rc;
-        CU(h, cudaMemsetAsync(d_overflow, 0, 4, h->s_compute));
-        SmArgs a{};
-        a.tab = h->d_tab;
-        a.edges = (const u64 *) h->edges.p;
-        a.n_edges = h->n_edges;
-        a.base_bit = h->base_bit;
-        a.out_lo = h->out_lo; a.out_hi = h->out_hi;
-        a.spb = h->spb; a.dec = h->total_dec;
-        a.first_buffer = h->first_buffer;
-        a.chunk_buffers = h->chunk_buffers;
-        a.n_chunks = nc;
-        a.entry0 = entry0;
+        if ((rc = ensure(h, h->slots, sizeof(SmMsg) * (size_t) nc * TAB_K * h->slot_cap))) return rc;
+        SmArgs a = base_sm_args(h, entry0);
+        CU(h, cudaMemsetAsync(a.overflow, 0, 4, h->s_compute));
         a.ran_with = (SmCarry *) h->chunk_ran.p;
-        a.slots = (SmMsg *) h->slots.p;
-        a.slot_cap = h->slot_cap;
         a.slot_count = (uint32_t *) h->slot_count.p;
-        a.n_ran = d_nran;
-        a.overflow = d_overflow;
-
         int cur = 0;
         rounds = 0;
         const unsigned grid = (nc + 31) / 32;
         for (;;) {
-            // a short burst of rounds, then one look at the last round's re-run counter
             const uint32_t burst = (rounds == 0) ? 3 : 2;
-            CU(h, cudaMemsetAsync(d_nran, 0, 128, h->s_compute));
+            CU(h, cudaMemsetAsync(a.n_ran, 0, 128, h->s_compute));
             for (uint32_t r = 0; r < burst; r++) {
                 a.round = rounds;
                 a.counter_idx = r;
@@ -289,12 +308,10 @@ int run_state_machine(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *exit_, 
             if (h_nran[burst - 1] == 0) break;          // a round that re-ran nothing: fixed point
             if (rounds > nc + 8) return fail(h, OOKD_ERR_STATE, "state machine stitch did not converge");
         }
-        h->exit_idx = cur;
         if (*h_overflow != 0) {
             h->slot_cap *= 4;
             continue;
         }
-        // gather
         CU(h, cudaMemcpyAsync(h->slot_off.p, h->slot_count.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice,
                               h->s_compute));
         scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
@@ -316,26 +333,125 @@ int run_state_machine(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *exit_, 
         CU(h, cudaMemcpyAsync(&last, (SmCarry *) h->chunk_exit[cur].p + (nc - 1), sizeof(SmCarry),
                               cudaMemcpyDeviceToHost, h->s_compute));
         CU(h, cudaStreamSynchronize(h->s_compute));
-        h->h_msgs.resize(n_msgs);
-        for (u64 i = 0; i < n_msgs; i++) {
-            const SmMsg &m = h->h_msgs_raw[i];
-            ookd_msg &o = h->h_msgs[i];
-            memset(&o, 0, sizeof(o));
-            o.out_sample = m.out_sample;
-            o.buffer_idx = ((m.out_sample + 1) * (u64) h->total_dec - 1) / h->spb;
-            o.num_bits = m.num_bits;
-            const uint32_t nbytes = (h->smc.max_bits + 7) / 8;
-            memcpy(o.data, m.data, nbytes);
-        }
-        if (exit_) carry_from_dev(last, *exit_);
-        if (res) {
-            res->n_msgs = n_msgs;
-            res->msgs = n_msgs ? h->h_msgs.data() : nullptr;
-            res->sm_rounds = rounds;
-        }
-        return OOKD_OK;
+        return finish_messages(h, h->h_msgs_raw.data(), n_msgs, last, rounds_before + rounds, exit_, res);
     }
     return fail(h, OOKD_ERR_OVERFLOW, "message slots overflowed after retries");
+}
+
+int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gpu_result *res)
+{
+    h->h_msgs.clear();
+    if (!h->have_sm || h->out_hi <= h->out_lo) {
+        if (exit_) carry_from_dev(entry0, *exit_);
+        if (res) { res->n_msgs = 0; res->msgs = nullptr; res->sm_rounds = 0; }
+        return OOKD_OK;
+    }
+    // canonical count for the entry's state (see sm_kernels.cuh)
+    if (entry0.state < h->smc.num_states && entry0.k > h->smc.states[entry0.state].ksat) {
+        entry0.k = h->smc.states[entry0.state].ksat;
+    }
+    const uint32_t nc = h->n_chunks;
+    int rc;
+    if ((rc = ensure(h, h->slot_count, sizeof(uint32_t) * (nc + 1)))) return rc;
+    if ((rc = ensure(h, h->slot_off, sizeof(uint32_t) * (nc + 1)))) return rc;
+    if ((rc = ensure(h, h->tab_entry, sizeof(SmCarry) * (size_t) nc * TAB_K))) return rc;
+    if ((rc = ensure(h, h->tab_exit, sizeof(SmCarry) * (size_t) nc * TAB_K))) return rc;
+    if ((rc = ensure(h, h->tab_nmsg, sizeof(uint32_t) * (size_t) nc * TAB_K))) return rc;
+    if ((rc = ensure(h, h->tab_cnt[0], sizeof(uint32_t) * nc))) return rc;
+    if ((rc = ensure(h, h->tab_cnt[1], sizeof(uint32_t) * nc))) return rc;
+    if ((rc = ensure(h, h->tab_link, (size_t) nc * TAB_K + 16))) return rc;
+    if ((rc = ensure(h, h->tab_chosen, (size_t) nc + 16))) return rc;
+
+    const uint32_t *h_overflow = (const uint32_t *) ((const char *) h->h_scalars + 32);
+    const uint32_t *h_walk = (const uint32_t *) ((const char *) h->h_scalars + 40);
+    uint32_t rounds = 0;
+    bool resolved = false;
+
+    for (int attempt = 0; attempt < 8 && !resolved; attempt++) {
+        if ((rc = ensure(h, h->slots, sizeof(SmMsg) * (size_t) nc * TAB_K * h->slot_cap))) return rc;
+        SmArgs a = base_sm_args(h, entry0);
+        a.tab_k = TAB_K;
+        a.tab_entry = (SmCarry *) h->tab_entry.p;
+        a.tab_exit = (SmCarry *) h->tab_exit.p;
+        a.tab_nmsg = (uint32_t *) h->tab_nmsg.p;
+        a.link = (uint8_t *) h->tab_link.p;
+        a.chosen = (uint8_t *) h->tab_chosen.p;
+        a.walk_status = (uint32_t *) ((char *) h->scalars.p + 40);
+        a.msg_counts = (uint32_t *) h->slot_count.p;
+        a.final_exit = (SmCarry *) ((char *) h->scalars.p + 192);
+        CU(h, cudaMemsetAsync(h->scalars.p, 0, 256, h->s_compute));
+        CU(h, cudaMemsetAsync(h->tab_cnt[0].p, 0, sizeof(uint32_t) * nc, h->s_compute));
+        const unsigned grid = (unsigned) (((u64) nc * TAB_K + 31) / 32);
+        int cur = 0;
+        rounds = 0;
+        bool table_failed = false;
+        for (;;) {
+            // round 0 (seeds) and round 1 (predecessors' exits) back to back, later rounds one at a time
+            const uint32_t burst = (rounds == 0) ? 2 : 1;
+            for (uint32_t r = 0; r < burst; r++) {
+                a.round = rounds;
+                a.counter_idx = rounds & 31;
+                if (rounds == 0) {
+                    a.cnt_in = (const uint32_t *) h->tab_cnt[0].p;
+                    a.cnt_out = (uint32_t *) h->tab_cnt[0].p;
+                } else {
+                    CU(h, cudaMemcpyAsync(h->tab_cnt[cur ^ 1].p, h->tab_cnt[cur].p, sizeof(uint32_t) * nc,
+                                          cudaMemcpyDeviceToDevice, h->s_compute));
+                    a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
+                    a.cnt_out = (uint32_t *) h->tab_cnt[cur ^ 1].p;
+                    cur ^= 1;
+                }
+                sm_table_round_kernel<<<grid, 32, 0, h->s_compute>>>(a);
+                h->launches++;
+                CU(h, cudaGetLastError());
+                rounds++;
+            }
+            a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
+            sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
+            sm_walk_kernel<<<1, 256, 0, h->s_compute>>>(a);
+            h->launches += 2;
+            CU(h, cudaGetLastError());
+            CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
+            CU(h, cudaStreamSynchronize(h->s_compute));
+            if (*h_overflow == 1) break;                    // message slots too small: grow and redo
+            if (h_walk[1] == 1) { resolved = true; break; }
+            if (*h_overflow == 2 || rounds >= 8) { table_failed = true; break; }
+        }
+        if (resolved) break;
+        if (*h_overflow == 1) {
+            h->slot_cap *= 4;
+            continue;
+        }
+        if (table_failed) {
+            return run_state_machine_jacobi(h, entry0, exit_, res, rounds);
+        }
+    }
+    if (!resolved) return fail(h, OOKD_ERR_OVERFLOW, "message slots overflowed after retries");
+
+    // ---- ordered gather of the chosen pairs' messages ----
+    SmArgs a = base_sm_args(h, entry0);
+    a.tab_k = TAB_K;
+    a.chosen = (uint8_t *) h->tab_chosen.p;
+    a.msg_counts = (uint32_t *) h->slot_count.p;
+    CU(h, cudaMemcpyAsync(h->slot_off.p, h->slot_count.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice, h->s_compute));
+    scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
+    h->launches++;
+    CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
+    CU(h, cudaStreamSynchronize(h->s_compute));
+    const u64 n_msgs = ((const u64 *) h->h_scalars)[1];
+    SmCarry last;
+    memcpy(&last, (const char *) h->h_scalars + 192, sizeof(SmCarry));
+    if (n_msgs) {
+        if ((rc = ensure(h, h->msgs_dev, sizeof(SmMsg) * n_msgs))) return rc;
+        sm_gather_table_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a, (const uint32_t *) h->slot_off.p,
+                                                                           (SmMsg *) h->msgs_dev.p);
+        h->launches++;
+        h->h_msgs_raw.resize(n_msgs);
+        CU(h, cudaMemcpyAsync(h->h_msgs_raw.data(), h->msgs_dev.p, sizeof(SmMsg) * n_msgs, cudaMemcpyDeviceToHost,
+                              h->s_compute));
+        CU(h, cudaStreamSynchronize(h->s_compute));
+    }
+    return finish_messages(h, h->h_msgs_raw.data(), n_msgs, last, rounds, exit_, res);
 }
 
 }  // namespace
@@ -378,7 +494,8 @@ void ookd_gpu_destroy(ookd_gpu *h)
     if (h->d_tab) cudaFree(h->d_tab);
     DevBuf *all[] = {&h->in, &h->bits, &h->inter[0], &h->inter[1], &h->block_counts, &h->edges, &h->scalars,
                      &h->chunk_exit[0], &h->chunk_exit[1], &h->chunk_ran, &h->slots, &h->slot_count,
-                     &h->slot_off, &h->msgs_dev};
+                     &h->slot_off, &h->msgs_dev, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
+                     &h->tab_cnt[1], &h->tab_link, &h->tab_chosen};
     for (DevBuf *b : all) release(*b);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
     for (auto e : h->ev_piece) cudaEventDestroy(e);

@@ -157,6 +157,7 @@ int ookd_sm_compile(const struct ookd_sm_desc *d, struct ookd_sm_compiled *out)
         struct ookd_sm_state_k *o = &out->states[s];
         o->first_trigger = st->first_trigger;
         o->num_triggers = st->num_triggers;
+        o->ksat = 0;
         if (st->duration_us == 0) {
             o->dmin = 0;
             o->dmax = OOKD_K_INF;
@@ -165,12 +166,15 @@ int ookd_sm_compile(const struct ookd_sm_desc *d, struct ookd_sm_compiled *out)
             o->dmax = b[q + 1].k;
             if (o->dmin > k_max) k_max = o->dmin;
             if (o->dmax > k_max) k_max = o->dmax;
+            if (o->dmin + 1 > o->ksat) o->ksat = o->dmin + 1;
+            if (o->dmax + 1 > o->ksat) o->ksat = o->dmax + 1;
         }
         if (st->timeout_us == 0) {
             o->ktimeout = OOKD_K_INF;
         } else {
             o->ktimeout = b[q + 2].k;
             if (o->ktimeout > k_max) k_max = o->ktimeout;
+            if (o->ktimeout + 1 > o->ksat) o->ksat = o->ktimeout + 1;
         }
         q += 3;
     }
@@ -190,6 +194,17 @@ int ookd_sm_compile(const struct ookd_sm_desc *d, struct ookd_sm_compiled *out)
             if (o->kmax > k_max) k_max = o->kmax;
         }
         q += 2;
+    }
+    /* per-state saturation also covers the windows of the state's own triggers */
+    for (uint32_t s = 0; s < d->num_states; s++) {
+        struct ookd_sm_state_k *o = &out->states[s];
+        for (uint32_t t = 0; t < o->num_triggers; t++) {
+            const struct ookd_sm_trigger_k *tk = &out->triggers[o->first_trigger + t];
+            if (tk->kmax != OOKD_K_INF) {
+                if (tk->kmin + 1 > o->ksat) o->ksat = tk->kmin + 1;
+                if (tk->kmax + 1 > o->ksat) o->ksat = tk->kmax + 1;
+            }
+        }
     }
     free(b);
 

@@ -10,12 +10,24 @@
 // twice, :526-538) and the first sample after a dropped buffer tail (prev_bit is stale there,
 // :549-552) take the single-sample path, which mirrors handle_rx_triggers one to one.
 //
-// Parallel form.  The output stream is cut into chunks of whole buffers, one thread each.
-// Round 0 runs every chunk from a guessed entry state (RESET, k=0, true previous bit); every
-// later round re-runs exactly the chunks whose entry (= predecessor's exit of the previous
-// round) differs from the entry they last ran with.  A round that re-runs nothing is a fixed
-// point, and the fixed point is the sequential result because chunk 0's entry is given and
-// each chunk is a deterministic function of its entry.
+// Parallel form.  The output stream is cut into chunks of whole buffers.  The machine's state at a
+// chunk boundary depends on everything before it, so each chunk keeps a small TABLE of
+// (entry state -> exit state, messages) pairs, one thread per pair:
+//   round 0   two speculative seeds per chunk: RESET at the chunk's first sample, and RESET at the
+//             chunk's first "anchor" (first rising edge from which a fresh machine appends a bit,
+//             i.e. a plausible message start; found by short probe runs); chunk 0 runs from the
+//             true entry;
+//   round r   every exit in chunk c-1's table that is not yet an entry of chunk c's table is run;
+//   link/walk exits are matched to the next chunk's entries and one thread walks the chain from
+//             chunk 0's true entry.  If the walk reaches the last chunk the decode is resolved:
+//             the chosen pairs ARE the sequential run, because each pair is the deterministic
+//             function of its entry.  Otherwise another round adds the missing entries.
+// A Jacobi relaxation over single exits (sm_round_kernel: re-run exactly the chunks whose entry
+// changed until nothing changes) is kept as the always-terminating fallback.
+//
+// Counts k saturate per state at ksat = 1 + (largest finite bound any predicate of that state
+// compares k with): beyond it every predicate of the state is constant, so the saturated machine is
+// indistinguishable from the reference's and equal situations compare equal.
 #pragma once
 
 #include "ookd_common.cuh"
@@ -44,6 +56,18 @@ struct SmArgs {
     uint32_t *slot_count;     // [n_chunks]
     uint32_t *n_ran;          // [rounds]
     uint32_t *overflow;
+    // table speculation
+    uint32_t tab_k;           // pairs per chunk
+    SmCarry *tab_entry;       // [n_chunks * tab_k]
+    SmCarry *tab_exit;        // [n_chunks * tab_k]
+    uint32_t *tab_nmsg;       // [n_chunks * tab_k]
+    const uint32_t *cnt_in;   // [n_chunks] pairs present before this round
+    uint32_t *cnt_out;        // [n_chunks] pairs present after it (initialised to cnt_in)
+    uint8_t  *link;           // [n_chunks * tab_k]
+    uint8_t  *chosen;         // [n_chunks]
+    uint32_t *walk_status;    // [0] = chunks resolved, [1] = 1 if complete
+    uint32_t *msg_counts;     // [n_chunks] messages of the chosen pair
+    SmCarry  *final_exit;     // exit of the last chunk's chosen pair (written by the walk)
 };
 
 __device__ __forceinline__ i64 first_output_of_buffer(const SmArgs &a, u64 b)
@@ -117,7 +141,7 @@ __device__ __forceinline__ int sm_eval(const SmTable &T, SmCarry &s, uint32_t b)
         }
     }
     if (fired < 0) {
-        s.k = (s.k + 1 < T.k_sat) ? s.k + 1 : T.k_sat;
+        s.k = (s.k + 1 < st.ksat) ? s.k + 1 : st.ksat;
         return 0;
     }
     int result;
@@ -196,51 +220,40 @@ __device__ __forceinline__ u64 edge_lower_bound(const u64 *edges, u64 n, u64 pos
     return lo;
 }
 
-__global__ void __launch_bounds__(32) sm_round_kernel(const SmArgs a)
+
+struct SpanOut {
+    SmMsg   *slots;
+    uint32_t cap;
+    uint32_t n_msgs;
+    uint32_t *overflow;       // null => count only (probe runs)
+};
+
+__device__ __forceinline__ void sm_emit(SpanOut &o, const SmCarry &s, i64 pos)
 {
-    __shared__ SmTable T;
-    {
-        const uint32_t *src = (const uint32_t *) a.tab;
-        uint32_t *dst = (uint32_t *) &T;
-        for (uint32_t i = threadIdx.x; i < sizeof(SmTable) / 4; i += blockDim.x) dst[i] = src[i];
+    if (o.n_msgs < o.cap) {
+        SmMsg m;
+        m.out_sample = (u64) pos;
+        m.num_bits = s.num_bits;
+        m.pad = 0;
+        m.data[0] = s.data[0]; m.data[1] = s.data[1]; m.data[2] = s.data[2]; m.data[3] = s.data[3];
+        o.slots[o.n_msgs] = m;
+    } else if (o.overflow) {
+        atomicExch(o.overflow, 1u);
     }
-    __syncthreads();
+    o.n_msgs++;
+}
 
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_chunks) return;
-
-    const i64 start = (c == 0) ? a.out_lo
-                               : first_output_of_buffer(a, a.first_buffer + (u64) c * a.chunk_buffers);
-    i64 end = first_output_of_buffer(a, a.first_buffer + (u64) (c + 1) * a.chunk_buffers);
-    if (end > a.out_hi || c == a.n_chunks - 1) end = a.out_hi;
-
-    // edges[e] is the first edge at or after `start`; e edges precede it
-    u64 e = edge_lower_bound(a.edges, a.n_edges, (u64) start);
-    uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);           // true decision at start-1
-
-    SmCarry s;
-    if (c == 0) {
-        s = a.entry0;
-    } else if (a.round == 0) {
-        s.state = 0; s.k = 0; s.num_bits = 0; s.prev = tb;
-        s.data[0] = s.data[1] = s.data[2] = s.data[3] = 0;
-    } else {
-        s = a.exit_prev[c - 1];
-    }
-    if (a.round > 0 && carry_equal(s, a.ran_with[c])) {
-        a.exit_cur[c] = a.exit_prev[c];
-        return;
-    }
-    a.ran_with[c] = s;
-    atomicAdd(&a.n_ran[a.counter_idx], 1u);
-
-    uint32_t n_msgs = 0;
-    SmMsg *slots = a.slots + (u64) c * a.slot_cap;
-
+// Run the machine over outputs [pos, end) from state s.  e = index of the first edge at or after
+// pos, tb = true decision at pos-1.  PROBE: stop early and report whether a machine started in
+// RESET at pos gets as far as appending a bit / emitting a message (1) or falls back to RESET (0).
+template <bool PROBE>
+__device__ __forceinline__ int sm_run_span(const SmArgs &a, const SmTable &T, SmCarry &s, i64 pos, i64 end,
+                                           u64 e, uint32_t tb, SpanOut &o)
+{
+    bool left_reset = false;
     const u64 INF = ~0ull;
     u64 next_edge = (e < a.n_edges) ? a.edges[e] : INF;
     u64 after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;   // one-ahead prefetch
-    i64 pos = start;
 
     while (pos < end) {
         const bool at_edge = (next_edge == (u64) pos);
@@ -254,18 +267,13 @@ __global__ void __launch_bounds__(32) sm_round_kernel(const SmArgs a)
                 after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;
             }
             pos++;
+            if (PROBE) {
+                if (r > 0 || s.num_bits > 0) return 1;
+                if (s.state != 0) left_reset = true;
+                if (r < 0 || (left_reset && s.state == 0)) return 0;
+            }
             if (r > 0) {
-                if (n_msgs < a.slot_cap) {
-                    SmMsg m;
-                    m.out_sample = (u64) (pos - 1);
-                    m.num_bits = s.num_bits;
-                    m.pad = 0;
-                    m.data[0] = s.data[0]; m.data[1] = s.data[1]; m.data[2] = s.data[2]; m.data[3] = s.data[3];
-                    slots[n_msgs] = m;
-                } else {
-                    atomicExch(a.overflow, 1u);
-                }
-                n_msgs++;
+                sm_emit(o, s, pos - 1);
             } else if (r < 0) {
                 // device_process gives up on this buffer: resume at the next buffer's first output
                 i64 nb = first_output_of_buffer(a, buffer_of_output(a, pos - 1) + 1);
@@ -295,28 +303,248 @@ __global__ void __launch_bounds__(32) sm_round_kernel(const SmArgs a)
             const int r = sm_apply(T, s, T.triggers[st.first_trigger + tf]);
             s.k = 0;
             pos++;
+            if (PROBE) {
+                if (r > 0 || s.num_bits > 0) return 1;
+                if (s.state == 0) return 0;
+            }
             if (r > 0) {
-                if (n_msgs < a.slot_cap) {
-                    SmMsg m;
-                    m.out_sample = (u64) (pos - 1);
-                    m.num_bits = s.num_bits;
-                    m.pad = 0;
-                    m.data[0] = s.data[0]; m.data[1] = s.data[1]; m.data[2] = s.data[2]; m.data[3] = s.data[3];
-                    slots[n_msgs] = m;
-                } else {
-                    atomicExch(a.overflow, 1u);
-                }
-                n_msgs++;
+                sm_emit(o, s, pos - 1);
             }
         } else {
+            const uint32_t ksat = T.states[s.state].ksat;
             const u64 kk = (u64) s.k + gap;
-            s.k = (kk < (u64) T.k_sat) ? (uint32_t) kk : T.k_sat;
+            s.k = (kk < (u64) ksat) ? (uint32_t) kk : ksat;
             pos = (i64) limit;
         }
     }
+    return 0;
+}
+
+__device__ __forceinline__ void load_table(SmTable &T, const SmTable *src_tab)
+{
+    const uint32_t *src = (const uint32_t *) src_tab;
+    uint32_t *dst = (uint32_t *) &T;
+    for (uint32_t i = threadIdx.x; i < sizeof(SmTable) / 4; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void chunk_bounds(const SmArgs &a, uint32_t c, i64 &start, i64 &end)
+{
+    start = (c == 0) ? a.out_lo : first_output_of_buffer(a, a.first_buffer + (u64) c * a.chunk_buffers);
+    end = first_output_of_buffer(a, a.first_buffer + (u64) (c + 1) * a.chunk_buffers);
+    if (end > a.out_hi || c == a.n_chunks - 1) end = a.out_hi;
+}
+
+__device__ __forceinline__ void carry_reset(SmCarry &s, uint32_t prev)
+{
+    s.state = 0; s.k = 0; s.num_bits = 0; s.prev = prev;
+    s.data[0] = s.data[1] = s.data[2] = s.data[3] = 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Table speculation: thread (c, j) = chunk c, pair slot j.
+// ---------------------------------------------------------------------------------------
+#define OOKD_TAB_INVALID 0xFFFFFFFFu      // entry.state of a seed that matches no real entry
+
+__global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
+{
+    __shared__ SmTable T;
+    load_table(T, a.tab);
+
+    const uint32_t K = a.tab_k;
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = gid / K, j = gid % K;
+    if (c >= a.n_chunks) return;
+
+    i64 start, end;
+    chunk_bounds(a, c, start, end);
+    u64 e = edge_lower_bound(a.edges, a.n_edges, (u64) start);
+    uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);           // true decision at start-1
+
+    SmCarry s, entry;
+    i64 pos = start;
+    uint32_t slot;
+    if (a.round == 0) {
+        if (j >= 2) return;
+        if (c == 0) {
+            if (j == 1) return;
+            s = a.entry0;
+            entry = s;
+        } else if (j == 0) {
+            carry_reset(s, tb);
+            entry = s;
+        } else {
+            // second seed: RESET at the chunk's first "anchor" -- the first rising edge from which a
+            // freshly reset machine gets as far as appending a bit (i.e. a plausible message start).
+            // A guess from the chunk's first sample usually lands mid-message, errors, and can stay
+            // out of step with the true run for many messages; the true run, whatever it did before,
+            // is normally idle when a message starts, so from the anchor on the two coincide.
+            u64 er = e;
+            if (tb == 1) er++;                 // edge e falls; the next one rises
+            bool found = false;
+            for (int tries = 0; tries < 96 && er < a.n_edges && a.edges[er] < (u64) end; tries++, er += 2) {
+                SmCarry p;
+                carry_reset(p, 0);
+                SpanOut po;
+                po.slots = nullptr; po.cap = 0; po.n_msgs = 0; po.overflow = nullptr;
+                if (sm_run_span<true>(a, T, p, (i64) a.edges[er], end, er, 0, po)) {
+                    found = true;
+                    break;
+                }
+            }
+            if (!found) return;
+            pos = (i64) a.edges[er];
+            e = er;
+            tb = 0;
+            carry_reset(s, 0);
+            entry = s;
+            entry.state = OOKD_TAB_INVALID;
+        }
+        slot = j;
+        atomicMax(&a.cnt_out[c], j + 1);
+    } else {
+        if (c == 0) return;
+        const uint32_t n_prev = a.cnt_in[c - 1];
+        if (j >= n_prev) return;
+        s = a.tab_exit[(u64) (c - 1) * K + j];
+        for (uint32_t i = 0; i < j; i++) {                 // duplicate among this round's candidates
+            if (carry_equal(s, a.tab_exit[(u64) (c - 1) * K + i])) return;
+        }
+        const uint32_t n_here = a.cnt_in[c];
+        for (uint32_t i = 0; i < n_here; i++) {            // already an entry of this chunk
+            if (carry_equal(s, a.tab_entry[(u64) c * K + i])) return;
+        }
+        slot = atomicAdd(&a.cnt_out[c], 1u);
+        if (slot >= K) {
+            atomicExch(a.overflow, 2u);                     // table full: host falls back
+            return;
+        }
+        entry = s;
+    }
+    atomicAdd(&a.n_ran[a.counter_idx], 1u);
+
+    SpanOut o;
+    o.slots = a.slots + ((u64) c * K + slot) * a.slot_cap;
+    o.cap = a.slot_cap;
+    o.n_msgs = 0;
+    o.overflow = a.overflow;
+    sm_run_span<false>(a, T, s, pos, end, e, tb, o);
+
+    a.tab_entry[(u64) c * K + slot] = entry;
+    a.tab_exit[(u64) c * K + slot] = s;
+    a.tab_nmsg[(u64) c * K + slot] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
+}
+
+// link[c][i] = slot of chunk c+1 whose entry equals exit[c][i] (0xFF if none)
+__global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
+{
+    const uint32_t K = a.tab_k;
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = gid / K, i = gid % K;
+    if (c >= a.n_chunks) return;
+    uint8_t l = 0xFF;
+    if (c + 1 < a.n_chunks && i < a.cnt_in[c]) {
+        const SmCarry x = a.tab_exit[(u64) c * K + i];
+        const uint32_t n_next = a.cnt_in[c + 1];
+        for (uint32_t q = 0; q < n_next; q++) {
+            if (carry_equal(x, a.tab_entry[(u64) (c + 1) * K + q])) { l = (uint8_t) q; break; }
+        }
+    }
+    a.link[(u64) c * K + i] = l;
+}
+
+// One CTA: stage link tiles in shared memory, thread 0 chases the chain from chunk 0 / slot 0.
+__global__ void __launch_bounds__(256) sm_walk_kernel(const SmArgs a)
+{
+    constexpr uint32_t TILE = 4096;                         // chunks per tile
+    __shared__ uint8_t s_link[TILE * 8];
+    __shared__ uint32_t s_cur, s_done;
+    const uint32_t K = a.tab_k;                              // <= 8
+    if (threadIdx.x == 0) { s_cur = 0; s_done = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < a.n_chunks; base += TILE) {
+        const uint32_t n = min(TILE, a.n_chunks - base);
+        for (uint32_t i = threadIdx.x; i < n * K; i += blockDim.x) s_link[i] = a.link[(u64) base * K + i];
+        __syncthreads();
+        if (threadIdx.x == 0 && s_done == base) {
+            uint32_t cur = s_cur, c = 0;
+            for (; c < n; c++) {
+                a.chosen[base + c] = (uint8_t) cur;
+                if (base + c + 1 == a.n_chunks) { c++; break; }
+                const uint8_t nx = s_link[c * K + cur];
+                if (nx == 0xFF) { c++; break; }
+                cur = nx;
+            }
+            s_cur = cur;
+            s_done = base + c;                               // chunks [0, s_done) have a chosen pair
+            if (c < n) s_done |= 0x80000000u;                // chain broke inside this tile
+        }
+        __syncthreads();
+        if (s_done & 0x80000000u) break;
+    }
+    __syncthreads();
+    const uint32_t done = s_done & 0x7FFFFFFFu;
+    if (threadIdx.x == 0) {
+        a.walk_status[0] = done;
+        a.walk_status[1] = (done == a.n_chunks) ? 1u : 0u;
+        if (done == a.n_chunks) {
+            *a.final_exit = a.tab_exit[(u64) (a.n_chunks - 1) * K + a.chosen[a.n_chunks - 1]];
+        }
+    }
+    for (uint32_t c = threadIdx.x; c < a.n_chunks; c += blockDim.x) {
+        a.msg_counts[c] = (c < done) ? a.tab_nmsg[(u64) c * K + a.chosen[c]] : 0u;
+    }
+}
+
+__global__ void sm_gather_table_kernel(const SmArgs a, const uint32_t *offsets, SmMsg *out)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chunks) return;
+    const uint32_t n = a.msg_counts[c];
+    const SmMsg *src = a.slots + ((u64) c * a.tab_k + a.chosen[c]) * a.slot_cap;
+    for (uint32_t i = 0; i < n; i++) out[offsets[c] + i] = src[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// Fallback: Jacobi relaxation, one exit per chunk (thread = chunk).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) sm_round_kernel(const SmArgs a)
+{
+    __shared__ SmTable T;
+    load_table(T, a.tab);
+
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chunks) return;
+
+    i64 start, end;
+    chunk_bounds(a, c, start, end);
+    const u64 e = edge_lower_bound(a.edges, a.n_edges, (u64) start);
+    const uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);
+
+    SmCarry s;
+    if (c == 0) {
+        s = a.entry0;
+    } else if (a.round == 0) {
+        carry_reset(s, tb);
+    } else {
+        s = a.exit_prev[c - 1];
+    }
+    if (a.round > 0 && carry_equal(s, a.ran_with[c])) {
+        a.exit_cur[c] = a.exit_prev[c];
+        return;
+    }
+    a.ran_with[c] = s;
+    atomicAdd(&a.n_ran[a.counter_idx], 1u);
+
+    SpanOut o;
+    o.slots = a.slots + (u64) c * a.slot_cap;
+    o.cap = a.slot_cap;
+    o.n_msgs = 0;
+    o.overflow = a.overflow;
+    sm_run_span<false>(a, T, s, start, end, e, tb, o);
 
     a.exit_cur[c] = s;
-    a.slot_count[c] = (n_msgs < a.slot_cap) ? n_msgs : a.slot_cap;
+    a.slot_count[c] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
 }
 
 // Ordered compaction of the per-chunk message slots (offsets = exclusive scan of slot_count).
