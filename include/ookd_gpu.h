@@ -171,7 +171,10 @@ struct ookd_gpu_result {
     float    kernel_ms;                      /* device time of the last call (CUDA events)       */
     float    fir_ms;                         /* ... of the FIR/threshold kernel(s) alone         */
     uint32_t gpu_launches;                   /* kernels launched by the last call                */
-    uint32_t refined_tiles;                  /* tiles that needed the exact path (screen mode)   */
+    uint32_t refined_tiles;                  /* tiles handed whole to the exact kernel (screen)  */
+    uint32_t refined_blocks;                 /* 8-output blocks recomputed exactly inside the
+                                                screening kernel                                  */
+    uint32_t reserved;
 };
 
 typedef struct ookd_gpu ookd_gpu;

@@ -106,7 +106,8 @@ class GpuResult(C.Structure):
     _fields_ = [("n_in", C.c_uint64), ("n_out", C.c_uint64), ("n_buffers", C.c_uint64),
                 ("n_edges", C.c_uint64), ("n_msgs", C.c_uint64), ("msgs", C.POINTER(Msg)),
                 ("first_bit", C.c_uint32), ("sm_rounds", C.c_uint32), ("kernel_ms", C.c_float),
-                ("fir_ms", C.c_float), ("gpu_launches", C.c_uint32), ("refined_tiles", C.c_uint32)]
+                ("fir_ms", C.c_float), ("gpu_launches", C.c_uint32), ("refined_tiles", C.c_uint32),
+                ("refined_blocks", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 def build_library():
@@ -301,7 +302,8 @@ class Gpu:
         return dict(n_in=int(res.n_in), n_out=int(res.n_out), n_buffers=int(res.n_buffers),
                     n_edges=int(res.n_edges), msgs=msgs, first_bit=int(res.first_bit),
                     sm_rounds=int(res.sm_rounds), kernel_ms=float(res.kernel_ms), fir_ms=float(res.fir_ms),
-                    gpu_launches=int(res.gpu_launches), refined_tiles=int(res.refined_tiles))
+                    gpu_launches=int(res.gpu_launches), refined_tiles=int(res.refined_tiles),
+                    refined_blocks=int(res.refined_blocks))
 
     @property
     def halo(self):

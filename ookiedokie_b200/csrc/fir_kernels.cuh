@@ -194,4 +194,175 @@ fir1_exact_tiled_kernel(const TiledArgs a, const TapsParam<T> taps)
     }
 }
 
+
+// =======================================================================================
+// 3. Screening kernel, one stage, decimation 1, T <= 32 taps, 8 outputs per thread.
+//
+//    The decision the reference takes for output n is  fl(re^2)+fl(im^2) >= P*  on the fp32
+//    in-order sums re, im.  Computing those sums costs 4T flops per sample, which on a B200 is
+//    ~6x more issue slots than the HBM read of the 4-byte sample allows.  But an OOK capture
+//    is mostly "carrier clearly on" or "carrier clearly off", and that can be PROVED per block
+//    of outputs from three sums over the samples S its windows touch (N = |S| = 40):
+//        X = sum x,  Q2 = sum |x|^2,   mu = X/N,   V = Q2 - |X|^2/N = sum |x - mu|^2
+//        y[n] = mu*G + sum_i t_i (x[n-i] - mu),    |sum_i t_i z_i| <= ||t||_2 sqrt(V)   (Cauchy-Schwarz)
+//    so  | |y[n]| - |mu||G| | <= ||t||_2 sqrt(V)  for all 8 outputs of the block, in exact arithmetic.
+//    The reference's rounding moves |y| by at most  gamma ||t||_2 sqrt(Q2)  (gamma ~ (T+1) 2^-24) and
+//    its power by 3 ulp.  With every slack rounded the safe way (ScreenParams, set on the host
+//    in double) the block is decided without a single MAC when the interval misses the
+//    threshold; otherwise its 8 outputs are recomputed with the exact in-order MACs (one output
+//    per lane, compacted through a shared-memory queue so that lanes stay full).  Decisions are
+//    therefore bit-identical to the exact kernel for EVERY input; only the cost is data dependent.
+//    Tiles with too many undecided blocks are handed to fir1_exact_tiled_kernel via tile_list.
+// =======================================================================================
+struct ScreenParams {
+    float g_hi, g_lo;        // |sum t_i| rounded up / down
+    float t2;                // ||t||_2 rounded up
+    float cg;                // gamma * ||t||_2 rounded up
+    float theta_lo, theta_hi;// sqrt(P*) shrunk / grown by 1e-5
+    float inv_n;             // 1/N
+    uint32_t dense_limit;    // undecided blocks per tile above which the tile goes to the dense list
+};
+
+struct ScreenArgs {
+    TiledArgs t;             // t.tile_list / t.tile_count here are OUTPUT: the dense list + its counter
+    uint32_t *dense_list;
+    uint32_t *dense_count;
+    uint32_t *stat_refined;  // [0] blocks refined in place, [1] tiles sent to the dense list
+    uint32_t tile_offset;    // first tile of this launch (tiles are numbered from t.out_lo)
+};
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));      // max relative error 2^-23
+    return r;
+}
+
+template <int T>
+__global__ void __launch_bounds__(256, 4)
+fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T> taps)
+{
+    constexpr int NT = 256, R = 8, L = NT * R;
+    constexpr int HB = (T - 1 + R - 1) / R;           // history blocks in front of the tile (4 for T=32)
+    constexpr int HALO = HB * R;
+    constexpr int NS = L + HALO;
+    constexpr int NB = NT + HB;                        // blocks with statistics
+    __shared__ float2 s_x[NS + (NS >> 3) + 1];
+    __shared__ float s_sx[NB], s_sy[NB], s_sq[NB];
+    __shared__ uint16_t s_queue[NT];
+    __shared__ uint32_t s_nq;
+
+    const TiledArgs &a = sa.t;
+    const uint32_t tile = blockIdx.x + sa.tile_offset;
+    const i64 o0 = a.out_lo + (i64) tile * L;
+    const i64 g0 = o0 - HALO;
+    if (threadIdx.x == 0) s_nq = 0;
+
+    // ---- load + convert + per-block statistics: thread t owns block t+HB; threads < HB also a halo block ----
+    const bool aligned = (((g0 - a.in_base) & 3) == 0) && ((((uintptr_t) a.in) & 15) == 0);
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        int blk;
+        if (pass == 0) {
+            blk = threadIdx.x + HB;
+        } else {
+            if (threadIdx.x >= HB) break;
+            blk = threadIdx.x;
+        }
+        const i64 g = g0 + (i64) blk * R;
+        uint32_t w[R];
+        if (aligned && g >= a.in_base && g >= 0 && g + R <= a.in_valid_end) {
+            const uint4 v0 = __ldg((const uint4 *) (a.in + (g - a.in_base)));
+            const uint4 v1 = __ldg((const uint4 *) (a.in + (g - a.in_base) + 4));
+            w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
+            w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < R; e++) {
+                const i64 ge = g + e;
+                w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
+            }
+        }
+        float sx = 0.0f, sy = 0.0f, sq = 0.0f;
+        float2 *dst = &s_x[blk * R + blk];             // s + (s >> 3) with s = blk*8 + e
+#pragma unroll
+        for (int e = 0; e < R; e++) {
+            const float2 x = sc16q11_to_float2(w[e]);
+            dst[e] = x;
+            sx += x.x;                                 // exact: multiples of 2^-11, |sum| < 2^10
+            sy += x.y;
+            sq = fmaf(x.x, x.x, sq);
+            sq = fmaf(x.y, x.y, sq);
+        }
+        s_sx[blk] = sx;
+        s_sy[blk] = sy;
+        s_sq[blk] = sq;
+    }
+    __syncthreads();
+
+    // ---- classify the 8 outputs of block t+HB from the statistics of blocks t .. t+HB ----
+    {
+        float X = 0.0f, Y = 0.0f, Q2 = 0.0f;
+#pragma unroll
+        for (int d = 0; d <= HB; d++) {
+            X += s_sx[threadIdx.x + d];
+            Y += s_sy[threadIdx.x + d];
+            Q2 += s_sq[threadIdx.x + d];
+        }
+        const float m2 = fmaf(X, X, Y * Y);
+        const float mu = sqrt_approx(m2) * sp.inv_n;
+        const float V = fmaxf(fmaf(-m2, sp.inv_n, Q2), 0.0f) + 2e-5f * Q2;
+        const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q2));
+        const bool all0 = (fmaf(mu, sp.g_hi, bc)) * 1.00001f < sp.theta_lo;
+        const bool all1 = (fmaf(mu, sp.g_lo, -bc)) * 0.99999f > sp.theta_hi;
+        const i64 o = o0 + (i64) threadIdx.x * R;
+        if (all0 || all1) {
+            if (o < a.out_hi) {
+                a.out_bits[(o - a.bit_base) >> 3] = all1 ? 0xFF : 0x00;
+            }
+        } else if (o < a.out_hi) {
+            const uint32_t q = atomicAdd(&s_nq, 1u);
+            s_queue[q] = (uint16_t) threadIdx.x;
+        }
+    }
+    __syncthreads();
+
+    const uint32_t nq = s_nq;
+    if (nq == 0) return;
+    if (nq > sp.dense_limit) {
+        if (threadIdx.x == 0) {
+            const uint32_t slot = atomicAdd(sa.dense_count, 1u);
+            sa.dense_list[slot] = tile;
+            atomicAdd(&sa.stat_refined[1], 1u);
+        }
+        return;
+    }
+    if (threadIdx.x == 0) atomicAdd(&sa.stat_refined[0], nq);
+
+    // ---- exact recomputation of the undecided blocks, one output per lane ----
+    for (uint32_t item = threadIdx.x; item < ((nq * R + 31) & ~31u); item += NT) {
+        const uint32_t qi = item >> 3, j = item & 7;
+        bool bit = false;
+        uint32_t blk_t = 0;
+        if (qi < nq) {
+            blk_t = s_queue[qi];
+            const int s_new = (blk_t + HB) * R + j;    // staged index of the newest sample of this output
+            float re = 0.0f, im = 0.0f;
+#pragma unroll
+            for (int i = 0; i < T; i++) {
+                const int s = s_new - i;
+                const float2 x = s_x[s + (s >> 3)];
+                re = mac_exact(re, taps.t[i], x.x);
+                im = mac_exact(im, taps.t[i], x.y);
+            }
+            bit = power_exact(re, im) >= a.pstar;
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);
+        if (qi < nq && j == 0) {
+            const i64 o = o0 + (i64) blk_t * R;
+            a.out_bits[(o - a.bit_base) >> 3] = (uint8_t) (ballot >> (threadIdx.x & 24));
+        }
+    }
+}
+
 }  // namespace ookd

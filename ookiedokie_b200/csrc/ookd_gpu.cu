@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -51,6 +52,8 @@ struct ookd_gpu {
     uint32_t spb = 8192;
     uint32_t chunk_buffers = 64;
     uint32_t flags = 0;
+    bool screen = false;
+    unsigned n_sm = 148;
 
     bool have_sm = false;
     ookd_sm_compiled smc{};
@@ -58,7 +61,7 @@ struct ookd_gpu {
 
     // workspaces
     DevBuf in, bits, inter[2], block_counts, edges, scalars, chunk_exit[2], chunk_ran, slots, slot_count,
-           slot_off, msgs_dev, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
+           slot_off, msgs_dev, dense_list, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
     uint32_t slot_cap = 8;
     void *h_scalars = nullptr;        // pinned, 256 B
     std::vector<ookd_msg> h_msgs;
@@ -74,6 +77,7 @@ struct ookd_gpu {
     uint32_t n_chunks = 0, base_bit = 0;
     int exit_idx = 0;
     uint32_t launches = 0;
+    uint32_t stat_refined_blocks = 0, stat_dense_tiles = 0;
 
     char err[256] = {0};
 };
@@ -144,25 +148,85 @@ void carry_from_dev(const SmCarry &d, ookd_sm_carry &c)
 }
 
 // ---- FIR/threshold over outputs [o_begin, o_end) of the shard (tile-aligned by the caller) ----
+constexpr int TILE_R = 8, TILE_L = 256 * TILE_R;
+
+void make_screen_params(const ookd_gpu *h, ScreenParams &sp)
+{
+    const Stage &st = h->stages[0];
+    double g = 0.0, t2 = 0.0;
+    for (float t : st.taps) {
+        g += (double) t;
+        t2 += (double) t * (double) t;
+    }
+    g = fabs(g);
+    t2 = sqrt(t2);
+    const double u = ldexp(1.0, -24);
+    const double gamma = 2.0 * (st.T + 2) * u;          // 2x the classical (T) u / (1 - T u) bound
+    const double theta = sqrt((double) h->pstar);
+    sp.g_hi = nextafterf((float) (g * (1.0 + 1e-6)), INFINITY);
+    sp.g_lo = nextafterf((float) (g * (1.0 - 1e-6)), 0.0f);
+    sp.t2 = nextafterf((float) (t2 * (1.0 + 1e-6)), INFINITY);
+    sp.cg = nextafterf((float) (gamma * t2 * (1.0 + 1e-6)), INFINITY);
+    sp.theta_lo = nextafterf((float) (theta * (1.0 - 1e-5)), 0.0f);
+    sp.theta_hi = nextafterf((float) (theta * (1.0 + 1e-5)), INFINITY);
+    const int hb = (st.T - 1 + TILE_R - 1) / TILE_R;
+    sp.inv_n = 1.0f / (float) ((hb + 1) * TILE_R);
+    sp.dense_limit = 96;
+}
+
+TiledArgs tiled_args(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
+{
+    TiledArgs a{};
+    a.in = d_in; a.in_base = in_base; a.in_valid_end = in_valid_end;
+    a.out_lo = h->bit_base; a.out_hi = h->out_hi;
+    a.out_bits = (uint8_t *) h->bits.p; a.bit_base = h->bit_base; a.pstar = h->pstar;
+    return a;
+}
+
 int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end, i64 o_begin, i64 o_end)
 {
     if (o_end <= o_begin) return OOKD_OK;
     if (h->path == FIR_TILED_1STAGE_32) {
-        constexpr int R = 8, L = 256 * R;
-        TiledArgs a{};
-        a.in = d_in; a.in_base = in_base; a.in_valid_end = in_valid_end;
-        a.out_lo = o_begin; a.out_hi = o_end;
-        a.out_bits = (uint8_t *) h->bits.p; a.bit_base = h->bit_base; a.pstar = h->pstar;
-        a.tile_list = nullptr; a.tile_count = nullptr;
         TapsParam<32> tp;
         memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
-        const u64 tiles = (u64) (o_end - o_begin + L - 1) / L;
-        fir1_exact_tiled_kernel<32, R><<<(unsigned) tiles, 256, 0, h->s_compute>>>(a, tp);
+        const u64 tiles = (u64) (o_end - o_begin + TILE_L - 1) / TILE_L;
+        const u64 tile0 = (u64) (o_begin - h->bit_base) / TILE_L;
+        if (h->screen) {
+            ScreenArgs sa{};
+            sa.t = tiled_args(h, d_in, in_base, in_valid_end);
+            sa.t.out_hi = o_end;
+            sa.dense_list = (uint32_t *) h->dense_list.p;
+            sa.dense_count = (uint32_t *) ((char *) h->scalars.p + 16);
+            sa.stat_refined = (uint32_t *) ((char *) h->scalars.p + 20);
+            sa.tile_offset = (uint32_t) tile0;
+            ScreenParams sp;
+            make_screen_params(h, sp);
+            fir1_screen_kernel<32><<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, sp, tp);
+        } else {
+            TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
+            a.out_lo = o_begin; a.out_hi = o_end;
+            fir1_exact_tiled_kernel<32, TILE_R><<<(unsigned) tiles, 256, 0, h->s_compute>>>(a, tp);
+        }
         h->launches++;
         CU(h, cudaGetLastError());
         return OOKD_OK;
     }
     return fail(h, OOKD_ERR_STATE, "launch_fir: no tiled path");
+}
+
+// Second pass of the screened path: exact tiled kernel over the tiles the screen gave up on.
+int launch_fir_dense(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
+{
+    if (!(h->path == FIR_TILED_1STAGE_32 && h->screen) || h->out_hi <= h->bit_base) return OOKD_OK;
+    TapsParam<32> tp;
+    memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
+    TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
+    a.tile_list = (const uint32_t *) h->dense_list.p;
+    a.tile_count = (const uint32_t *) ((char *) h->scalars.p + 16);
+    fir1_exact_tiled_kernel<32, TILE_R><<<2 * h->n_sm, 256, 0, h->s_compute>>>(a, tp);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return OOKD_OK;
 }
 
 // ---- shape-agnostic chain: one launch per stage, intermediates in HBM ----
@@ -494,7 +558,7 @@ void ookd_gpu_destroy(ookd_gpu *h)
     if (h->d_tab) cudaFree(h->d_tab);
     DevBuf *all[] = {&h->in, &h->bits, &h->inter[0], &h->inter[1], &h->block_counts, &h->edges, &h->scalars,
                      &h->chunk_exit[0], &h->chunk_exit[1], &h->chunk_ran, &h->slots, &h->slot_count,
-                     &h->slot_off, &h->msgs_dev, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
+                     &h->slot_off, &h->msgs_dev, &h->dense_list, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
                      &h->tab_cnt[1], &h->tab_link, &h->tab_chosen};
     for (DevBuf *b : all) release(*b);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -587,6 +651,11 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
             h->path = FIR_TILED_1STAGE_32;
         }
     }
+    h->n_sm = (unsigned) prop.multiProcessorCount;
+    // the screen needs a finite positive power threshold (thr <= 0 decides 1 everywhere, NaN 0 everywhere;
+    // the exact kernels handle those directly)
+    h->screen = (h->path == FIR_TILED_1STAGE_32) && !(h->flags & OOKD_FLAG_NO_SCREEN) && h->pstar > 0.0f &&
+                h->pstar < 3.0e38f;
 
     // ---- state machine ----
     if (cfg->sm) {
@@ -662,11 +731,15 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     if ((rc = ensure(h, h->bits, (n_bits / 8 + 64 + 8) & ~7ull))) return rc;
 
     CU(h, cudaEventRecord(h->ev_t0, h->s_compute));
+    if (h->screen) {
+        if ((rc = ensure(h, h->dense_list, sizeof(uint32_t) * (n_bits / TILE_L + 2)))) return rc;
+        CU(h, cudaMemsetAsync((char *) h->scalars.p + 16, 0, 12, h->s_compute));
+    }
 
     // ---- input staging + FIR/threshold ----
     const u64 n_have = halo_avail + n_samples;                 // samples present at iq
     const uint32_t *d_in = (const uint32_t *) iq;
-    constexpr u64 TILE = 256 * 8;                              // outputs per tile of the tiled path
+    constexpr u64 TILE = TILE_L;                               // outputs per tile of the tiled path
     CU(h, cudaEventRecord(h->ev_f0, h->s_compute));
     if (!iq_is_device_ptr) {
         if ((rc = ensure(h, h->in, n_have * 4 + 16))) return rc;
@@ -718,6 +791,7 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
                                         (uint32_t *) h->bits.p, h->bit_base))) return rc;
         }
     }
+    if ((rc = launch_fir_dense(h, d_in, in_base, in_valid_end))) return rc;
     CU(h, cudaEventRecord(h->ev_f1, h->s_compute));
 
     // ---- edges ----
@@ -740,12 +814,15 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
         // scalars[0] = total edges; also fetch the first word of decisions for first_bit/base_bit
         CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
         CU(h, cudaMemcpyAsync((char *) h->h_scalars + 8, h->bits.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 16, (char *) h->scalars.p + 16, 12, cudaMemcpyDeviceToHost, h->s_compute));
         CU(h, cudaStreamSynchronize(h->s_compute));
         h->n_edges = ((const u64 *) h->h_scalars)[0];
         const u64 w0 = ((const u64 *) h->h_scalars)[1];
         // decision preceding the shard (or decision 0 itself at the capture start)
         h->base_bit = (uint32_t) ((w0 >> (h->pre ? h->pre - 1 : 0)) & 1);
         if (res) res->first_bit = (uint32_t) ((w0 >> h->pre) & 1);
+        h->stat_refined_blocks = ((const uint32_t *) h->h_scalars)[5];
+        h->stat_dense_tiles = ((const uint32_t *) h->h_scalars)[6];
         if ((rc = ensure(h, h->edges, sizeof(u64) * (h->n_edges + 2)))) return rc;
         if (h->n_edges) {
             ea.edges = (u64 *) h->edges.p;
@@ -772,6 +849,8 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
         res->n_buffers = h->n_buffers;
         res->n_edges = h->n_edges;
         res->gpu_launches = h->launches;
+        res->refined_tiles = h->stat_dense_tiles;
+        res->refined_blocks = h->stat_refined_blocks;
         cudaEventElapsedTime(&res->kernel_ms, h->ev_t0, h->ev_t1);
         cudaEventElapsedTime(&res->fir_ms, h->ev_f0, h->ev_f1);
     }

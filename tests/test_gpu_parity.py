@@ -89,3 +89,59 @@ def test_decode_matches_oracle(devname, filt, n_msgs, sigma, amp, spb, flags):
     assert got["msgs"] == ref["msgs"]
     if sigma <= 0.02 and amp > 0.9:
         assert [m[3] for m in got["msgs"]] == msgs      # clean enough: every transmitted message decodes
+
+
+def _piecewise_capture(rng, n, levels, sigma_lsb, seg=(200, 5000), full_range=False):
+    """Carrier whose amplitude jumps between the given levels (fractions of full scale), random phase,
+    rounded Gaussian noise.  Built with numpy only (no device model needed: decisions/edges are compared)."""
+    amp = np.empty(n, np.float64)
+    pos = 0
+    while pos < n:
+        ln = int(rng.integers(seg[0], seg[1]))
+        amp[pos:pos + ln] = rng.choice(levels)
+        pos += ln
+    ph = rng.uniform(0, 2 * np.pi)
+    i = amp * np.cos(ph) * 2048 + rng.normal(0, sigma_lsb, n)
+    q = amp * np.sin(ph) * 2048 + rng.normal(0, sigma_lsb, n)
+    lim = 32767 if full_range else 2047
+    return np.stack([np.clip(np.rint(i), -lim - 1, lim), np.clip(np.rint(q), -lim - 1, lim)], 1).astype(np.int16)
+
+
+SCREEN_CASES = [
+    # levels, sigma (LSB), threshold, full_range
+    ([0.0, 0.95], 41.0, 0.1, False),                 # the benchmark regime
+    ([0.0, 0.95], 0.0, 0.1, False),                  # clean
+    ([0.0, 0.1, 0.95], 5.0, 0.1, False),             # a level sitting on the threshold
+    ([0.09, 0.1, 0.11, 0.0999, 0.1001], 1.0, 0.1, False),
+    ([0.0, 0.3], 205.0, 0.1, False),                 # low SNR: almost every tile goes to the dense list
+    ([0.0, 0.05, 0.2, 0.5], 20.0, 0.25, False),
+    ([0.0, 4.0, 15.0], 300.0, 0.7, True),            # beyond the 12-bit range
+    ([0.0], 0.0, 0.1, False),                        # all zero
+    ([0.5], 0.0, 0.5, False),                        # constant exactly at the threshold
+]
+
+
+@pytest.mark.parametrize("filt", ["fs32_fs4", "fs64_fs8"])
+@pytest.mark.parametrize("levels,sigma,thr,full", SCREEN_CASES)
+def test_screen_decisions_equal_exact(filt, levels, sigma, thr, full):
+    rng = np.random.default_rng(abs(hash((filt, tuple(levels), sigma, thr))) % (2 ** 32))
+    iq = _piecewise_capture(rng, 300000, levels, sigma, full_range=full)
+    stages = O.load_filter(filt)
+    ref = O.rx(iq, stages, None, threshold_=thr, samples_per_buffer=8192, want_bits=True)
+    for flags in (0, B.FLAG_NO_SCREEN, B.FLAG_FORCE_GENERIC):
+        g = B.Gpu(filter_stages=stages, threshold=thr, samples_per_buffer=8192, flags=flags)
+        got = g.decode(iq)
+        assert np.array_equal(g.bits(), ref["bits"]), (flags, got["refined_blocks"], got["refined_tiles"])
+        fb, edges = g.edges()
+        assert fb == ref["first_bit"] and np.array_equal(edges, ref["edges"])
+
+
+def test_screen_actually_screens():
+    # in the benchmark regime nearly every block must be decided without MACs
+    rng = np.random.default_rng(1)
+    iq = _piecewise_capture(rng, 1 << 20, [0.0, 0.95], 41.0, seg=(1500, 12000))
+    g = B.Gpu(filter_stages=O.load_filter("fs32_fs4"), threshold=0.1)
+    got = g.decode(iq)
+    blocks = (1 << 20) // 8
+    assert got["refined_tiles"] == 0
+    assert got["refined_blocks"] < 0.1 * blocks, got
