@@ -196,39 +196,50 @@ fir1_exact_tiled_kernel(const TiledArgs a, const TapsParam<T> taps)
 
 
 // =======================================================================================
-// 3. Screening kernel, one stage, decimation 1, T <= 32 taps, 8 outputs per thread.
+// 3. Screening kernel, one stage, decimation 1, T = 32 taps, 16 outputs per thread.
 //
 //    The decision the reference takes for output n is  fl(re^2)+fl(im^2) >= P*  on the fp32
 //    in-order sums re, im.  Computing those sums costs 4T flops per sample, which on a B200 is
 //    ~6x more issue slots than the HBM read of the 4-byte sample allows.  But an OOK capture
-//    is mostly "carrier clearly on" or "carrier clearly off", and that can be PROVED per block
-//    of outputs from three sums over the samples S its windows touch (N = |S| = 40):
-//        X = sum x,  Q2 = sum |x|^2,   mu = X/N,   V = Q2 - |X|^2/N = sum |x - mu|^2
-//        y[n] = mu*G + sum_i t_i (x[n-i] - mu),    |sum_i t_i z_i| <= ||t||_2 sqrt(V)   (Cauchy-Schwarz)
-//    so  | |y[n]| - |mu||G| | <= ||t||_2 sqrt(V)  for all 8 outputs of the block, in exact arithmetic.
-//    The reference's rounding moves |y| by at most  gamma ||t||_2 sqrt(Q2)  (gamma ~ (T+1) 2^-24) and
-//    its power by 3 ulp.  With every slack rounded the safe way (ScreenParams, set on the host
-//    in double) the block is decided without a single MAC when the interval misses the
-//    threshold; otherwise its 8 outputs are recomputed with the exact in-order MACs (one output
-//    per lane, compacted through a shared-memory queue so that lanes stay full).  Decisions are
-//    therefore bit-identical to the exact kernel for EVERY input; only the cost is data dependent.
-//    Tiles with too many undecided blocks are handed to fir1_exact_tiled_kernel via tile_list.
+//    is mostly "carrier clearly off" or "carrier clearly on", and both can be PROVED from sums
+//    of the raw integers, without a single MAC:
+//
+//    off:  |y[n]| = |sum_i t_i x[n-i]| <= ||t||_2 sqrt(E_n),  E_n = sum over the T samples of the
+//          window of |x|^2 (Cauchy-Schwarz).  In integer LSB units E_n is EXACT in 32-bit
+//          arithmetic (|I|,|Q| < 4096 is checked), and the reference's rounding moves |y| by at
+//          most gamma ||t||_2 sqrt(E_n) and its power by 3 ulp, so  E_n < K0  (K0 computed on the
+//          host in double, rounded down) implies the reference decides 0.  E_n is formed for
+//          every output from per-thread running prefix sums:
+//              E_n = (tot[t-2] - pre[t-2][j]) + tot[t-1] + pre[t][j]        (16 samples per thread)
+//    on:   for any complex mu,  y[n] = mu G + sum_i t_i (x[n-i] - mu), hence
+//          |y[n]| >= |mu||G| - ||t||_2 sqrt(V),  V = sum over a superset S of the window of
+//          |x-mu|^2 = Q - |X|^2/N for mu = mean over S (S = the 48 samples of threads t-2..t).
+//          If that lower bound, less the rounding allowance, clears the threshold, all 16
+//          outputs of the thread decide 1.
+//
+//    Groups of 8 outputs that neither test settles are recomputed with the exact in-order MACs
+//    (one output per lane, compacted through a shared-memory queue so lanes stay full, samples
+//    re-read through L1/L2).  Decisions are therefore bit-identical to the exact kernel for EVERY
+//    input; only the cost is data dependent.  Tiles with too many undecided groups, or with a
+//    sample outside the 13-bit range the integer sums are sized for, are handed whole to
+//    fir1_exact_tiled_kernel through the dense list.
 // =======================================================================================
 struct ScreenParams {
-    float g_hi, g_lo;        // |sum t_i| rounded up / down
+    uint32_t k0;             // off test: window energy (LSB^2) strictly below this => decision 0
+    float g_lo;              // |sum t_i| rounded down
     float t2;                // ||t||_2 rounded up
     float cg;                // gamma * ||t||_2 rounded up
-    float theta_lo, theta_hi;// sqrt(P*) shrunk / grown by 1e-5
-    float inv_n;             // 1/N
-    uint32_t dense_limit;    // undecided blocks per tile above which the tile goes to the dense list
+    float theta_hi;          // sqrt(P*) * 2048 grown by 1e-5
+    float inv_n;             // 1/48
+    uint32_t dense_limit;    // undecided groups per tile above which the tile goes to the dense list
 };
 
 struct ScreenArgs {
-    TiledArgs t;             // t.tile_list / t.tile_count here are OUTPUT: the dense list + its counter
-    uint32_t *dense_list;
+    TiledArgs t;
+    uint32_t *dense_list;    // OUTPUT: indices of 2048-output tiles for fir1_exact_tiled_kernel
     uint32_t *dense_count;
-    uint32_t *stat_refined;  // [0] blocks refined in place, [1] tiles sent to the dense list
-    uint32_t tile_offset;    // first tile of this launch (tiles are numbered from t.out_lo)
+    uint32_t *stat_refined;  // [0] groups refined in place, [1] tiles sent to the dense list
+    uint32_t tile_offset;    // first (4096-output) tile of this launch, numbered from t.out_lo
 };
 
 __device__ __forceinline__ float sqrt_approx(float x)
@@ -242,116 +253,159 @@ template <int T>
 __global__ void __launch_bounds__(256, 4)
 fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T> taps)
 {
-    constexpr int NT = 256, R = 8, L = NT * R;
-    constexpr int HB = (T - 1 + R - 1) / R;           // history blocks in front of the tile (4 for T=32)
-    constexpr int HALO = HB * R;
-    constexpr int NS = L + HALO;
-    constexpr int NB = NT + HB;                        // blocks with statistics
-    __shared__ float2 s_x[NS + (NS >> 3) + 1];
-    __shared__ float s_sx[NB], s_sy[NB], s_sq[NB];
-    __shared__ uint16_t s_queue[NT];
-    __shared__ uint32_t s_nq;
+    static_assert(T == 32, "window = exactly two 16-sample thread spans");
+    constexpr int NT = 256, SPT = 16, L = NT * SPT;    // 4096 outputs per tile
+    constexpr int HT = 2;                              // history "threads" in front of the tile (32 samples)
+    __shared__ uint4 s_pre[(NT + HT) * 4];             // per thread span: 16 running prefix sums of |x|^2
+    __shared__ int2 s_xy[NT + HT];                     // per thread span: sum I, sum Q
+    __shared__ uint16_t s_queue[2 * NT];
+    __shared__ uint32_t s_nq, s_bad;
 
     const TiledArgs &a = sa.t;
     const uint32_t tile = blockIdx.x + sa.tile_offset;
     const i64 o0 = a.out_lo + (i64) tile * L;
-    const i64 g0 = o0 - HALO;
-    if (threadIdx.x == 0) s_nq = 0;
+    const i64 g0 = o0 - HT * SPT;
+    if (threadIdx.x == 0) { s_nq = 0; s_bad = 0; }
 
-    // ---- load + convert + per-block statistics: thread t owns block t+HB; threads < HB also a halo block ----
     const bool aligned = (((g0 - a.in_base) & 3) == 0) && ((((uintptr_t) a.in) & 15) == 0);
+    const bool interior = aligned && g0 >= a.in_base && g0 >= 0 && (g0 + L + HT * SPT) <= a.in_valid_end;
+
+    // ---- pass over the raw words: running prefix of |x|^2, sums of I and Q, range guard ----
+    uint32_t pre[SPT];
+    int sx = 0, sy = 0;
 #pragma unroll
     for (int pass = 0; pass < 2; pass++) {
-        int blk;
+        int span;
         if (pass == 0) {
-            blk = threadIdx.x + HB;
+            span = threadIdx.x + HT;
         } else {
-            if (threadIdx.x >= HB) break;
-            blk = threadIdx.x;
+            if (threadIdx.x >= HT) break;
+            span = threadIdx.x;
         }
-        const i64 g = g0 + (i64) blk * R;
-        uint32_t w[R];
-        if (aligned && g >= a.in_base && g >= 0 && g + R <= a.in_valid_end) {
-            const uint4 v0 = __ldg((const uint4 *) (a.in + (g - a.in_base)));
-            const uint4 v1 = __ldg((const uint4 *) (a.in + (g - a.in_base) + 4));
-            w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
-            w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+        const i64 g = g0 + (i64) span * SPT;
+        uint32_t w[SPT];
+        if (interior) {
+            const uint4 *src = (const uint4 *) (a.in + (g - a.in_base));
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const uint4 x = __ldg(src + v);
+                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            }
         } else {
 #pragma unroll
-            for (int e = 0; e < R; e++) {
+            for (int e = 0; e < SPT; e++) {
                 const i64 ge = g + e;
                 w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
             }
         }
-        float sx = 0.0f, sy = 0.0f, sq = 0.0f;
-        float2 *dst = &s_x[blk * R + blk];             // s + (s >> 3) with s = blk*8 + e
+        uint32_t run = 0, guard = 0;
+        int xs = 0, ys = 0;
+        uint32_t p[SPT];
 #pragma unroll
-        for (int e = 0; e < R; e++) {
-            const float2 x = sc16q11_to_float2(w[e]);
-            dst[e] = x;
-            sx += x.x;                                 // exact: multiples of 2^-11, |sum| < 2^10
-            sy += x.y;
-            sq = fmaf(x.x, x.x, sq);
-            sq = fmaf(x.y, x.y, sq);
+        for (int e = 0; e < SPT; e++) {
+            const int I = (int) (short) (w[e] & 0xFFFFu);
+            const int Q = ((int) w[e]) >> 16;
+            const uint32_t q = (uint32_t) (I * I) + (uint32_t) (Q * Q);
+            guard |= q;
+            run += q;
+            p[e] = run;
+            xs += I;
+            ys += Q;
         }
-        s_sx[blk] = sx;
-        s_sy[blk] = sy;
-        s_sq[blk] = sq;
+        if (guard >> 25) atomicOr(&s_bad, 1u);          // some |I| or |Q| >= 4096: sums not guaranteed
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            // rotate the four 16-byte chunks by (span >> 1) so that a warp's stores spread over all banks
+            s_pre[span * 4 + ((v + (span >> 1)) & 3)] = make_uint4(p[4 * v], p[4 * v + 1], p[4 * v + 2], p[4 * v + 3]);
+        }
+        s_xy[span] = make_int2(xs, ys);
+        if (pass == 0) {
+#pragma unroll
+            for (int e = 0; e < SPT; e++) pre[e] = p[e];
+            sx = xs; sy = ys;
+        }
     }
     __syncthreads();
 
-    // ---- classify the 8 outputs of block t+HB from the statistics of blocks t .. t+HB ----
-    {
-        float X = 0.0f, Y = 0.0f, Q2 = 0.0f;
+    // ---- decide the 16 outputs of this thread (two groups of 8) ----
+    const int span = threadIdx.x + HT;
+    uint32_t bits16 = 0;
+    bool undecided_lo = false, undecided_hi = false;
+    const i64 o = o0 + (i64) threadIdx.x * SPT;
+    if (s_bad == 0) {
+        uint32_t p2[SPT];
 #pragma unroll
-        for (int d = 0; d <= HB; d++) {
-            X += s_sx[threadIdx.x + d];
-            Y += s_sy[threadIdx.x + d];
-            Q2 += s_sq[threadIdx.x + d];
+        for (int v = 0; v < 4; v++) {
+            const uint4 x = s_pre[(span - 2) * 4 + ((v + ((span - 2) >> 1)) & 3)];
+            p2[4 * v] = x.x; p2[4 * v + 1] = x.y; p2[4 * v + 2] = x.z; p2[4 * v + 3] = x.w;
         }
-        const float m2 = fmaf(X, X, Y * Y);
-        const float mu = sqrt_approx(m2) * sp.inv_n;
-        const float V = fmaxf(fmaf(-m2, sp.inv_n, Q2), 0.0f) + 2e-5f * Q2;
-        const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q2));
-        const bool all0 = (fmaf(mu, sp.g_hi, bc)) * 1.00001f < sp.theta_lo;
-        const bool all1 = (fmaf(mu, sp.g_lo, -bc)) * 0.99999f > sp.theta_hi;
-        const i64 o = o0 + (i64) threadIdx.x * R;
-        if (all0 || all1) {
-            if (o < a.out_hi) {
-                a.out_bits[(o - a.bit_base) >> 3] = all1 ? 0xFF : 0x00;
-            }
-        } else if (o < a.out_hi) {
-            const uint32_t q = atomicAdd(&s_nq, 1u);
-            s_queue[q] = (uint16_t) threadIdx.x;
+        const uint4 last1 = s_pre[(span - 1) * 4 + ((3 + ((span - 1) >> 1)) & 3)];
+        const uint32_t tot1 = last1.w, tot2 = p2[SPT - 1];
+        const uint32_t base = tot2 + tot1;
+        uint32_t emax_lo = 0, emax_hi = 0;
+#pragma unroll
+        for (int j = 0; j < SPT; j++) {
+            const uint32_t e = base - p2[j] + pre[j];   // window of output j: samples (t-2, j+1) .. (t, j)
+            if (j < 8) emax_lo = max(emax_lo, e); else emax_hi = max(emax_hi, e);
         }
+        const bool off_lo = emax_lo < sp.k0, off_hi = emax_hi < sp.k0;
+        bool on = false;
+        if (!(off_lo && off_hi)) {
+            const int2 xy1 = s_xy[span - 1], xy2 = s_xy[span - 2];
+            const float X = (float) (sx + xy1.x + xy2.x), Y = (float) (sy + xy1.y + xy2.y);
+            const float Q = (float) (base + pre[SPT - 1]);
+            const float m2 = fmaf(X, X, Y * Y);
+            const float mu = sqrt_approx(m2) * sp.inv_n;
+            const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
+            const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
+            on = fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi;
+        }
+        if (on) {
+            bits16 = 0xFFFFu;
+        } else {
+            undecided_lo = !off_lo;
+            undecided_hi = !off_hi;
+        }
+    } else {
+        undecided_lo = undecided_hi = true;
+    }
+    if (o < a.out_hi) {
+        // undecided groups are overwritten by the refinement below (or by the dense pass)
+        const i64 byte = (o - a.bit_base) >> 3;
+        a.out_bits[byte] = (uint8_t) bits16;
+        if (o + 8 < a.out_hi) a.out_bits[byte + 1] = (uint8_t) (bits16 >> 8);
+        if (undecided_lo) s_queue[atomicAdd(&s_nq, 1u)] = (uint16_t) (2 * threadIdx.x);
+        if (undecided_hi && o + 8 < a.out_hi) s_queue[atomicAdd(&s_nq, 1u)] = (uint16_t) (2 * threadIdx.x + 1);
     }
     __syncthreads();
 
     const uint32_t nq = s_nq;
     if (nq == 0) return;
-    if (nq > sp.dense_limit) {
+    if (nq > sp.dense_limit || s_bad) {
         if (threadIdx.x == 0) {
-            const uint32_t slot = atomicAdd(sa.dense_count, 1u);
-            sa.dense_list[slot] = tile;
+            const uint32_t slot = atomicAdd(sa.dense_count, 2u);
+            sa.dense_list[slot] = 2 * tile;              // the exact kernel works on 2048-output tiles
+            sa.dense_list[slot + 1] = 2 * tile + 1;
             atomicAdd(&sa.stat_refined[1], 1u);
         }
         return;
     }
     if (threadIdx.x == 0) atomicAdd(&sa.stat_refined[0], nq);
 
-    // ---- exact recomputation of the undecided blocks, one output per lane ----
-    for (uint32_t item = threadIdx.x; item < ((nq * R + 31) & ~31u); item += NT) {
+    // ---- exact recomputation of the undecided groups, one output per lane ----
+    for (uint32_t item = threadIdx.x; item < ((nq * 8 + 31) & ~31u); item += NT) {
         const uint32_t qi = item >> 3, j = item & 7;
         bool bit = false;
-        uint32_t blk_t = 0;
+        uint32_t grp = 0;
         if (qi < nq) {
-            blk_t = s_queue[qi];
-            const int s_new = (blk_t + HB) * R + j;    // staged index of the newest sample of this output
+            grp = s_queue[qi];
+            const i64 n = o0 + (i64) grp * 8 + j;       // output index == index of its newest sample
             float re = 0.0f, im = 0.0f;
 #pragma unroll
             for (int i = 0; i < T; i++) {
-                const int s = s_new - i;
-                const float2 x = s_x[s + (s >> 3)];
+                const i64 g = n - i;
+                const uint32_t w = (g >= 0 && g >= a.in_base && g < a.in_valid_end) ? __ldg(a.in + (g - a.in_base)) : 0u;
+                const float2 x = sc16q11_to_float2(w);
                 re = mac_exact(re, taps.t[i], x.x);
                 im = mac_exact(im, taps.t[i], x.y);
             }
@@ -359,8 +413,8 @@ fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T
         }
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);
         if (qi < nq && j == 0) {
-            const i64 o = o0 + (i64) blk_t * R;
-            a.out_bits[(o - a.bit_base) >> 3] = (uint8_t) (ballot >> (threadIdx.x & 24));
+            const i64 og = o0 + (i64) grp * 8;
+            a.out_bits[(og - a.bit_base) >> 3] = (uint8_t) (ballot >> (threadIdx.x & 24));
         }
     }
 }

@@ -150,6 +150,8 @@ void carry_from_dev(const SmCarry &d, ookd_sm_carry &c)
 // ---- FIR/threshold over outputs [o_begin, o_end) of the shard (tile-aligned by the caller) ----
 constexpr int TILE_R = 8, TILE_L = 256 * TILE_R;
 
+constexpr int SCREEN_L = 4096;          // outputs per tile of the screening kernel
+
 void make_screen_params(const ookd_gpu *h, ScreenParams &sp)
 {
     const Stage &st = h->stages[0];
@@ -161,17 +163,20 @@ void make_screen_params(const ookd_gpu *h, ScreenParams &sp)
     g = fabs(g);
     t2 = sqrt(t2);
     const double u = ldexp(1.0, -24);
-    const double gamma = 2.0 * (st.T + 2) * u;          // 2x the classical (T) u / (1 - T u) bound
-    const double theta = sqrt((double) h->pstar);
-    sp.g_hi = nextafterf((float) (g * (1.0 + 1e-6)), INFINITY);
+    const double gamma = 2.0 * (st.T + 2) * u;          // 2x the classical T u / (1 - T u) bound
+    const double pstar = (double) h->pstar;
+    // off test:  ||t||^2 (1+gamma)^2 (1+3u) E/2048^2 < P*   <=  E < K0
+    double k0 = pstar * 2048.0 * 2048.0 / (t2 * t2 * (1.0 + gamma) * (1.0 + gamma) * (1.0 + 3.0 * u));
+    k0 = floor(k0 * (1.0 - 1e-6));
+    if (k0 < 0.0) k0 = 0.0;
+    if (k0 > 4.0e9) k0 = 4.0e9;
+    sp.k0 = (uint32_t) k0;
     sp.g_lo = nextafterf((float) (g * (1.0 - 1e-6)), 0.0f);
     sp.t2 = nextafterf((float) (t2 * (1.0 + 1e-6)), INFINITY);
     sp.cg = nextafterf((float) (gamma * t2 * (1.0 + 1e-6)), INFINITY);
-    sp.theta_lo = nextafterf((float) (theta * (1.0 - 1e-5)), 0.0f);
-    sp.theta_hi = nextafterf((float) (theta * (1.0 + 1e-5)), INFINITY);
-    const int hb = (st.T - 1 + TILE_R - 1) / TILE_R;
-    sp.inv_n = 1.0f / (float) ((hb + 1) * TILE_R);
-    sp.dense_limit = 96;
+    sp.theta_hi = nextafterf((float) (sqrt(pstar) * 2048.0 * (1.0 + 1e-5)), INFINITY);
+    sp.inv_n = 1.0f / 48.0f;
+    sp.dense_limit = 128;                               // of 512 groups per tile
 }
 
 TiledArgs tiled_args(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
@@ -190,8 +195,9 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
         TapsParam<32> tp;
         memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
         const u64 tiles = (u64) (o_end - o_begin + TILE_L - 1) / TILE_L;
-        const u64 tile0 = (u64) (o_begin - h->bit_base) / TILE_L;
         if (h->screen) {
+            const u64 stiles = (u64) (o_end - o_begin + SCREEN_L - 1) / SCREEN_L;
+            const u64 tile0 = (u64) (o_begin - h->bit_base) / SCREEN_L;
             ScreenArgs sa{};
             sa.t = tiled_args(h, d_in, in_base, in_valid_end);
             sa.t.out_hi = o_end;
@@ -201,7 +207,7 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
             sa.tile_offset = (uint32_t) tile0;
             ScreenParams sp;
             make_screen_params(h, sp);
-            fir1_screen_kernel<32><<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, sp, tp);
+            fir1_screen_kernel<32><<<(unsigned) stiles, 256, 0, h->s_compute>>>(sa, sp, tp);
         } else {
             TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
             a.out_lo = o_begin; a.out_hi = o_end;
@@ -732,14 +738,14 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
 
     CU(h, cudaEventRecord(h->ev_t0, h->s_compute));
     if (h->screen) {
-        if ((rc = ensure(h, h->dense_list, sizeof(uint32_t) * (n_bits / TILE_L + 2)))) return rc;
+        if ((rc = ensure(h, h->dense_list, sizeof(uint32_t) * (n_bits / TILE_L + 4)))) return rc;
         CU(h, cudaMemsetAsync((char *) h->scalars.p + 16, 0, 12, h->s_compute));
     }
 
     // ---- input staging + FIR/threshold ----
     const u64 n_have = halo_avail + n_samples;                 // samples present at iq
     const uint32_t *d_in = (const uint32_t *) iq;
-    constexpr u64 TILE = TILE_L;                               // outputs per tile of the tiled path
+    constexpr u64 TILE = SCREEN_L;                             // piece boundaries: whole tiles of either kernel
     CU(h, cudaEventRecord(h->ev_f0, h->s_compute));
     if (!iq_is_device_ptr) {
         if ((rc = ensure(h, h->in, n_have * 4 + 16))) return rc;
