@@ -371,9 +371,12 @@ fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T
     }
     if (o < a.out_hi) {
         // undecided groups are overwritten by the refinement below (or by the dense pass)
-        const i64 byte = (o - a.bit_base) >> 3;
-        a.out_bits[byte] = (uint8_t) bits16;
-        if (o + 8 < a.out_hi) a.out_bits[byte + 1] = (uint8_t) (bits16 >> 8);
+        const i64 byte = (o - a.bit_base) >> 3;          // even: 16 outputs per thread
+        if (o + 8 < a.out_hi) {
+            *(uint16_t *) (a.out_bits + byte) = (uint16_t) bits16;
+        } else {
+            a.out_bits[byte] = (uint8_t) bits16;
+        }
         if (undecided_lo) s_queue[atomicAdd(&s_nq, 1u)] = (uint16_t) (2 * threadIdx.x);
         if (undecided_hi && o + 8 < a.out_hi) s_queue[atomicAdd(&s_nq, 1u)] = (uint16_t) (2 * threadIdx.x + 1);
     }
@@ -401,13 +404,23 @@ fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T
             grp = s_queue[qi];
             const i64 n = o0 + (i64) grp * 8 + j;       // output index == index of its newest sample
             float re = 0.0f, im = 0.0f;
+            if (n - (T - 1) >= a.in_base && n - (T - 1) >= 0 && n < a.in_valid_end) {
+                const uint32_t *src = a.in + (n - a.in_base);       // whole window present: no per-tap checks
 #pragma unroll
-            for (int i = 0; i < T; i++) {
-                const i64 g = n - i;
-                const uint32_t w = (g >= 0 && g >= a.in_base && g < a.in_valid_end) ? __ldg(a.in + (g - a.in_base)) : 0u;
-                const float2 x = sc16q11_to_float2(w);
-                re = mac_exact(re, taps.t[i], x.x);
-                im = mac_exact(im, taps.t[i], x.y);
+                for (int i = 0; i < T; i++) {
+                    const float2 x = sc16q11_to_float2(__ldg(src - i));
+                    re = mac_exact(re, taps.t[i], x.x);
+                    im = mac_exact(im, taps.t[i], x.y);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < T; i++) {
+                    const i64 g = n - i;
+                    const uint32_t w = (g >= 0 && g >= a.in_base && g < a.in_valid_end) ? __ldg(a.in + (g - a.in_base)) : 0u;
+                    const float2 x = sc16q11_to_float2(w);
+                    re = mac_exact(re, taps.t[i], x.x);
+                    im = mac_exact(im, taps.t[i], x.y);
+                }
             }
             bit = power_exact(re, im) >= a.pstar;
         }

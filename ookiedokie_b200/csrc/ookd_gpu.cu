@@ -326,6 +326,7 @@ SmArgs base_sm_args(ookd_gpu *h, const SmCarry &entry0)
     a.base_bit = h->base_bit;
     a.out_lo = h->out_lo; a.out_hi = h->out_hi;
     a.spb = h->spb; a.dec = h->total_dec;
+    a.opb = (h->spb % h->total_dec == 0) ? h->spb / h->total_dec : 0;
     a.first_buffer = h->first_buffer;
     a.chunk_buffers = h->chunk_buffers;
     a.n_chunks = h->n_chunks;
@@ -451,7 +452,6 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
         a.final_exit = (SmCarry *) ((char *) h->scalars.p + 192);
         CU(h, cudaMemsetAsync(h->scalars.p, 0, 256, h->s_compute));
         CU(h, cudaMemsetAsync(h->tab_cnt[0].p, 0, sizeof(uint32_t) * nc, h->s_compute));
-        const unsigned grid = (unsigned) (((u64) nc * TAB_K + 31) / 32);
         int cur = 0;
         rounds = 0;
         bool table_failed = false;
@@ -471,21 +471,24 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
                     a.cnt_out = (uint32_t *) h->tab_cnt[cur ^ 1].p;
                     cur ^= 1;
                 }
-                sm_table_round_kernel<<<grid, 32, 0, h->s_compute>>>(a);
+                {
+                    const u64 warps = (u64) nc * (rounds == 0 ? 2 : TAB_K);
+                    sm_table_round_kernel<<<(unsigned) ((warps + 3) / 4), 128, 0, h->s_compute>>>(a);
+                }
                 h->launches++;
                 CU(h, cudaGetLastError());
                 rounds++;
             }
             a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
             sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
-            sm_walk_kernel<<<1, 256, 0, h->s_compute>>>(a);
+            sm_walk_kernel<<<1, 1024, 0, h->s_compute>>>(a);
             h->launches += 2;
             CU(h, cudaGetLastError());
             CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
             CU(h, cudaStreamSynchronize(h->s_compute));
             if (*h_overflow == 1) break;                    // message slots too small: grow and redo
             if (h_walk[1] == 1) { resolved = true; break; }
-            if (*h_overflow == 2 || rounds >= 8) { table_failed = true; break; }
+            if (*h_overflow == 2 || rounds >= 16) { table_failed = true; break; }
         }
         if (resolved) break;
         if (*h_overflow == 1) {

@@ -42,6 +42,7 @@ struct SmArgs {
     i64  out_lo, out_hi;      // outputs covered by this shard
     u64  spb;                 // input samples per buffer
     u64  dec;                 // total decimation
+    uint32_t opb;             // outputs per buffer when spb % dec == 0, else 0
     u64  first_buffer;        // buffer index whose first output is out_lo
     uint32_t chunk_buffers;
     uint32_t n_chunks;
@@ -72,12 +73,24 @@ struct SmArgs {
 
 __device__ __forceinline__ i64 first_output_of_buffer(const SmArgs &a, u64 b)
 {
+    if (a.opb) return (i64) (b * a.opb);         // spb is a multiple of the decimation
     return (i64) ((b * a.spb) / a.dec);          // outputs produced by the first b buffers
 }
 
 __device__ __forceinline__ u64 buffer_of_output(const SmArgs &a, i64 m)
 {
     return (((u64) m + 1) * a.dec - 1) / a.spb;   // buffer holding the input that emits m
+}
+
+// First output of the buffer after the one holding output m, given that m lies in [lo, lo + 2^32):
+// 32-bit arithmetic on the offset from a buffer boundary `lo` when buffers hold a whole number of outputs.
+__device__ __forceinline__ i64 next_buffer_start(const SmArgs &a, i64 m, i64 lo)
+{
+    if (a.opb) {
+        const uint32_t rel = (uint32_t) (m - lo);
+        return lo + (i64) ((rel / a.opb + 1) * (u64) a.opb);
+    }
+    return first_output_of_buffer(a, buffer_of_output(a, m) + 1);
 }
 
 __device__ __forceinline__ bool carry_equal(const SmCarry &x, const SmCarry &y)
@@ -248,7 +261,7 @@ __device__ __forceinline__ void sm_emit(SpanOut &o, const SmCarry &s, i64 pos)
 // RESET at pos gets as far as appending a bit / emitting a message (1) or falls back to RESET (0).
 template <bool PROBE>
 __device__ __forceinline__ int sm_run_span(const SmArgs &a, const SmTable &T, SmCarry &s, i64 pos, i64 end,
-                                           u64 e, uint32_t tb, SpanOut &o)
+                                           u64 e, uint32_t tb, SpanOut &o, i64 chunk_lo)
 {
     bool left_reset = false;
     const u64 INF = ~0ull;
@@ -276,7 +289,7 @@ __device__ __forceinline__ int sm_run_span(const SmArgs &a, const SmTable &T, Sm
                 sm_emit(o, s, pos - 1);
             } else if (r < 0) {
                 // device_process gives up on this buffer: resume at the next buffer's first output
-                i64 nb = first_output_of_buffer(a, buffer_of_output(a, pos - 1) + 1);
+                i64 nb = next_buffer_start(a, pos - 1, chunk_lo);
                 if (nb > end) nb = end;
                 if (nb > pos) {
                     if (next_edge < (u64) nb) {
@@ -346,14 +359,19 @@ __device__ __forceinline__ void carry_reset(SmCarry &s, uint32_t prev)
 // ---------------------------------------------------------------------------------------
 #define OOKD_TAB_INVALID 0xFFFFFFFFu      // entry.state of a seed that matches no real entry
 
-__global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
+// One WARP per (chunk, slot); only lane 0 runs the machine.  The work is a chain of dependent
+// steps, so what matters is latency, not lanes: giving every run its own warp keeps runs from
+// serialising each other through divergence (8 runs sharing a warp cost ~8x the latency).
+__global__ void __launch_bounds__(128) sm_table_round_kernel(const SmArgs a)
 {
     __shared__ SmTable T;
     load_table(T, a.tab);
+    if ((threadIdx.x & 31) != 0) return;
 
     const uint32_t K = a.tab_k;
-    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t c = gid / K, j = gid % K;
+    const uint32_t KR = (a.round == 0) ? 2u : K;             // slots launched this round
+    const uint32_t gid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t c = gid / KR, j = gid % KR;
     if (c >= a.n_chunks) return;
 
     i64 start, end;
@@ -387,7 +405,7 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
                 carry_reset(p, 0);
                 SpanOut po;
                 po.slots = nullptr; po.cap = 0; po.n_msgs = 0; po.overflow = nullptr;
-                if (sm_run_span<true>(a, T, p, (i64) a.edges[er], end, er, 0, po)) {
+                if (sm_run_span<true>(a, T, p, (i64) a.edges[er], a.out_hi, er, 0, po, start)) {
                     found = true;
                     break;
                 }
@@ -428,7 +446,7 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
     o.cap = a.slot_cap;
     o.n_msgs = 0;
     o.overflow = a.overflow;
-    sm_run_span<false>(a, T, s, pos, end, e, tb, o);
+    sm_run_span<false>(a, T, s, pos, end, e, tb, o, start);
 
     a.tab_entry[(u64) c * K + slot] = entry;
     a.tab_exit[(u64) c * K + slot] = s;
@@ -453,37 +471,74 @@ __global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
     a.link[(u64) c * K + i] = l;
 }
 
-// One CTA: stage link tiles in shared memory, thread 0 chases the chain from chunk 0 / slot 0.
-__global__ void __launch_bounds__(256) sm_walk_kernel(const SmArgs a)
+// One CTA resolves the chain from chunk 0 / slot 0.  Chasing 1 link per step would serialise
+// n_chunks shared-memory latencies, so links are first composed over segments of SEG chunks (one
+// thread per segment, all K start slots at once), the short chain over segments is walked by one
+// thread, and every thread then replays its own segment from its now-known entry slot.
+__global__ void __launch_bounds__(1024) sm_walk_kernel(const SmArgs a)
 {
-    constexpr uint32_t TILE = 4096;                         // chunks per tile
-    __shared__ uint8_t s_link[TILE * 8];
-    __shared__ uint32_t s_cur, s_done;
-    const uint32_t K = a.tab_k;                              // <= 8
-    if (threadIdx.x == 0) { s_cur = 0; s_done = 0; }
+    constexpr uint32_t SEG = 32;
+    __shared__ uint8_t s_map[1024 * 8];                      // composed map of each segment
+    __shared__ uint8_t s_in[1024];                           // entry slot of each segment (0xFF = unreachable)
+    __shared__ uint32_t s_carry, s_max;
+    const uint32_t K = a.tab_k;                              // == 8 (one 8-byte link row per chunk)
+    if (threadIdx.x == 0) { s_carry = 0; s_max = 0; }
     __syncthreads();
-    for (uint32_t base = 0; base < a.n_chunks; base += TILE) {
-        const uint32_t n = min(TILE, a.n_chunks - base);
-        for (uint32_t i = threadIdx.x; i < n * K; i += blockDim.x) s_link[i] = a.link[(u64) base * K + i];
-        __syncthreads();
-        if (threadIdx.x == 0 && s_done == base) {
-            uint32_t cur = s_cur, c = 0;
-            for (; c < n; c++) {
-                a.chosen[base + c] = (uint8_t) cur;
-                if (base + c + 1 == a.n_chunks) { c++; break; }
-                const uint8_t nx = s_link[c * K + cur];
-                if (nx == 0xFF) { c++; break; }
-                cur = nx;
+    uint32_t done = 0;
+
+    for (uint32_t base = 0; base < a.n_chunks; base += 1024 * SEG) {
+        const uint32_t n_here = min(1024u * SEG, a.n_chunks - base);
+        const uint32_t n_seg = (n_here + SEG - 1) / SEG;
+        const uint32_t sg = threadIdx.x;
+        const uint32_t c_lo = base + sg * SEG, c_hi = min(c_lo + SEG, base + n_here);
+        // compose: m[k] = slot of chunk c_hi reached when chunk c_lo is entered in slot k
+        if (sg < n_seg) {
+            uint32_t m[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) m[k] = (uint32_t) k;
+            for (uint32_t c = c_lo; c < c_hi; c++) {
+                const uint2 lw = *(const uint2 *) (a.link + (u64) c * 8);
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t cur = m[k];
+                    const uint32_t word = (cur < 4) ? lw.x : lw.y;
+                    m[k] = (cur == 0xFF) ? 0xFFu : ((word >> (8 * (cur & 3))) & 0xFFu);
+                }
             }
-            s_cur = cur;
-            s_done = base + c;                               // chunks [0, s_done) have a chosen pair
-            if (c < n) s_done |= 0x80000000u;                // chain broke inside this tile
+#pragma unroll
+            for (int k = 0; k < 8; k++) s_map[sg * 8 + k] = (uint8_t) m[k];
         }
         __syncthreads();
-        if (s_done & 0x80000000u) break;
+        if (threadIdx.x == 0) {
+            uint32_t cur = s_carry, sgi = 0;
+            for (; sgi < n_seg; sgi++) {
+                s_in[sgi] = (uint8_t) cur;
+                const uint32_t nx = s_map[sgi * 8 + cur];
+                if (nx == 0xFF) { sgi++; break; }
+                cur = nx;
+            }
+            for (uint32_t r = sgi; r < n_seg; r++) s_in[r] = 0xFF;
+            s_carry = cur;
+        }
+        __syncthreads();
+        // replay the own segment to record the chosen slot of every chunk
+        if (sg < n_seg && s_in[sg] != 0xFF) {
+            uint32_t cur = s_in[sg], my_done = 0;
+            for (uint32_t c = c_lo; c < c_hi; c++) {
+                a.chosen[c] = (uint8_t) cur;
+                my_done = c + 1;
+                if (c + 1 == a.n_chunks) break;
+                const uint32_t nx = a.link[(u64) c * 8 + cur];
+                if (nx == 0xFF) break;
+                cur = nx;
+            }
+            atomicMax(&s_max, my_done);
+        }
+        __syncthreads();
+        done = s_max;                                        // chunks [0, done) have a chosen pair
+        if (done < base + n_here) break;                     // chain broke: another round is needed
     }
     __syncthreads();
-    const uint32_t done = s_done & 0x7FFFFFFFu;
     if (threadIdx.x == 0) {
         a.walk_status[0] = done;
         a.walk_status[1] = (done == a.n_chunks) ? 1u : 0u;
@@ -541,7 +596,7 @@ __global__ void __launch_bounds__(32) sm_round_kernel(const SmArgs a)
     o.cap = a.slot_cap;
     o.n_msgs = 0;
     o.overflow = a.overflow;
-    sm_run_span<false>(a, T, s, start, end, e, tb, o);
+    sm_run_span<false>(a, T, s, start, end, e, tb, o, start);
 
     a.exit_cur[c] = s;
     a.slot_count[c] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
