@@ -81,6 +81,11 @@ class Msg(C.Structure):
                 ("reserved", C.c_uint32), ("data", C.c_uint8 * MSG_BYTES)]
 
 
+MSG_DTYPE = np.dtype([("out_sample", "<u8"), ("buffer_idx", "<u8"), ("num_bits", "<u4"), ("reserved", "<u4"),
+                      ("data", "u1", (MSG_BYTES,))])
+assert MSG_DTYPE.itemsize == C.sizeof(Msg)
+
+
 class SmCarry(C.Structure):
     _fields_ = [("state", C.c_uint32), ("k", C.c_uint32), ("num_bits", C.c_uint32),
                 ("prev_bit", C.c_uint32), ("data", C.c_uint8 * MSG_BYTES)]
@@ -297,8 +302,16 @@ class Gpu:
             raise OokdError(f"{what}: {lib().ookd_gpu_strerror(rc).decode()} ({lib().ookd_gpu_last_error(self.h).decode()})")
 
     def _result(self, res):
-        msgs = [(int(res.msgs[i].out_sample), int(res.msgs[i].buffer_idx), int(res.msgs[i].num_bits),
-                 bytes(res.msgs[i].data[:self.msg_bytes])) for i in range(res.n_msgs)]
+        # one bulk copy of the message array (56-byte records) instead of per-field ctypes access
+        n = int(res.n_msgs)
+        if n:
+            raw = np.ctypeslib.as_array(C.cast(res.msgs, C.POINTER(C.c_uint8)), shape=(n * C.sizeof(Msg),)).copy()
+            rec = raw.view(MSG_DTYPE)
+            nb = self.msg_bytes
+            msgs = list(zip(rec["out_sample"].tolist(), rec["buffer_idx"].tolist(), rec["num_bits"].tolist(),
+                            [bytes(d[:nb]) for d in rec["data"]]))
+        else:
+            msgs = []
         return dict(n_in=int(res.n_in), n_out=int(res.n_out), n_buffers=int(res.n_buffers),
                     n_edges=int(res.n_edges), msgs=msgs, first_bit=int(res.first_bit),
                     sm_rounds=int(res.sm_rounds), kernel_ms=float(res.kernel_ms), fir_ms=float(res.fir_ms),

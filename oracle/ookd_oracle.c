@@ -209,6 +209,7 @@ struct ookd_oracle_sm {
     uint32_t num_bits;
     int      prev_bit;
     double   elapsed_us;
+    uint32_t k_count;                   /* additions since the last fire (mirror of elapsed_us) */
     uint32_t sample_rate;
 };
 
@@ -259,6 +260,27 @@ void ookd_oracle_sm_destroy(ookd_oracle_sm *sm)
 }
 
 const uint8_t *ookd_oracle_sm_data(const ookd_oracle_sm *sm) { return sm->data; }
+
+/* Snapshot / restore of the streaming state (state_machine.c:57-75), for tests that cut a capture
+ * into shards.  elapsed_us is restored by replaying the k additions that produced it. */
+void ookd_oracle_sm_get_state(const ookd_oracle_sm *sm, uint32_t *state, uint32_t *k, uint32_t *num_bits,
+                              uint32_t *prev_bit, uint8_t *data32)
+{
+    *state = sm->curr; *k = sm->k_count; *num_bits = sm->num_bits; *prev_bit = (uint32_t) sm->prev_bit;
+    memcpy(data32, sm->data, OOKD_ORACLE_MSG_BYTES);
+}
+
+void ookd_oracle_sm_set_state(ookd_oracle_sm *sm, uint32_t state, uint32_t k, uint32_t num_bits,
+                              uint32_t prev_bit, const uint8_t *data32)
+{
+    sm->curr = state; sm->num_bits = num_bits; sm->prev_bit = (int) prev_bit;
+    memcpy(sm->data, data32, OOKD_ORACLE_MSG_BYTES);
+    sm->elapsed_us = 0.0;
+    for (uint32_t i = 0; i < k; i++) {
+        sm->elapsed_us += ((double) 1 / (double) sm->sample_rate) * 1e6;
+    }
+    sm->k_count = k;
+}
 uint32_t ookd_oracle_sm_num_bits(const ookd_oracle_sm *sm) { return sm->num_bits; }
 
 /* state_machine.c:100-133: window is [d-0.15d, d+0.15d] evaluated in double,
@@ -311,6 +333,7 @@ static int oo_eval(ookd_oracle_sm *sm, int b)
 
     if (!fired) {
         sm->elapsed_us += ((double) 1 / (double) sm->sample_rate) * 1e6;   /* :78-82, :514 */
+        sm->k_count++;
         return 0;
     }
 
@@ -348,6 +371,7 @@ static int oo_eval(ookd_oracle_sm *sm, int b)
         sm->curr = 0;
     }
     sm->elapsed_us = 0;
+    sm->k_count = 0;
     return result;
 }
 

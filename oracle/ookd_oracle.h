@@ -87,6 +87,10 @@ void ookd_oracle_sm_destroy(ookd_oracle_sm *sm);
 int ookd_oracle_sm_process(ookd_oracle_sm *sm, const uint8_t *bits, uint32_t count,
                            uint32_t *num_proc);
 const uint8_t *ookd_oracle_sm_data(const ookd_oracle_sm *sm);
+void ookd_oracle_sm_get_state(const ookd_oracle_sm *sm, uint32_t *state, uint32_t *k, uint32_t *num_bits,
+                              uint32_t *prev_bit, uint8_t *data32);
+void ookd_oracle_sm_set_state(ookd_oracle_sm *sm, uint32_t state, uint32_t k, uint32_t num_bits,
+                              uint32_t prev_bit, const uint8_t *data32);
 uint32_t ookd_oracle_sm_num_bits(const ookd_oracle_sm *sm);
 
 /* The whole loop body of ookiedokie_rx (ookiedokie.c:238-290) + bladeRF_file.c:97-126

@@ -77,6 +77,8 @@ def lib():
         L.ookd_oracle_sm_process.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.ookd_oracle_sm_data.restype = C.POINTER(C.c_uint8)
         L.ookd_oracle_sm_data.argtypes = [C.c_void_p]
+        L.ookd_oracle_sm_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.ookd_oracle_sm_set_state.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.ookd_oracle_sm_num_bits.restype = C.c_uint32
         L.ookd_oracle_sm_num_bits.argtypes = [C.c_void_p]
         L.ookd_oracle_rx.restype = C.c_int
@@ -211,6 +213,17 @@ class Sm:
         n = C.c_uint32(0)
         r = lib().ookd_oracle_sm_process(self.h, b.ctypes.data, len(b), C.byref(n))
         return r, n.value
+
+    def get_state(self):
+        """-> carry tuple (state, k, num_bits, prev_bit, data32) in the layout of struct ookd_sm_carry."""
+        st, k, nb, pv = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        data = (C.c_uint8 * MSG_BYTES)()
+        lib().ookd_oracle_sm_get_state(self.h, C.byref(st), C.byref(k), C.byref(nb), C.byref(pv), data)
+        return (st.value, k.value, nb.value, pv.value, bytes(data))
+
+    def set_state(self, carry):
+        data = (C.c_uint8 * MSG_BYTES)(*carry[4])
+        lib().ookd_oracle_sm_set_state(self.h, carry[0], carry[1], carry[2], carry[3], data)
 
     def data(self):
         p = lib().ookd_oracle_sm_data(self.h)

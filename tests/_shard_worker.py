@@ -1,0 +1,75 @@
+"""Worker for tests/test_shard_gloo.py: one rank of the time-shard stitch protocol on CPU (gloo).
+The GPU runner is replaced by a stand-in that steps the CPU oracle's state machine over the shard's
+threshold decisions, buffer by buffer with device_process's drop rule -- the protocol code
+(ookiedokie_b200/shard.py) is the real one."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import oracle as O  # noqa: E402
+from ookiedokie_b200 import shard as S  # noqa: E402
+import ookd_testutil as util  # noqa: E402
+
+
+class OracleShardRunner:
+    def __init__(self, device, sample_rate, bits, out_lo, opb):
+        self.device, self.rate, self.bits, self.out_lo, self.opb = device, sample_rate, bits, out_lo, opb
+        self.calls = []
+
+    def _run(self, entry):
+        sm = O.Sm(self.device, self.rate)
+        if entry is not None:
+            sm.set_state(entry)
+        msgs = []
+        nbytes = (self.device["num_bits"] + 7) // 8
+        for b0 in range(0, len(self.bits), self.opb):
+            buf = self.bits[b0:b0 + self.opb]
+            total, r = 0, 0
+            while total < len(buf) and r != -1:
+                r, n = sm.process(buf[total:])
+                total += n
+                if r == 1:
+                    m = self.out_lo + b0 + total - 1
+                    msgs.append((m, (m + 1 - 1) // self.opb, sm.get_state()[2], sm.data()[:nbytes]))
+        return dict(msgs=msgs), sm.get_state()
+
+    def decode(self, entry):
+        self.calls.append("decode")
+        return self._run(entry)
+
+    def resolve(self, entry):
+        self.calls.append("resolve")
+        return self._run(entry)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    out_path = sys.argv[1]
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    spb = 8192
+    dev = O.load_device("p3l-nexa2012")
+    iq, sent, _ = util.capture(dev, 5, sigma=0.02, phase=0.4, seed=77, fields=util.nexa_fields)
+    stages = O.load_filter("fs32_fs4")
+    full = O.rx(iq, stages, dev, samples_per_buffer=spb, want_bits=True)
+    n_buf = full["n_buffers"]
+    per = (n_buf + world - 1) // world
+    lo, hi = rank * per * spb, min((rank + 1) * per * spb, len(full["bits"]))
+    runner = OracleShardRunner(dev, 3000000, full["bits"][lo:hi], lo, spb)
+    res, exit_c, rounds = S.stitch(runner, rank, world)
+    msgs = S.gather_messages(res["msgs"], rank, world, (dev["num_bits"] + 7) // 8)
+    if rank == 0:
+        ok = [tuple(m) for m in msgs] == [tuple(m) for m in full["msgs"]]
+        json.dump(dict(ok=ok, n=len(msgs), want=len(full["msgs"]), rounds=rounds), open(out_path, "w"))
+    json.dump(dict(calls=runner.calls), open(out_path + f".rank{rank}", "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
