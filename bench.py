@@ -71,15 +71,51 @@ def noise_scale():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region: NVML polled every 5 ms in-process (the same
+    counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; nvidia-smi -lms cannot
+    sample a region shorter than its own start-up), nvidia-smi as the fallback."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
         self.proc = None
+        self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            reasons = [("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                       ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                       ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                       ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+            try:
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            except Exception:
+                mx = 0
+            while not self.stop_flag:
+                try:
+                    sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    try:
+                        mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:
+                        mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    self.rows.append([str(sm), str(mx), "0"] + ["Active" if mask & bit else "Not Active" for _, bit in reasons])
+                except Exception:
+                    break
+                time.sleep(0.005)
+            return
+        self._run_smi()
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -92,6 +128,9 @@ class ClockSampler(threading.Thread):
             pass
 
     def stop(self):
+        self.stop_flag = True
+        if self.nvml is not None:
+            self.join(timeout=1.0)
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
@@ -256,10 +295,12 @@ def main():
             device_ptr=d_iq.data_ptr())
     torch.cuda.synchronize()
 
+    gpu.want_list = False           # keep messages as one structured array; no per-message Python work
+
     def one_step(iq_arg):
         runner = S.GpuShardRunner(gpu, iq_arg, first, n, last)
         res, exit_c, rounds = S.stitch(runner, rank, world)
-        msgs = S.gather_messages(res["msgs"], rank, world, dev.nbytes)
+        msgs = S.gather_messages_raw(res["msgs_raw"], rank, world)
         return res, msgs, runner
 
     dev_arg = (d_iq.data_ptr(), halo_avail + n)
@@ -312,11 +353,11 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dte = float(te.item())
-        d2h = len(res_e["msgs"]) * 56 + 3 * 256 + 48
+        d2h = len(res_e["msgs_raw"]) * 56 + 3 * 256 + 48
         e2e = {"value": world * n / (dte / args.e2e_steps) / 1e6, "unit": UNIT, "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps}
         if rank == 0 and msgs is not None and msgs_e is not None:
-            assert msgs_e == msgs, "host-input decode differs from device-input decode"
+            assert np.array_equal(msgs_e, msgs), "host-input decode differs from device-input decode"
         cpu_prefix = h_iq[halo_avail * 2: (halo_avail + min(n, args.cpu_samples)) * 2].copy() if rank == 0 else None
         B.lib().ookd_gpu_host_free(hptr)
     else:
@@ -328,7 +369,7 @@ def main():
         nc = cpu_prefix.size // 2
         if reference_binary() is not None:
             v, rows = run_reference_cpu(cpu_prefix)
-            n_gpu_rows = sum(1 for m in msgs if (m[0] + 1) <= (nc // SPB) * SPB) if msgs else 0
+            n_gpu_rows = int((msgs["out_sample"] + 1 <= (nc // SPB) * SPB).sum()) if msgs is not None else 0
             cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "host_cores_available": os.cpu_count(),
                    "sample": f"first {nc} samples ({nc * 4 / 2**20:.0f} MiB) of the same capture; "
                              f"{rows} messages (GPU decoded {n_gpu_rows} in the same span)"}

@@ -86,6 +86,12 @@ MSG_DTYPE = np.dtype([("out_sample", "<u8"), ("buffer_idx", "<u8"), ("num_bits",
 assert MSG_DTYPE.itemsize == C.sizeof(Msg)
 
 
+def msgs_to_tuples(rec, nbytes):
+    """Structured message array -> [(out_sample, buffer_idx, num_bits, data bytes)]."""
+    return list(zip(rec["out_sample"].tolist(), rec["buffer_idx"].tolist(), rec["num_bits"].tolist(),
+                    [bytes(d[:nbytes]) for d in rec["data"]]))
+
+
 class SmCarry(C.Structure):
     _fields_ = [("state", C.c_uint32), ("k", C.c_uint32), ("num_bits", C.c_uint32),
                 ("prev_bit", C.c_uint32), ("data", C.c_uint8 * MSG_BYTES)]
@@ -289,6 +295,7 @@ class Gpu:
             self.h = None
             raise OokdError(f"ookd_gpu_create: {L.ookd_gpu_strerror(rc).decode()}")
         self.device_id = device_id
+        self.want_list = True        # build res["msgs"] (list of tuples) besides res["msgs_raw"]
 
     def close(self):
         if getattr(self, "h", None):
@@ -307,12 +314,10 @@ class Gpu:
         if n:
             raw = np.ctypeslib.as_array(C.cast(res.msgs, C.POINTER(C.c_uint8)), shape=(n * C.sizeof(Msg),)).copy()
             rec = raw.view(MSG_DTYPE)
-            nb = self.msg_bytes
-            msgs = list(zip(rec["out_sample"].tolist(), rec["buffer_idx"].tolist(), rec["num_bits"].tolist(),
-                            [bytes(d[:nb]) for d in rec["data"]]))
         else:
-            msgs = []
-        return dict(n_in=int(res.n_in), n_out=int(res.n_out), n_buffers=int(res.n_buffers),
+            rec = np.zeros(0, dtype=MSG_DTYPE)
+        msgs = msgs_to_tuples(rec, self.msg_bytes) if self.want_list else None
+        return dict(msgs_raw=rec, n_in=int(res.n_in), n_out=int(res.n_out), n_buffers=int(res.n_buffers),
                     n_edges=int(res.n_edges), msgs=msgs, first_bit=int(res.first_bit),
                     sm_rounds=int(res.sm_rounds), kernel_ms=float(res.kernel_ms), fir_ms=float(res.fir_ms),
                     gpu_launches=int(res.gpu_launches), refined_tiles=int(res.refined_tiles),

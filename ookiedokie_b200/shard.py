@@ -74,33 +74,36 @@ def stitch(runner, rank, world, guess=None):
 
 def gather_messages(msgs, rank, world, nbytes):
     """msgs: [(out_sample, buffer_idx, num_bits, data)] per rank -> full ordered list on rank 0 (None elsewhere)."""
+    from .binding import MSG_DTYPE, msgs_to_tuples
+    rec = np.zeros(len(msgs), dtype=MSG_DTYPE)
+    for i, (o, b, nb, data) in enumerate(msgs):
+        rec[i]["out_sample"], rec[i]["buffer_idx"], rec[i]["num_bits"] = o, b, nb
+        rec[i]["data"][:len(data)] = np.frombuffer(bytes(data), dtype=np.uint8)
+    out = gather_messages_raw(rec, rank, world)
+    return None if out is None else msgs_to_tuples(out, nbytes)
+
+
+def gather_messages_raw(rec, rank, world):
+    """Structured message arrays (binding.MSG_DTYPE) per rank -> concatenated array on rank 0 (None elsewhere).
+    Two small collectives: the counts, then one padded byte block per rank."""
     if world == 1:
-        return list(msgs)
+        return rec
     dev = _dev()
-    cnt = torch.tensor([len(msgs)], dtype=torch.int64, device=dev)
+    cnt = torch.tensor([len(rec)], dtype=torch.int64, device=dev)
     counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(counts, cnt)
-    counts = [int(c.item()) for c in counts]
+    counts = [int(c) for c in torch.cat(counts).cpu().tolist()]
     cap = max(max(counts), 1)
-    buf = np.zeros((cap, MSG_REC), dtype=np.uint8)
-    for i, (o, b, nb, data) in enumerate(msgs):
-        buf[i, 0:8] = np.frombuffer(np.uint64(o).tobytes(), dtype=np.uint8)
-        buf[i, 8:16] = np.frombuffer(np.uint64(b).tobytes(), dtype=np.uint8)
-        buf[i, 16:20] = np.frombuffer(np.uint32(nb).tobytes(), dtype=np.uint8)
-        buf[i, 20:20 + len(data)] = np.frombuffer(bytes(data), dtype=np.uint8)
+    isz = rec.dtype.itemsize
+    buf = np.zeros(cap * isz, dtype=np.uint8)
+    buf[:len(rec) * isz] = rec.view(np.uint8).reshape(-1)
     mine = torch.from_numpy(buf).to(dev)
     allb = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allb, mine)
     if rank != 0:
         return None
-    out = []
-    for r in range(world):
-        a = allb[r].cpu().numpy()
-        for i in range(counts[r]):
-            rec = a[i].tobytes()
-            out.append((int(np.frombuffer(rec[0:8], dtype=np.uint64)[0]), int(np.frombuffer(rec[8:16], dtype=np.uint64)[0]),
-                        int(np.frombuffer(rec[16:20], dtype=np.uint32)[0]), rec[20:20 + nbytes]))
-    return out
+    parts = [allb[r].cpu().numpy()[:counts[r] * isz].view(rec.dtype) for r in range(world)]
+    return np.concatenate(parts)
 
 
 class GpuShardRunner:
