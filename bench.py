@@ -280,7 +280,7 @@ def main():
     fir = H.Fir(FILTER_NAME)
     dev = H.Device(DEVICE_NAME, FS // fir.total_decimation)
     gpu = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
-                flags=args.flags, sm_chunk_buffers=args.chunk_buffers)
+                flags=args.flags, sm_chunk_buffers=args.chunk_buffers, sm_warmup=1 if world > 1 else 0)
     n = args.samples
     halo = gpu.halo
     first = rank * n
@@ -300,7 +300,7 @@ def main():
     def one_step(iq_arg):
         runner = S.GpuShardRunner(gpu, iq_arg, first, n, last)
         res, exit_c, rounds = S.stitch(runner, rank, world)
-        msgs = S.gather_messages_raw(res["msgs_raw"], rank, world)
+        msgs = S.gather_messages_raw(res["msgs_raw"], rank, world, res.get("_counts"))
         return res, msgs, runner
 
     dev_arg = (d_iq.data_ptr(), halo_avail + n)

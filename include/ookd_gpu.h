@@ -153,6 +153,10 @@ struct ookd_gpu_config {
     int32_t  device_id;                      /* CUDA ordinal; -1 => current device     */
     uint32_t flags;                          /* OOKD_FLAG_*                            */
     uint32_t sm_chunk_buffers;               /* buffers per state-machine work item; 0 => default */
+    uint32_t sm_warmup;                      /* != 0: shards decoded without an entry state also read one
+                                                chunk of history (ookd_gpu_halo() grows accordingly) and
+                                                derive a provisional entry from it, so that multi-GPU time
+                                                shards normally need no second pass (see result.entry_used) */
 };
 
 #define OOKD_FLAG_FORCE_GENERIC  1u          /* always use the shape-agnostic FIR kernels       */
@@ -174,7 +178,9 @@ struct ookd_gpu_result {
     uint32_t refined_tiles;                  /* tiles handed whole to the exact kernel (screen)  */
     uint32_t refined_blocks;                 /* 8-output blocks recomputed exactly inside the
                                                 screening kernel                                  */
-    uint32_t reserved;
+    uint32_t entry_is_provisional;           /* 1: entry_used was derived from the warm-up history and must
+                                                be checked against the previous shard's exit              */
+    struct ookd_sm_carry entry_used;         /* state-machine state the shard was entered with            */
 };
 
 typedef struct ookd_gpu ookd_gpu;

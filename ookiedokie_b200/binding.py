@@ -110,7 +110,7 @@ class SmCarry(C.Structure):
 class GpuConfig(C.Structure):
     _fields_ = [("filter", C.POINTER(FilterDesc)), ("sm", C.POINTER(SmDesc)), ("threshold", C.c_float),
                 ("samples_per_buffer", C.c_uint32), ("device_id", C.c_int32), ("flags", C.c_uint32),
-                ("sm_chunk_buffers", C.c_uint32)]
+                ("sm_chunk_buffers", C.c_uint32), ("sm_warmup", C.c_uint32)]
 
 
 class GpuResult(C.Structure):
@@ -118,7 +118,7 @@ class GpuResult(C.Structure):
                 ("n_edges", C.c_uint64), ("n_msgs", C.c_uint64), ("msgs", C.POINTER(Msg)),
                 ("first_bit", C.c_uint32), ("sm_rounds", C.c_uint32), ("kernel_ms", C.c_float),
                 ("fir_ms", C.c_float), ("gpu_launches", C.c_uint32), ("refined_tiles", C.c_uint32),
-                ("refined_blocks", C.c_uint32), ("reserved", C.c_uint32)]
+                ("refined_blocks", C.c_uint32), ("entry_is_provisional", C.c_uint32), ("entry_used", SmCarry)]
 
 
 def build_library():
@@ -269,7 +269,7 @@ class Gpu:
     """One ookd_gpu handle."""
 
     def __init__(self, filter_stages=None, sm=None, threshold=0.1, samples_per_buffer=8192, device_id=-1,
-                 flags=0, sm_chunk_buffers=0):
+                 flags=0, sm_chunk_buffers=0, sm_warmup=0):
         L = lib()
         cfg = GpuConfig()
         self._keep = []
@@ -289,6 +289,7 @@ class Gpu:
         cfg.device_id = device_id
         cfg.flags = flags
         cfg.sm_chunk_buffers = sm_chunk_buffers
+        cfg.sm_warmup = sm_warmup
         self.h = C.c_void_p()
         rc = L.ookd_gpu_create(C.byref(self.h), C.byref(cfg))
         if rc != 0:
@@ -321,7 +322,8 @@ class Gpu:
                     n_edges=int(res.n_edges), msgs=msgs, first_bit=int(res.first_bit),
                     sm_rounds=int(res.sm_rounds), kernel_ms=float(res.kernel_ms), fir_ms=float(res.fir_ms),
                     gpu_launches=int(res.gpu_launches), refined_tiles=int(res.refined_tiles),
-                    refined_blocks=int(res.refined_blocks))
+                    refined_blocks=int(res.refined_blocks), entry_is_provisional=int(res.entry_is_provisional),
+                    entry_used=res.entry_used.astuple())
 
     @property
     def halo(self):

@@ -47,6 +47,7 @@ struct ookd_gpu {
     uint32_t total_dec = 1;
     uint32_t halo_fir = 0;            // input samples of history the FIR chain needs
     uint32_t halo = 0;                // what callers must provide in front of a shard
+    uint32_t halo_near = 0;           // the part of it the FIR / edge detector need
     FirPath path = FIR_GENERIC;
     float threshold = 0.1f, pstar = 0.0f;
     uint32_t spb = 8192;
@@ -61,8 +62,16 @@ struct ookd_gpu {
 
     // workspaces
     DevBuf in, bits, inter[2], block_counts, edges, scalars, chunk_exit[2], chunk_ran, slots, slot_count,
-           slot_off, msgs_dev, dense_list, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
+           slot_off, msgs_dev, dense_list, final_entry, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
     uint32_t slot_cap = 8;
+    bool tables_valid = false;       // entry/exit tables of the last decode can be extended by resolve
+    int tab_cur = 0;
+    bool warmup = false;             // config: derive provisional entries from one chunk of history
+    u64 warm_in = 0;                 // input samples of that history
+    bool warm = false;               // last decode used it
+    i64 report_lo = 0;               // first output that belongs to the shard (out_lo may start earlier)
+    SmCarry entry_used{};
+    uint32_t first_chunk = 0;
     void *h_scalars = nullptr;        // pinned, 256 B
     std::vector<ookd_msg> h_msgs;
     std::vector<SmMsg> h_msgs_raw;
@@ -297,11 +306,14 @@ constexpr uint32_t TAB_K = 8;
 int finish_messages(ookd_gpu *h, const SmMsg *raw, u64 n_msgs, const SmCarry &last, uint32_t rounds,
                     ookd_sm_carry *exit_, ookd_gpu_result *res)
 {
-    h->h_msgs.resize(n_msgs);
+    h->h_msgs.clear();
+    h->h_msgs.reserve(n_msgs);
     const uint32_t nbytes = (h->smc.max_bits + 7) / 8;
     for (u64 i = 0; i < n_msgs; i++) {
         const SmMsg &m = raw[i];
-        ookd_msg &o = h->h_msgs[i];
+        if ((i64) m.out_sample < h->report_lo) continue;      // completed in the warm-up history: previous shard's
+        h->h_msgs.emplace_back();
+        ookd_msg &o = h->h_msgs.back();
         memset(&o, 0, sizeof(o));
         o.out_sample = m.out_sample;
         o.buffer_idx = ((m.out_sample + 1) * (u64) h->total_dec - 1) / h->spb;
@@ -310,9 +322,11 @@ int finish_messages(ookd_gpu *h, const SmMsg *raw, u64 n_msgs, const SmCarry &la
     }
     if (exit_) carry_from_dev(last, *exit_);
     if (res) {
-        res->n_msgs = n_msgs;
-        res->msgs = n_msgs ? h->h_msgs.data() : nullptr;
+        res->n_msgs = h->h_msgs.size();
+        res->msgs = h->h_msgs.empty() ? nullptr : h->h_msgs.data();
         res->sm_rounds = rounds;
+        carry_from_dev(h->entry_used, res->entry_used);
+        res->entry_is_provisional = (h->warm && h->first_chunk == 0) ? 1u : 0u;
     }
     return OOKD_OK;
 }
@@ -335,6 +349,8 @@ SmArgs base_sm_args(ookd_gpu *h, const SmCarry &entry0)
     a.slot_cap = h->slot_cap;
     a.n_ran = (uint32_t *) ((char *) h->scalars.p + 64);
     a.overflow = (uint32_t *) ((char *) h->scalars.p + 32);
+    a.warm = h->warm ? 1u : 0u;
+    a.first_chunk = 0;
     return a;
 }
 
@@ -409,7 +425,7 @@ int run_state_machine_jacobi(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *
     return fail(h, OOKD_ERR_OVERFLOW, "message slots overflowed after retries");
 }
 
-int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gpu_result *res)
+int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gpu_result *res, bool incremental = false)
 {
     h->h_msgs.clear();
     if (!h->have_sm || h->out_hi <= h->out_lo) {
@@ -432,15 +448,26 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
     if ((rc = ensure(h, h->tab_cnt[1], sizeof(uint32_t) * nc))) return rc;
     if ((rc = ensure(h, h->tab_link, (size_t) nc * TAB_K + 16))) return rc;
     if ((rc = ensure(h, h->tab_chosen, (size_t) nc + 16))) return rc;
+    if ((rc = ensure(h, h->final_entry, sizeof(SmCarry)))) return rc;
 
     const uint32_t *h_overflow = (const uint32_t *) ((const char *) h->h_scalars + 32);
     const uint32_t *h_walk = (const uint32_t *) ((const char *) h->h_scalars + 40);
     uint32_t rounds = 0;
     bool resolved = false;
 
+    if (!(incremental && h->tables_valid)) incremental = false;
+    h->tables_valid = false;
+    // With warm-up history chunk 0 lies in front of the shard.  A decode walks from its anchored seed and
+    // reports the state it reaches at the shard's first output; a resolve (explicit entry) bypasses it.
+    h->first_chunk = (h->warm && incremental) ? 1u : 0u;
+    h->entry_used = entry0;
+
     for (int attempt = 0; attempt < 8 && !resolved; attempt++) {
         if ((rc = ensure(h, h->slots, sizeof(SmMsg) * (size_t) nc * TAB_K * h->slot_cap))) return rc;
         SmArgs a = base_sm_args(h, entry0);
+        a.start_slot = (uint32_t *) ((char *) h->scalars.p + 48);
+        a.first_chunk = h->first_chunk;
+        a.final_entry = (SmCarry *) h->final_entry.p;
         a.tab_k = TAB_K;
         a.tab_entry = (SmCarry *) h->tab_entry.p;
         a.tab_exit = (SmCarry *) h->tab_exit.p;
@@ -451,13 +478,26 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
         a.msg_counts = (uint32_t *) h->slot_count.p;
         a.final_exit = (SmCarry *) ((char *) h->scalars.p + 192);
         CU(h, cudaMemsetAsync(h->scalars.p, 0, 256, h->s_compute));
-        CU(h, cudaMemsetAsync(h->tab_cnt[0].p, 0, sizeof(uint32_t) * nc, h->s_compute));
         int cur = 0;
         rounds = 0;
         bool table_failed = false;
+        if (incremental) {
+            // tables of the previous decode stay; chunk 0 gets the corrected entry
+            cur = h->tab_cur;
+            a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
+            a.cnt_out = (uint32_t *) h->tab_cnt[cur].p;
+            a.round = 1;
+            sm_table_add_entry_kernel<<<1, 32, 0, h->s_compute>>>(a);
+            h->launches++;
+            CU(h, cudaGetLastError());
+            rounds = 1;
+        } else {
+            CU(h, cudaMemsetAsync(h->tab_cnt[0].p, 0, sizeof(uint32_t) * nc, h->s_compute));
+        }
         for (;;) {
-            // round 0 (seeds) and round 1 (predecessors' exits) back to back, later rounds one at a time
-            const uint32_t burst = (rounds == 0) ? 2 : 1;
+            // round 0 (seeds) and round 1 (predecessors' exits) back to back, later rounds one at a time;
+            // an incremental resolve first checks whether the new pair already links up
+            const uint32_t burst = incremental ? ((rounds == 1) ? 0 : 1) : ((rounds == 0) ? 2 : 1);
             for (uint32_t r = 0; r < burst; r++) {
                 a.round = rounds;
                 a.counter_idx = rounds & 31;
@@ -487,15 +527,18 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
             CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
             CU(h, cudaStreamSynchronize(h->s_compute));
             if (*h_overflow == 1) break;                    // message slots too small: grow and redo
-            if (h_walk[1] == 1) { resolved = true; break; }
+            if (h_walk[1] == 1) { resolved = true; h->tab_cur = cur; break; }
             if (*h_overflow == 2 || rounds >= 16) { table_failed = true; break; }
+            if (incremental && rounds == 1) rounds = 2;     // next: ordinary rounds (>= 1 semantics)
         }
         if (resolved) break;
+        incremental = false;                                // anything else: rebuild the tables from scratch
         if (*h_overflow == 1) {
             h->slot_cap *= 4;
             continue;
         }
         if (table_failed) {
+            if (h->warm) return fail(h, OOKD_ERR_STATE, "state machine tables did not resolve; decode this shard with an explicit entry");
             return run_state_machine_jacobi(h, entry0, exit_, res, rounds);
         }
     }
@@ -514,6 +557,10 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
     const u64 n_msgs = ((const u64 *) h->h_scalars)[1];
     SmCarry last;
     memcpy(&last, (const char *) h->h_scalars + 192, sizeof(SmCarry));
+    if (h->warm && h->first_chunk == 0) {
+        CU(h, cudaMemcpyAsync(&h->entry_used, h->final_entry.p, sizeof(SmCarry), cudaMemcpyDeviceToHost, h->s_compute));
+        if (!n_msgs) CU(h, cudaStreamSynchronize(h->s_compute));
+    }
     if (n_msgs) {
         if ((rc = ensure(h, h->msgs_dev, sizeof(SmMsg) * n_msgs))) return rc;
         sm_gather_table_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a, (const uint32_t *) h->slot_off.p,
@@ -524,6 +571,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
                               h->s_compute));
         CU(h, cudaStreamSynchronize(h->s_compute));
     }
+    h->tables_valid = true;
     return finish_messages(h, h->h_msgs_raw.data(), n_msgs, last, rounds, exit_, res);
 }
 
@@ -567,7 +615,7 @@ void ookd_gpu_destroy(ookd_gpu *h)
     if (h->d_tab) cudaFree(h->d_tab);
     DevBuf *all[] = {&h->in, &h->bits, &h->inter[0], &h->inter[1], &h->block_counts, &h->edges, &h->scalars,
                      &h->chunk_exit[0], &h->chunk_exit[1], &h->chunk_ran, &h->slots, &h->slot_count,
-                     &h->slot_off, &h->msgs_dev, &h->dense_list, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
+                     &h->slot_off, &h->msgs_dev, &h->dense_list, &h->final_entry, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
                      &h->tab_cnt[1], &h->tab_link, &h->tab_chosen};
     for (DevBuf *b : all) release(*b);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -604,6 +652,7 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     h->spb = cfg->samples_per_buffer;
     h->flags = cfg->flags;
     h->chunk_buffers = cfg->sm_chunk_buffers ? cfg->sm_chunk_buffers : 64;
+    h->warmup = cfg->sm_warmup != 0;
 
 #define CREATE_FAIL(code)                                                                        \
     do { ookd_gpu_destroy(h); return (code); } while (0)
@@ -653,6 +702,18 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     h->halo_fir = (uint32_t) halo;
     // one extra byte of decisions in front of a shard gives the edge detector its predecessor
     h->halo = (uint32_t) ((halo + 8 * dec + 3) & ~3ull);
+    if (h->warmup && cfg->sm) {
+        // the warm-up history is exactly one chunk, and a chunk must be a whole number of lcm(spb, dec) units
+        const u64 unit = dec / gcd64(h->spb, dec);
+        h->chunk_buffers = (uint32_t) ((h->chunk_buffers + unit - 1) / unit * unit);
+        h->warm_in = (u64) h->chunk_buffers * h->spb;
+        if (h->halo + h->warm_in > 0xFFFFFFFFull) CREATE_FAIL(OOKD_ERR_ARG);
+        h->halo_near = h->halo;
+        h->halo = (uint32_t) (h->halo + h->warm_in);
+    } else {
+        h->warmup = false;
+        h->halo_near = h->halo;
+    }
 
     h->path = FIR_GENERIC;
     if (!(h->flags & OOKD_FLAG_FORCE_GENERIC)) {
@@ -710,6 +771,7 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     if (!iq && n_samples) return fail(h, OOKD_ERR_ARG, "null input");
     CU(h, cudaSetDevice(h->device));
     h->have_last = false;
+    h->tables_valid = false;
     h->h_edges_valid = false;
     h->launches = 0;
     if (res) memset(res, 0, sizeof(*res));
@@ -724,16 +786,20 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     const u64 halo_avail = first_sample < h->halo ? first_sample : h->halo;
     const i64 in_base = (i64) (first_sample - halo_avail);
     const i64 in_valid_end = (i64) (first_sample + n_samples);
-    h->out_lo = (i64) (first_sample / D);
+    // warm-up: without an entry state, start one chunk early and let the state machine find its footing
+    h->warm = h->warmup && h->have_sm && !entry && first_sample >= h->halo;
+    const u64 proc_first = first_sample - (h->warm ? h->warm_in : 0);
+    h->report_lo = (i64) (first_sample / D);
+    h->out_lo = (i64) (proc_first / D);
     h->out_hi = (i64) ((first_sample + n_eff) / D);
     h->pre = (h->out_lo > 0) ? 8 : 0;
     h->bit_base = h->out_lo - h->pre;
-    h->first_buffer = first_sample / spb;
+    h->first_buffer = proc_first / spb;
     h->n_buffers = n_eff / spb;
     h->n_in = n_eff;
     const u64 n_bits = (u64) (h->out_hi - h->bit_base);
-    const u64 n_out = (u64) (h->out_hi - h->out_lo);
-    h->n_chunks = (uint32_t) ((h->n_buffers + h->chunk_buffers - 1) / h->chunk_buffers);
+    const u64 n_out = (u64) (h->out_hi - h->report_lo);
+    h->n_chunks = (uint32_t) (((first_sample + n_eff - proc_first) / spb + h->chunk_buffers - 1) / h->chunk_buffers);
     if (h->n_chunks == 0) h->n_chunks = 1;
 
     int rc;
@@ -747,6 +813,7 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
 
     // ---- input staging + FIR/threshold ----
     const u64 n_have = halo_avail + n_samples;                 // samples present at iq
+    (void) n_out;
     const uint32_t *d_in = (const uint32_t *) iq;
     constexpr u64 TILE = SCREEN_L;                             // piece boundaries: whole tiles of either kernel
     CU(h, cudaEventRecord(h->ev_f0, h->s_compute));
@@ -823,13 +890,15 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
         // scalars[0] = total edges; also fetch the first word of decisions for first_bit/base_bit
         CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
         CU(h, cudaMemcpyAsync((char *) h->h_scalars + 8, h->bits.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 240, (const char *) h->bits.p + (((u64) (h->report_lo - h->bit_base)) >> 6) * 8,
+                              8, cudaMemcpyDeviceToHost, h->s_compute));
         CU(h, cudaMemcpyAsync((char *) h->h_scalars + 16, (char *) h->scalars.p + 16, 12, cudaMemcpyDeviceToHost, h->s_compute));
         CU(h, cudaStreamSynchronize(h->s_compute));
         h->n_edges = ((const u64 *) h->h_scalars)[0];
         const u64 w0 = ((const u64 *) h->h_scalars)[1];
         // decision preceding the shard (or decision 0 itself at the capture start)
         h->base_bit = (uint32_t) ((w0 >> (h->pre ? h->pre - 1 : 0)) & 1);
-        if (res) res->first_bit = (uint32_t) ((w0 >> h->pre) & 1);
+        if (res) res->first_bit = (uint32_t) ((((const u64 *) h->h_scalars)[30] >> ((u64) (h->report_lo - h->bit_base) & 63)) & 1);
         h->stat_refined_blocks = ((const uint32_t *) h->h_scalars)[5];
         h->stat_dense_tiles = ((const uint32_t *) h->h_scalars)[6];
         if ((rc = ensure(h, h->edges, sizeof(u64) * (h->n_edges + 2)))) return rc;
@@ -882,13 +951,13 @@ int ookd_gpu_resolve(ookd_gpu *h, const struct ookd_sm_carry *entry, struct ookd
     carry_to_dev(*entry, e0);
     h->launches = 0;
     CU(h, cudaEventRecord(h->ev_t0, h->s_compute));
-    const int rc = run_state_machine(h, e0, exit_, res);
+    const int rc = run_state_machine(h, e0, exit_, res, true);
     if (rc) return rc;
     CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
     CU(h, cudaEventSynchronize(h->ev_t1));
     if (res) {
         res->n_in = h->n_in;
-        res->n_out = (u64) (h->out_hi - h->out_lo);
+        res->n_out = (u64) (h->out_hi - h->report_lo);
         res->n_buffers = h->n_buffers;
         res->n_edges = h->n_edges;
         res->gpu_launches = h->launches;
@@ -911,15 +980,19 @@ int ookd_gpu_edges(ookd_gpu *h, const uint64_t **edges, uint64_t *n_edges, uint3
         }
         h->h_edges_valid = true;
     }
-    *edges = (const uint64_t *) h->h_edges.data();
-    *n_edges = h->n_edges;
+    // edges inside the warm-up history belong to the previous shard
+    size_t skip = 0;
+    while (skip < h->h_edges.size() && (i64) h->h_edges[skip] < h->report_lo) skip++;
+    *edges = (const uint64_t *) h->h_edges.data() + skip;
+    *n_edges = h->h_edges.size() - skip;
     if (first_bit) {
         // decision of the shard's first output
         u64 w0 = 0;
-        if (h->out_hi > h->bit_base) {
-            CU(h, cudaMemcpy(&w0, h->bits.p, 8, cudaMemcpyDeviceToHost));
+        const u64 b = (u64) (h->report_lo - h->bit_base);
+        if (h->out_hi > h->report_lo) {
+            CU(h, cudaMemcpy(&w0, (const char *) h->bits.p + (b >> 6) * 8, 8, cudaMemcpyDeviceToHost));
         }
-        *first_bit = (uint32_t) ((w0 >> h->pre) & 1);
+        *first_bit = (uint32_t) ((w0 >> (b & 63)) & 1);
     }
     return OOKD_OK;
 }
@@ -929,7 +1002,7 @@ int ookd_gpu_bits(ookd_gpu *h, uint8_t *bits_out, uint64_t max_out, uint64_t *n_
     if (!h || !n_out) return OOKD_ERR_ARG;
     if (!h->have_last) return fail(h, OOKD_ERR_STATE, "no decode yet");
     CU(h, cudaSetDevice(h->device));
-    const u64 n = (u64) (h->out_hi - h->out_lo);
+    const u64 n = (u64) (h->out_hi - h->report_lo);
     *n_out = n;
     if (!bits_out) return OOKD_OK;
     const u64 n_bits = (u64) (h->out_hi - h->bit_base);
@@ -939,7 +1012,7 @@ int ookd_gpu_bits(ookd_gpu *h, uint8_t *bits_out, uint64_t max_out, uint64_t *n_
     }
     const u64 lim = n < max_out ? n : max_out;
     for (u64 i = 0; i < lim; i++) {
-        const u64 b = i + h->pre;
+        const u64 b = i + (u64) (h->report_lo - h->bit_base);
         bits_out[i] = (packed[b >> 3] >> (b & 7)) & 1;
     }
     return OOKD_OK;

@@ -69,6 +69,10 @@ struct SmArgs {
     uint32_t *walk_status;    // [0] = chunks resolved, [1] = 1 if complete
     uint32_t *msg_counts;     // [n_chunks] messages of the chosen pair
     SmCarry  *final_exit;     // exit of the last chunk's chosen pair (written by the walk)
+    uint32_t *start_slot;     // slot of chunk first_chunk the walk starts from
+    uint32_t first_chunk;     // chunk the walk starts at (1 when chunk 0 is a warm-up chunk being bypassed)
+    uint32_t warm;            // chunk 0 is a warm-up chunk in front of the shard: it has no true entry
+    SmCarry  *final_entry;    // warm: state at the shard's first output = exit of chunk 0's chosen pair
 };
 
 __device__ __forceinline__ i64 first_output_of_buffer(const SmArgs &a, u64 b)
@@ -384,7 +388,7 @@ __global__ void __launch_bounds__(128) sm_table_round_kernel(const SmArgs a)
     uint32_t slot;
     if (a.round == 0) {
         if (j >= 2) return;
-        if (c == 0) {
+        if (c == 0 && !a.warm) {
             if (j == 1) return;
             s = a.entry0;
             entry = s;
@@ -417,6 +421,7 @@ __global__ void __launch_bounds__(128) sm_table_round_kernel(const SmArgs a)
             carry_reset(s, 0);
             entry = s;
             entry.state = OOKD_TAB_INVALID;
+            if (c == 0) *a.start_slot = 1;       // warm-up chunk: prefer the anchored run
         }
         slot = j;
         atomicMax(&a.cnt_out[c], j + 1);
@@ -453,6 +458,40 @@ __global__ void __launch_bounds__(128) sm_table_round_kernel(const SmArgs a)
     a.tab_nmsg[(u64) c * K + slot] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
 }
 
+// Resolve: a corrected entry for chunk 0 (the shard's true entry state arrived from the previous
+// shard).  Every other pair of every table stays valid -- pairs are functions of their entry only --
+// so just chunk 0 gains a pair (unless it already has this entry) and the walk restarts from it.
+__global__ void __launch_bounds__(32) sm_table_add_entry_kernel(const SmArgs a)
+{
+    __shared__ SmTable T;
+    load_table(T, a.tab);
+    if (threadIdx.x != 0) return;
+    const uint32_t K = a.tab_k;
+    const uint32_t c = a.first_chunk;
+    const uint32_t n_here = a.cnt_out[c];
+    SmCarry s = a.entry0;
+    for (uint32_t i = 0; i < n_here; i++) {
+        if (carry_equal(s, a.tab_entry[(u64) c * K + i])) { *a.start_slot = i; return; }
+    }
+    if (n_here >= K) { atomicExch(a.overflow, 2u); return; }
+    i64 start, end;
+    chunk_bounds(a, c, start, end);
+    const u64 e = edge_lower_bound(a.edges, a.n_edges, (u64) start);
+    const uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);
+    SpanOut o;
+    o.slots = a.slots + ((u64) c * K + n_here) * a.slot_cap;
+    o.cap = a.slot_cap;
+    o.n_msgs = 0;
+    o.overflow = a.overflow;
+    const SmCarry entry = s;
+    sm_run_span<false>(a, T, s, start, end, e, tb, o, start);
+    a.tab_entry[(u64) c * K + n_here] = entry;
+    a.tab_exit[(u64) c * K + n_here] = s;
+    a.tab_nmsg[(u64) c * K + n_here] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
+    a.cnt_out[c] = n_here + 1;
+    *a.start_slot = n_here;
+}
+
 // link[c][i] = slot of chunk c+1 whose entry equals exit[c][i] (0xFF if none)
 __global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
 {
@@ -482,11 +521,11 @@ __global__ void __launch_bounds__(1024) sm_walk_kernel(const SmArgs a)
     __shared__ uint8_t s_in[1024];                           // entry slot of each segment (0xFF = unreachable)
     __shared__ uint32_t s_carry, s_max;
     const uint32_t K = a.tab_k;                              // == 8 (one 8-byte link row per chunk)
-    if (threadIdx.x == 0) { s_carry = 0; s_max = 0; }
+    if (threadIdx.x == 0) { s_carry = *a.start_slot; s_max = 0; }
     __syncthreads();
     uint32_t done = 0;
 
-    for (uint32_t base = 0; base < a.n_chunks; base += 1024 * SEG) {
+    for (uint32_t base = a.first_chunk; base < a.n_chunks; base += 1024 * SEG) {
         const uint32_t n_here = min(1024u * SEG, a.n_chunks - base);
         const uint32_t n_seg = (n_here + SEG - 1) / SEG;
         const uint32_t sg = threadIdx.x;
@@ -544,10 +583,11 @@ __global__ void __launch_bounds__(1024) sm_walk_kernel(const SmArgs a)
         a.walk_status[1] = (done == a.n_chunks) ? 1u : 0u;
         if (done == a.n_chunks) {
             *a.final_exit = a.tab_exit[(u64) (a.n_chunks - 1) * K + a.chosen[a.n_chunks - 1]];
+            if (a.warm && a.first_chunk == 0) *a.final_entry = a.tab_exit[a.chosen[0]];
         }
     }
     for (uint32_t c = threadIdx.x; c < a.n_chunks; c += blockDim.x) {
-        a.msg_counts[c] = (c < done) ? a.tab_nmsg[(u64) c * K + a.chosen[c]] : 0u;
+        a.msg_counts[c] = (c >= a.first_chunk && c < done) ? a.tab_nmsg[(u64) c * K + a.chosen[c]] : 0u;
     }
 }
 

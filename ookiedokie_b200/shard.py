@@ -41,34 +41,46 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
 
+REC_BYTES = 112         # exit carry (48) | entry used (48) | changed flag (4) | message count (4) | pad (8)
+
+
 def stitch(runner, rank, world, guess=None):
-    """Run the protocol above.  Returns (result, exit, rounds)."""
-    entry_used = None if rank == 0 else (guess if guess is not None else INITIAL_CARRY)
+    """Run the protocol above.  Returns (result, exit, rounds).  One 112-byte all-gather per round; the
+    last round's records also carry every rank's message count (used by gather_messages_raw).
+
+    With handles created with sm_warmup the first decode already enters each shard in the state its own
+    warm-up history leads to (result["entry_used"]); the first gather then only CONFIRMS that every
+    entry equals the predecessor's exit, and no rank runs a second pass."""
+    entry_used = None if rank == 0 else guess
     res, exit_c = runner.decode(entry_used)
     if world == 1:
         return res, exit_c, 1
-    if entry_used is None:
-        entry_used = INITIAL_CARRY
+    entry_used = tuple(res["entry_used"]) if "entry_used" in res else (entry_used or INITIAL_CARRY)
     dev = _dev()
     rounds = 1
+    changed_last = 0
     while True:
-        mine = torch.frombuffer(bytearray(carry_to_bytes(exit_c)), dtype=torch.uint8).to(dev)
-        gathered = [torch.empty(CARRY_BYTES, dtype=torch.uint8, device=dev) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        changed = False
-        true_entry = entry_used
-        if rank > 0:
-            true_entry = carry_from_bytes(gathered[rank - 1].cpu().numpy().tobytes())
-            changed = true_entry != entry_used
-        flag = torch.tensor([1 if changed else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        if int(flag.item()) == 0:
+        n_msgs = len(res["msgs_raw"]) if "msgs_raw" in res else len(res["msgs"])
+        rec = (carry_to_bytes(exit_c) + carry_to_bytes(entry_used) +
+               np.array([changed_last, n_msgs, 0, 0], dtype=np.uint32).tobytes())
+        mine = torch.frombuffer(bytearray(rec), dtype=torch.uint8).to(dev)
+        gathered = torch.empty(world * REC_BYTES, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, mine)
+        g = gathered.cpu().numpy().reshape(world, REC_BYTES)
+        # consistent iff every rank's entry is its predecessor's exit (every rank sees the same records)
+        ok = all(g[r, 48:96].tobytes() == g[r - 1, :48].tobytes() for r in range(1, world))
+        if ok:
+            res["_counts"] = g[:, 100:104].copy().view(np.uint32).reshape(-1).tolist()
             return res, exit_c, rounds
-        if changed:
-            res, exit_c = runner.resolve(true_entry)
-            entry_used = true_entry
+        changed_last = 0
+        if rank > 0:
+            true_entry = carry_from_bytes(g[rank - 1, :48].tobytes())
+            if true_entry != entry_used:
+                res, exit_c = runner.resolve(true_entry)
+                entry_used = true_entry
+                changed_last = 1
         rounds += 1
-        if rounds > world + 2:
+        if rounds > world + 3:
             raise RuntimeError("shard stitch did not converge")
 
 
@@ -83,26 +95,28 @@ def gather_messages(msgs, rank, world, nbytes):
     return None if out is None else msgs_to_tuples(out, nbytes)
 
 
-def gather_messages_raw(rec, rank, world):
+def gather_messages_raw(rec, rank, world, counts=None):
     """Structured message arrays (binding.MSG_DTYPE) per rank -> concatenated array on rank 0 (None elsewhere).
     Two small collectives: the counts, then one padded byte block per rank."""
     if world == 1:
         return rec
     dev = _dev()
-    cnt = torch.tensor([len(rec)], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, cnt)
-    counts = [int(c) for c in torch.cat(counts).cpu().tolist()]
+    if counts is None:
+        cnt = torch.tensor([len(rec)], dtype=torch.int64, device=dev)
+        cl = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(cl, cnt)
+        counts = [int(c) for c in torch.cat(cl).cpu().tolist()]
     cap = max(max(counts), 1)
     isz = rec.dtype.itemsize
     buf = np.zeros(cap * isz, dtype=np.uint8)
     buf[:len(rec) * isz] = rec.view(np.uint8).reshape(-1)
     mine = torch.from_numpy(buf).to(dev)
-    allb = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(allb, mine)
+    allb = torch.empty(world * cap * isz, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allb, mine)
     if rank != 0:
         return None
-    parts = [allb[r].cpu().numpy()[:counts[r] * isz].view(rec.dtype) for r in range(world)]
+    flat = allb.cpu().numpy()
+    parts = [flat[r * cap * isz: r * cap * isz + counts[r] * isz].view(rec.dtype) for r in range(world)]
     return np.concatenate(parts)
 
 

@@ -37,7 +37,7 @@ class OracleShardRunner:
                 if r == 1:
                     m = self.out_lo + b0 + total - 1
                     msgs.append((m, (m + 1 - 1) // self.opb, sm.get_state()[2], sm.data()[:nbytes]))
-        return dict(msgs=msgs), sm.get_state()
+        return dict(msgs=msgs, entry_used=entry if entry is not None else S.INITIAL_CARRY), sm.get_state()
 
     def decode(self, entry):
         self.calls.append("decode")
