@@ -108,7 +108,8 @@ class ClockSampler(threading.Thread):
                         mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                     except Exception:
                         mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                    self.rows.append([str(sm), str(mx), "0"] + ["Active" if mask & bit else "Not Active" for _, bit in reasons])
+                    self.rows.append([str(sm), str(mx), "0"] + ["Active" if mask & bit else "Not Active" for _, bit in reasons]
+                                     + [time.perf_counter()])
                 except Exception:
                     break
                 time.sleep(0.005)
@@ -127,14 +128,19 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def stop(self):
+    def stop(self, t_start=None, t_end=None):
+        """Summary of the samples taken inside [t_start, t_end] (all samples if none fall inside)."""
         self.stop_flag = True
         if self.nvml is not None:
             self.join(timeout=1.0)
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], 0, set()
-        for r in self.rows:
+        rows = self.rows
+        if t_start is not None:
+            inside = [r for r in rows if len(r) > 7 and t_start <= r[7] <= t_end]
+            rows = inside or rows
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -299,15 +305,14 @@ def main():
 
     def one_step(iq_arg):
         runner = S.GpuShardRunner(gpu, iq_arg, first, n, last)
-        res, exit_c, rounds = S.stitch(runner, rank, world)
-        msgs = S.gather_messages_raw(res["msgs_raw"], rank, world, res.get("_counts"))
+        res, exit_c, rounds, msgs = S.stitch_and_gather(runner, rank, world)
         return res, msgs, runner
 
     dev_arg = (d_iq.data_ptr(), halo_avail + n)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                 # started before the warm-up so that it is sampling when the timed region begins
     for _ in range(args.warmup):
         one_step(dev_arg)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     t0 = time.perf_counter()
     launches = 0
@@ -319,8 +324,9 @@ def main():
         fir_ms += runner.fir_ms
         kernel_ms += runner.kernel_ms
     barrier()
-    dt = time.perf_counter() - t0
-    clocks = sampler.stop()
+    t1 = time.perf_counter()
+    dt = t1 - t0
+    clocks = sampler.stop(t0, t1)
     t = torch.tensor([dt, fir_ms, kernel_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

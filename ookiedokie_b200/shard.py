@@ -44,6 +44,41 @@ def _dev():
 REC_BYTES = 112         # exit carry (48) | entry used (48) | changed flag (4) | message count (4) | pad (8)
 
 
+def stitch_and_gather(runner, rank, world, msg_cap=4096):
+    """stitch() + gather_messages_raw() with ONE collective in the common case: every rank ships its
+    carry record together with its (padded) message block; if the records are consistent the job is done.
+    Returns (result, exit, rounds, messages on rank 0 | None)."""
+    from .binding import MSG_DTYPE
+    res, exit_c = runner.decode(None)
+    if world == 1:
+        return res, exit_c, 1, res["msgs_raw"]
+    entry_used = tuple(res["entry_used"])
+    dev = _dev()
+    isz = MSG_DTYPE.itemsize
+    rec = res["msgs_raw"]
+    if len(rec) <= msg_cap:
+        buf = np.zeros(REC_BYTES + msg_cap * isz, dtype=np.uint8)
+        buf[:REC_BYTES] = np.frombuffer(carry_to_bytes(exit_c) + carry_to_bytes(entry_used) +
+                                        np.array([0, len(rec), 0, 0], dtype=np.uint32).tobytes(), dtype=np.uint8)
+        buf[REC_BYTES:REC_BYTES + len(rec) * isz] = rec.view(np.uint8).reshape(-1)
+        mine = torch.from_numpy(buf).to(dev)
+        allb = torch.empty(world * buf.size, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allb, mine)
+        g = allb.cpu().numpy().reshape(world, buf.size)
+        counts = g[:, 100:104].copy().view(np.uint32).reshape(-1).tolist()
+        ok = all(g[r, 48:96].tobytes() == g[r - 1, :48].tobytes() for r in range(1, world)) and max(counts) <= msg_cap
+        if ok:
+            msgs = None
+            if rank == 0:
+                msgs = np.concatenate([g[r, REC_BYTES:REC_BYTES + counts[r] * isz].copy().view(MSG_DTYPE)
+                                       for r in range(world)])
+            return res, exit_c, 1, msgs
+    # inconsistent entries (or an oversized message list): fall back to the round protocol
+    res, exit_c, rounds = _stitch_rounds(runner, rank, world, res, exit_c, entry_used, dev)
+    msgs = gather_messages_raw(res["msgs_raw"], rank, world, res.get("_counts"))
+    return res, exit_c, rounds + 1, msgs
+
+
 def stitch(runner, rank, world, guess=None):
     """Run the protocol above.  Returns (result, exit, rounds).  One 112-byte all-gather per round; the
     last round's records also carry every rank's message count (used by gather_messages_raw).
@@ -56,7 +91,10 @@ def stitch(runner, rank, world, guess=None):
     if world == 1:
         return res, exit_c, 1
     entry_used = tuple(res["entry_used"]) if "entry_used" in res else (entry_used or INITIAL_CARRY)
-    dev = _dev()
+    return _stitch_rounds(runner, rank, world, res, exit_c, entry_used, _dev())
+
+
+def _stitch_rounds(runner, rank, world, res, exit_c, entry_used, dev):
     rounds = 1
     changed_last = 0
     while True:
