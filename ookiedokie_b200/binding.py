@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libookd_gpu.so")
+LIB_PATH = os.environ.get("OOKD_GPU_LIB") or os.path.join(_HERE, "lib", "libookd_gpu.so")
 
 MAX_STAGES = 8
 MSG_BYTES = 32

@@ -219,10 +219,11 @@ fir1_exact_tiled_kernel(const TiledArgs a, const TapsParam<T> taps)
 //
 //    Groups of 8 outputs that neither test settles are recomputed with the exact in-order MACs
 //    (one output per lane, compacted through a shared-memory queue so lanes stay full, samples
-//    re-read through L1/L2).  Decisions are therefore bit-identical to the exact kernel for EVERY
-//    input; only the cost is data dependent.  Tiles with too many undecided groups, or with a
-//    sample outside the 13-bit range the integer sums are sized for, are handed whole to
-//    fir1_exact_tiled_kernel through the dense list.
+//    re-read through L1/L2) by fir1_refine_kernel from a global work list.  Decisions are therefore
+//    bit-identical to the exact kernel for EVERY input; only the cost is data dependent.  Spans
+//    holding a sample outside the range the 32-bit sums are sized for are simply left undecided.
+//    If more groups are undecided than the work list holds (low-SNR captures), the host redoes the
+//    range with fir1_exact_tiled_kernel and stops screening on that handle.
 // =======================================================================================
 struct ScreenParams {
     uint32_t k0;             // off test: window energy (LSB^2) strictly below this => decision 0
@@ -231,14 +232,13 @@ struct ScreenParams {
     float cg;                // gamma * ||t||_2 rounded up
     float theta_hi;          // sqrt(P*) * 2048 grown by 1e-5
     float inv_n;             // 1/48
-    uint32_t dense_limit;    // undecided groups per tile above which the tile goes to the dense list
 };
 
 struct ScreenArgs {
     TiledArgs t;
-    uint32_t *dense_list;    // OUTPUT: indices of 2048-output tiles for fir1_exact_tiled_kernel
-    uint32_t *dense_count;
-    uint32_t *stat_refined;  // [0] groups refined in place, [1] tiles sent to the dense list
+    uint32_t *work_list;     // OUTPUT: indices of 8-output groups (relative to t.bit_base) left to the exact path
+    uint32_t *work_count;    // number of groups pushed (may exceed work_cap: then the host redoes the range exactly)
+    uint32_t work_cap;
     uint32_t tile_offset;    // first (4096-output) tile of this launch, numbered from t.out_lo
 };
 
@@ -249,29 +249,52 @@ __device__ __forceinline__ float sqrt_approx(float x)
     return r;
 }
 
+#ifndef OOKD_SCREEN_MINB
+#define OOKD_SCREEN_MINB 5
+#endif
+
+// prefix sums / sums / range guard of one 16-sample span
+__device__ __forceinline__ void screen_span_stats(const uint32_t (&w)[16], uint32_t (&pre)[16], int &sx, int &sy,
+                                                  uint32_t &guard)
+{
+    uint32_t run = 0;
+    int xs = 0, ys = 0;
+    guard = 0;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int I = (int) (short) (w[e] & 0xFFFFu);
+        const int Q = ((int) w[e]) >> 16;
+        const uint32_t q = (uint32_t) (I * I) + (uint32_t) (Q * Q);
+        guard |= q;
+        run += q;
+        pre[e] = run;
+        xs += I;
+        ys += Q;
+    }
+    sx = xs;
+    sy = ys;
+}
+
 template <int T>
-__global__ void __launch_bounds__(256, 4)
-fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T> taps)
+__global__ void __launch_bounds__(256, OOKD_SCREEN_MINB)
+fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp)
 {
     static_assert(T == 32, "window = exactly two 16-sample thread spans");
     constexpr int NT = 256, SPT = 16, L = NT * SPT;    // 4096 outputs per tile
-    constexpr int HT = 2;                              // history "threads" in front of the tile (32 samples)
-    __shared__ uint4 s_pre[(NT + HT) * 4];             // per thread span: 16 running prefix sums of |x|^2
-    __shared__ int2 s_xy[NT + HT];                     // per thread span: sum I, sum Q
-    __shared__ uint16_t s_queue[2 * NT];
-    __shared__ uint32_t s_nq, s_bad;
+    constexpr int HT = 2;                              // history spans in front of the tile (32 samples)
+    __shared__ uint4 s_pre[(NT + HT) * 4];             // per span: 16 running prefix sums of |x|^2 (chunk-rotated)
+    __shared__ int2 s_xy[NT + HT];                     // per span: sum I, sum Q
+    __shared__ uint8_t s_flag[NT + HT];                // per span: some |x|^2 >= 2^25 (32-bit sums not guaranteed)
 
     const TiledArgs &a = sa.t;
     const uint32_t tile = blockIdx.x + sa.tile_offset;
     const i64 o0 = a.out_lo + (i64) tile * L;
     const i64 g0 = o0 - HT * SPT;
-    if (threadIdx.x == 0) { s_nq = 0; s_bad = 0; }
-
-    const bool aligned = (((g0 - a.in_base) & 3) == 0) && ((((uintptr_t) a.in) & 15) == 0);
-    const bool interior = aligned && g0 >= a.in_base && g0 >= 0 && (g0 + L + HT * SPT) <= a.in_valid_end;
+    const bool fast = ((((uintptr_t) a.in) & 15) == 0) && (((g0 - a.in_base) & 3) == 0) && g0 >= a.in_base && g0 >= 0 &&
+                      (g0 + L + HT * SPT) <= a.in_valid_end;
 
     // ---- pass over the raw words: running prefix of |x|^2, sums of I and Q, range guard ----
-    uint32_t pre[SPT];
+    uint32_t pre[SPT], guard = 0;
     int sx = 0, sy = 0;
 #pragma unroll
     for (int pass = 0; pass < 2; pass++) {
@@ -284,7 +307,7 @@ fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T
         }
         const i64 g = g0 + (i64) span * SPT;
         uint32_t w[SPT];
-        if (interior) {
+        if (fast) {
             const uint4 *src = (const uint4 *) (a.in + (g - a.in_base));
 #pragma unroll
             for (int v = 0; v < 4; v++) {
@@ -298,31 +321,20 @@ fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T
                 w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
             }
         }
-        uint32_t run = 0, guard = 0;
-        int xs = 0, ys = 0;
-        uint32_t p[SPT];
-#pragma unroll
-        for (int e = 0; e < SPT; e++) {
-            const int I = (int) (short) (w[e] & 0xFFFFu);
-            const int Q = ((int) w[e]) >> 16;
-            const uint32_t q = (uint32_t) (I * I) + (uint32_t) (Q * Q);
-            guard |= q;
-            run += q;
-            p[e] = run;
-            xs += I;
-            ys += Q;
-        }
-        if (guard >> 25) atomicOr(&s_bad, 1u);          // some |I| or |Q| >= 4096: sums not guaranteed
+        uint32_t p[SPT], gd;
+        int xs, ys;
+        screen_span_stats(w, p, xs, ys, gd);
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             // rotate the four 16-byte chunks by (span >> 1) so that a warp's stores spread over all banks
             s_pre[span * 4 + ((v + (span >> 1)) & 3)] = make_uint4(p[4 * v], p[4 * v + 1], p[4 * v + 2], p[4 * v + 3]);
         }
         s_xy[span] = make_int2(xs, ys);
+        s_flag[span] = (gd >> 25) ? 1 : 0;
         if (pass == 0) {
 #pragma unroll
             for (int e = 0; e < SPT; e++) pre[e] = p[e];
-            sx = xs; sy = ys;
+            sx = xs; sy = ys; guard = gd;
         }
     }
     __syncthreads();
@@ -332,20 +344,21 @@ fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T
     uint32_t bits16 = 0;
     bool undecided_lo = false, undecided_hi = false;
     const i64 o = o0 + (i64) threadIdx.x * SPT;
-    if (s_bad == 0) {
+    const bool bad = (guard >> 25) || s_flag[span - 1] || s_flag[span - 2];
+    if (!bad) {
         uint32_t p2[SPT];
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             const uint4 x = s_pre[(span - 2) * 4 + ((v + ((span - 2) >> 1)) & 3)];
             p2[4 * v] = x.x; p2[4 * v + 1] = x.y; p2[4 * v + 2] = x.z; p2[4 * v + 3] = x.w;
         }
-        const uint4 last1 = s_pre[(span - 1) * 4 + ((3 + ((span - 1) >> 1)) & 3)];
-        const uint32_t tot1 = last1.w, tot2 = p2[SPT - 1];
+        const uint32_t tot1 = s_pre[(span - 1) * 4 + ((3 + ((span - 1) >> 1)) & 3)].w, tot2 = p2[SPT - 1];
         const uint32_t base = tot2 + tot1;
+        // window of output j: samples (t-2, j+1) .. (t, j):  E_j = base + pre[j] - p2[j]   (exact in u32)
         uint32_t emax_lo = 0, emax_hi = 0;
 #pragma unroll
         for (int j = 0; j < SPT; j++) {
-            const uint32_t e = base - p2[j] + pre[j];   // window of output j: samples (t-2, j+1) .. (t, j)
+            const uint32_t e = base + pre[j] - p2[j];
             if (j < 8) emax_lo = max(emax_lo, e); else emax_hi = max(emax_hi, e);
         }
         const bool off_lo = emax_lo < sp.k0, off_hi = emax_hi < sp.k0;
@@ -369,43 +382,58 @@ fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T
     } else {
         undecided_lo = undecided_hi = true;
     }
-    if (o < a.out_hi) {
-        // undecided groups are overwritten by the refinement below (or by the dense pass)
-        const i64 byte = (o - a.bit_base) >> 3;          // even: 16 outputs per thread
-        if (o + 8 < a.out_hi) {
+    const bool in_lo = o < a.out_hi, in_hi = o + 8 < a.out_hi;
+    if (in_lo) {
+        // undecided groups are overwritten by fir1_refine_kernel
+        const i64 byte = (o - a.bit_base) >> 3;              // even: 16 outputs per thread
+        if (in_hi) {
             *(uint16_t *) (a.out_bits + byte) = (uint16_t) bits16;
         } else {
             a.out_bits[byte] = (uint8_t) bits16;
         }
-        if (undecided_lo) s_queue[atomicAdd(&s_nq, 1u)] = (uint16_t) (2 * threadIdx.x);
-        if (undecided_hi && o + 8 < a.out_hi) s_queue[atomicAdd(&s_nq, 1u)] = (uint16_t) (2 * threadIdx.x + 1);
     }
-    __syncthreads();
-
-    const uint32_t nq = s_nq;
-    if (nq == 0) return;
-    if (nq > sp.dense_limit || s_bad) {
-        if (threadIdx.x == 0) {
-            const uint32_t slot = atomicAdd(sa.dense_count, 2u);
-            sa.dense_list[slot] = 2 * tile;              // the exact kernel works on 2048-output tiles
-            sa.dense_list[slot + 1] = 2 * tile + 1;
-            atomicAdd(&sa.stat_refined[1], 1u);
+    // ---- undecided groups -> global work list (warp-aggregated reservation, no CTA barrier) ----
+    const bool push_lo = undecided_lo && in_lo, push_hi = undecided_hi && in_hi;
+    const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, push_lo), m_hi = __ballot_sync(0xFFFFFFFFu, push_hi);
+    const uint32_t n_push = __popc(m_lo) + __popc(m_hi);
+    if (n_push) {
+        const int lane = threadIdx.x & 31;
+        uint32_t slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(sa.work_count, n_push);
+        slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+        const uint32_t below = (1u << lane) - 1;
+        const uint32_t grp0 = (uint32_t) ((o - a.bit_base) >> 3);
+        if (push_lo) {
+            const uint32_t s = slot0 + __popc(m_lo & below);
+            if (s < sa.work_cap) sa.work_list[s] = grp0;
         }
-        return;
+        if (push_hi) {
+            const uint32_t s = slot0 + __popc(m_lo) + __popc(m_hi & below);
+            if (s < sa.work_cap) sa.work_list[s] = grp0 + 1;
+        }
     }
-    if (threadIdx.x == 0) atomicAdd(&sa.stat_refined[0], nq);
+}
 
-    // ---- exact recomputation of the undecided groups, one output per lane ----
-    for (uint32_t item = threadIdx.x; item < ((nq * 8 + 31) & ~31u); item += NT) {
-        const uint32_t qi = item >> 3, j = item & 7;
+// Exact recomputation of the groups the screen left undecided: one output per lane (8 lanes per group),
+// samples re-read through L1/L2.  Grid-stride over the global work list, so lanes stay full whatever the
+// distribution of undecided groups over the capture.
+template <int T>
+__global__ void __launch_bounds__(256) fir1_refine_kernel(const ScreenArgs sa, const TapsParam<T> taps)
+{
+    const TiledArgs &a = sa.t;
+    const uint32_t n_groups = min(*sa.work_count, sa.work_cap);
+    const u64 n_items = ((u64) n_groups * 8 + 31) & ~31ull;
+    for (u64 item = (u64) blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (u64) gridDim.x * blockDim.x) {
+        const u64 qi = item >> 3;
+        const uint32_t j = (uint32_t) (item & 7);
         bool bit = false;
         uint32_t grp = 0;
-        if (qi < nq) {
-            grp = s_queue[qi];
-            const i64 n = o0 + (i64) grp * 8 + j;       // output index == index of its newest sample
+        if (qi < n_groups) {
+            grp = sa.work_list[qi];
+            const i64 n = a.bit_base + (i64) grp * 8 + j;    // output index == index of its newest sample
             float re = 0.0f, im = 0.0f;
             if (n - (T - 1) >= a.in_base && n - (T - 1) >= 0 && n < a.in_valid_end) {
-                const uint32_t *src = a.in + (n - a.in_base);       // whole window present: no per-tap checks
+                const uint32_t *src = a.in + (n - a.in_base);   // whole window present: no per-tap checks
 #pragma unroll
                 for (int i = 0; i < T; i++) {
                     const float2 x = sc16q11_to_float2(__ldg(src - i));
@@ -425,9 +453,8 @@ fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp, const TapsParam<T
             bit = power_exact(re, im) >= a.pstar;
         }
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);
-        if (qi < nq && j == 0) {
-            const i64 og = o0 + (i64) grp * 8;
-            a.out_bits[(og - a.bit_base) >> 3] = (uint8_t) (ballot >> (threadIdx.x & 24));
+        if (qi < n_groups && j == 0) {
+            a.out_bits[grp] = (uint8_t) (ballot >> (threadIdx.x & 24));
         }
     }
 }

@@ -87,6 +87,7 @@ struct ookd_gpu {
     int exit_idx = 0;
     uint32_t launches = 0;
     uint32_t stat_refined_blocks = 0, stat_dense_tiles = 0;
+    uint32_t work_cap = 0;
 
     char err[256] = {0};
 };
@@ -185,7 +186,6 @@ void make_screen_params(const ookd_gpu *h, ScreenParams &sp)
     sp.cg = nextafterf((float) (gamma * t2 * (1.0 + 1e-6)), INFINITY);
     sp.theta_hi = nextafterf((float) (sqrt(pstar) * 2048.0 * (1.0 + 1e-5)), INFINITY);
     sp.inv_n = 1.0f / 48.0f;
-    sp.dense_limit = 128;                               // of 512 groups per tile
 }
 
 TiledArgs tiled_args(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
@@ -195,6 +195,16 @@ TiledArgs tiled_args(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_vali
     a.out_lo = h->bit_base; a.out_hi = h->out_hi;
     a.out_bits = (uint8_t *) h->bits.p; a.bit_base = h->bit_base; a.pstar = h->pstar;
     return a;
+}
+
+ScreenArgs screen_args(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
+{
+    ScreenArgs sa{};
+    sa.t = tiled_args(h, d_in, in_base, in_valid_end);
+    sa.work_list = (uint32_t *) h->dense_list.p;
+    sa.work_count = (uint32_t *) ((char *) h->scalars.p + 16);
+    sa.work_cap = h->work_cap;
+    return sa;
 }
 
 int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end, i64 o_begin, i64 o_end)
@@ -207,16 +217,12 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
         if (h->screen) {
             const u64 stiles = (u64) (o_end - o_begin + SCREEN_L - 1) / SCREEN_L;
             const u64 tile0 = (u64) (o_begin - h->bit_base) / SCREEN_L;
-            ScreenArgs sa{};
-            sa.t = tiled_args(h, d_in, in_base, in_valid_end);
+            ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
             sa.t.out_hi = o_end;
-            sa.dense_list = (uint32_t *) h->dense_list.p;
-            sa.dense_count = (uint32_t *) ((char *) h->scalars.p + 16);
-            sa.stat_refined = (uint32_t *) ((char *) h->scalars.p + 20);
             sa.tile_offset = (uint32_t) tile0;
             ScreenParams sp;
             make_screen_params(h, sp);
-            fir1_screen_kernel<32><<<(unsigned) stiles, 256, 0, h->s_compute>>>(sa, sp, tp);
+            fir1_screen_kernel<32><<<(unsigned) stiles, 256, 0, h->s_compute>>>(sa, sp);
         } else {
             TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
             a.out_lo = o_begin; a.out_hi = o_end;
@@ -229,16 +235,27 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
     return fail(h, OOKD_ERR_STATE, "launch_fir: no tiled path");
 }
 
-// Second pass of the screened path: exact tiled kernel over the tiles the screen gave up on.
-int launch_fir_dense(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
+// Second pass of the screened path: exact recomputation of the groups the screen left undecided.
+int launch_fir_refine(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
 {
     if (!(h->path == FIR_TILED_1STAGE_32 && h->screen) || h->out_hi <= h->bit_base) return OOKD_OK;
     TapsParam<32> tp;
     memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
+    ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
+    fir1_refine_kernel<32><<<8 * h->n_sm, 256, 0, h->s_compute>>>(sa, tp);
+    h->launches++;
+    CU(h, cudaGetLastError());
+    return OOKD_OK;
+}
+
+// The work list overflowed (most of the capture is near the threshold): decide the whole range exactly.
+int launch_fir_exact_all(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
+{
+    TapsParam<32> tp;
+    memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
     TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
-    a.tile_list = (const uint32_t *) h->dense_list.p;
-    a.tile_count = (const uint32_t *) ((char *) h->scalars.p + 16);
-    fir1_exact_tiled_kernel<32, TILE_R><<<2 * h->n_sm, 256, 0, h->s_compute>>>(a, tp);
+    const u64 tiles = (u64) (h->out_hi - h->bit_base + TILE_L - 1) / TILE_L;
+    fir1_exact_tiled_kernel<32, TILE_R><<<(unsigned) tiles, 256, 0, h->s_compute>>>(a, tp);
     h->launches++;
     CU(h, cudaGetLastError());
     return OOKD_OK;
@@ -807,7 +824,13 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
 
     CU(h, cudaEventRecord(h->ev_t0, h->s_compute));
     if (h->screen) {
-        if ((rc = ensure(h, h->dense_list, sizeof(uint32_t) * (n_bits / TILE_L + 4)))) return rc;
+        // work list for undecided 8-output groups: room for 1/8 of all groups (beyond that the capture is
+        // mostly "near the threshold" and screening is pointless)
+        const u64 groups = n_bits / 8 + 1;
+        u64 cap = groups / 8 + 65536;
+        if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;
+        h->work_cap = (uint32_t) cap;
+        if ((rc = ensure(h, h->dense_list, sizeof(uint32_t) * cap))) return rc;
         CU(h, cudaMemsetAsync((char *) h->scalars.p + 16, 0, 12, h->s_compute));
     }
 
@@ -867,7 +890,7 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
                                         (uint32_t *) h->bits.p, h->bit_base))) return rc;
         }
     }
-    if ((rc = launch_fir_dense(h, d_in, in_base, in_valid_end))) return rc;
+    if ((rc = launch_fir_refine(h, d_in, in_base, in_valid_end))) return rc;
     CU(h, cudaEventRecord(h->ev_f1, h->s_compute));
 
     // ---- edges ----
@@ -899,8 +922,27 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
         // decision preceding the shard (or decision 0 itself at the capture start)
         h->base_bit = (uint32_t) ((w0 >> (h->pre ? h->pre - 1 : 0)) & 1);
         if (res) res->first_bit = (uint32_t) ((((const u64 *) h->h_scalars)[30] >> ((u64) (h->report_lo - h->bit_base) & 63)) & 1);
-        h->stat_refined_blocks = ((const uint32_t *) h->h_scalars)[5];
-        h->stat_dense_tiles = ((const uint32_t *) h->h_scalars)[6];
+        h->stat_refined_blocks = ((const uint32_t *) h->h_scalars)[4];
+        h->stat_dense_tiles = 0;
+        if (h->screen && h->stat_refined_blocks > h->work_cap) {
+            // too many undecided groups for the work list: redo the decisions exactly, recount the edges, and
+            // stop screening on this handle (the capture is not in the regime where it pays)
+            h->stat_dense_tiles = 1;
+            h->screen = false;
+            if ((rc = launch_fir_exact_all(h, d_in, in_base, in_valid_end))) return rc;
+            edge_count_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(ea);
+            scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>(ea.block_counts, eg, (u64 *) h->scalars.p);
+            h->launches += 2;
+            CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
+            CU(h, cudaMemcpyAsync((char *) h->h_scalars + 8, h->bits.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
+            CU(h, cudaMemcpyAsync((char *) h->h_scalars + 240, (const char *) h->bits.p + (((u64) (h->report_lo - h->bit_base)) >> 6) * 8,
+                                  8, cudaMemcpyDeviceToHost, h->s_compute));
+            CU(h, cudaStreamSynchronize(h->s_compute));
+            h->n_edges = ((const u64 *) h->h_scalars)[0];
+            const u64 w0b = ((const u64 *) h->h_scalars)[1];
+            h->base_bit = (uint32_t) ((w0b >> (h->pre ? h->pre - 1 : 0)) & 1);
+            if (res) res->first_bit = (uint32_t) ((((const u64 *) h->h_scalars)[30] >> ((u64) (h->report_lo - h->bit_base) & 63)) & 1);
+        }
         if ((rc = ensure(h, h->edges, sizeof(u64) * (h->n_edges + 2)))) return rc;
         if (h->n_edges) {
             ea.edges = (u64 *) h->edges.p;
