@@ -514,7 +514,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
         for (;;) {
             // round 0 (seeds) and round 1 (predecessors' exits) back to back, later rounds one at a time;
             // an incremental resolve first checks whether the new pair already links up
-            const uint32_t burst = incremental ? ((rounds == 1) ? 0 : 1) : ((rounds == 0) ? 2 : 1);
+            const uint32_t burst = incremental ? ((rounds == 1) ? 0 : 1) : ((rounds == 0) ? 3 : 1);
             for (uint32_t r = 0; r < burst; r++) {
                 a.round = rounds;
                 a.counter_idx = rounds & 31;
@@ -529,8 +529,8 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
                     cur ^= 1;
                 }
                 {
-                    const u64 warps = (u64) nc * (rounds == 0 ? 2 : TAB_K);
-                    sm_table_round_kernel<<<(unsigned) ((warps + 3) / 4), 128, 0, h->s_compute>>>(a);
+                    const u64 warps = (u64) nc * (rounds == 0 ? 1 : TAB_K);
+                    sm_table_round_kernel<<<(unsigned) warps, 32, 0, h->s_compute>>>(a);
                 }
                 h->launches++;
                 CU(h, cudaGetLastError());
@@ -543,6 +543,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
             CU(h, cudaGetLastError());
             CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
             CU(h, cudaStreamSynchronize(h->s_compute));
+            if (getenv("OOKD_DEBUG")) fprintf(stderr, "[ookd] sm rounds=%u resolved=%u/%u overflow=%u\n", rounds, h_walk[0], nc, *h_overflow);
             if (*h_overflow == 1) break;                    // message slots too small: grow and redo
             if (h_walk[1] == 1) { resolved = true; h->tab_cur = cur; break; }
             if (*h_overflow == 2 || rounds >= 16) { table_failed = true; break; }

@@ -13,10 +13,10 @@
 // Parallel form.  The output stream is cut into chunks of whole buffers.  The machine's state at a
 // chunk boundary depends on everything before it, so each chunk keeps a small TABLE of
 // (entry state -> exit state, messages) pairs, one thread per pair:
-//   round 0   two speculative seeds per chunk: RESET at the chunk's first sample, and RESET at the
-//             chunk's first "anchor" (first rising edge from which a fresh machine appends a bit,
-//             i.e. a plausible message start; found by short probe runs); chunk 0 runs from the
-//             true entry;
+//   round 0   one speculative seed per chunk: RESET at the chunk's first "anchor" (first rising edge
+//             from which a fresh machine appends a bit, i.e. a plausible message start; the 32 lanes
+//             of the warp probe 32 candidate edges at once), or RESET at the chunk's first sample when
+//             it has none; chunk 0 runs from the true entry;
 //   round r   every exit in chunk c-1's table that is not yet an entry of chunk c's table is run;
 //   link/walk exits are matched to the next chunk's entries and one thread walks the chain from
 //             chunk 0's true entry.  If the walk reaches the last chunk the decode is resolved:
@@ -337,11 +337,17 @@ __device__ __forceinline__ int sm_run_span(const SmArgs &a, const SmTable &T, Sm
     return 0;
 }
 
+// Copy the used part of the compiled machine into shared memory (header, states, triggers).
 __device__ __forceinline__ void load_table(SmTable &T, const SmTable *src_tab)
 {
-    const uint32_t *src = (const uint32_t *) src_tab;
-    uint32_t *dst = (uint32_t *) &T;
-    for (uint32_t i = threadIdx.x; i < sizeof(SmTable) / 4; i += blockDim.x) dst[i] = src[i];
+    const uint32_t ns = src_tab->num_states, nt = src_tab->num_triggers;
+    if (threadIdx.x == 0) {
+        T.num_states = ns; T.num_triggers = nt; T.max_bits = src_tab->max_bits; T.k_sat = src_tab->k_sat;
+    }
+    const uint32_t *ss = (const uint32_t *) src_tab->states, *st = (const uint32_t *) src_tab->triggers;
+    uint32_t *ds = (uint32_t *) T.states, *dt = (uint32_t *) T.triggers;
+    for (uint32_t i = threadIdx.x; i < ns * (sizeof(ookd_sm_state_k) / 4); i += blockDim.x) ds[i] = ss[i];
+    for (uint32_t i = threadIdx.x; i < nt * (sizeof(ookd_sm_trigger_k) / 4); i += blockDim.x) dt[i] = st[i];
     __syncthreads();
 }
 
@@ -366,17 +372,20 @@ __device__ __forceinline__ void carry_reset(SmCarry &s, uint32_t prev)
 // One WARP per (chunk, slot); only lane 0 runs the machine.  The work is a chain of dependent
 // steps, so what matters is latency, not lanes: giving every run its own warp keeps runs from
 // serialising each other through divergence (8 runs sharing a warp cost ~8x the latency).
-__global__ void __launch_bounds__(128) sm_table_round_kernel(const SmArgs a)
+__global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
 {
     __shared__ SmTable T;
-    load_table(T, a.tab);
-    if ((threadIdx.x & 31) != 0) return;
-
     const uint32_t K = a.tab_k;
-    const uint32_t KR = (a.round == 0) ? 2u : K;             // slots launched this round
-    const uint32_t gid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t KR = (a.round == 0) ? 1u : K;             // warps (= CTAs) per chunk this round
+    const uint32_t gid = blockIdx.x;
     const uint32_t c = gid / KR, j = gid % KR;
     if (c >= a.n_chunks) return;
+    if (a.round != 0) {
+        // cheap rejection before anything is staged: most (chunk, slot) pairs have nothing new to run
+        if (c == 0 || j >= a.cnt_in[c - 1]) return;
+    }
+    load_table(T, a.tab);
 
     i64 start, end;
     chunk_bounds(a, c, start, end);
@@ -387,45 +396,56 @@ __global__ void __launch_bounds__(128) sm_table_round_kernel(const SmArgs a)
     i64 pos = start;
     uint32_t slot;
     if (a.round == 0) {
-        if (j >= 2) return;
+        // One speculative seed per chunk (chunk 0 of a shard with a known entry runs from that entry):
+        // RESET at the chunk's first "anchor" -- the first rising edge from which a freshly reset machine
+        // gets as far as appending a bit, i.e. a plausible message start -- or, when the chunk has none,
+        // RESET at its first sample.  A guess from the first sample usually lands mid-message, errors,
+        // and can stay out of step with the true run for many messages; the true run, whatever it did
+        // before, is normally idle when a message starts, so from the anchor on the two coincide.
+        // The 32 lanes probe 32 candidate edges at once; lane 0 then does the real run.
+        bool have_anchor = false;
+        u64 anchor_e = 0;
+        if (!(c == 0 && !a.warm)) {
+            const u64 er0 = e + (tb == 1 ? 1 : 0);          // edge e falls when tb == 1; the next one rises
+            for (int batch = 0; batch < 3 && !have_anchor; batch++) {
+                const u64 er = er0 + 2 * (u64) (batch * 32 + lane);
+                const bool cand = er < a.n_edges && a.edges[er] < (u64) end;
+                bool alive = false;
+                if (cand) {
+                    SmCarry p;
+                    carry_reset(p, 0);
+                    SpanOut po;
+                    po.slots = nullptr; po.cap = 0; po.n_msgs = 0; po.overflow = nullptr;
+                    alive = sm_run_span<true>(a, T, p, (i64) a.edges[er], a.out_hi, er, 0, po, start) != 0;
+                }
+                const uint32_t m_alive = __ballot_sync(0xFFFFFFFFu, alive);
+                const uint32_t m_cand = __ballot_sync(0xFFFFFFFFu, cand);
+                if (m_alive) {
+                    have_anchor = true;
+                    anchor_e = er0 + 2 * (u64) (batch * 32 + (__ffs(m_alive) - 1));
+                }
+                if (m_cand != 0xFFFFFFFFu) break;            // ran out of rising edges in this chunk
+            }
+        }
+        if (lane != 0) return;
         if (c == 0 && !a.warm) {
-            if (j == 1) return;
             s = a.entry0;
             entry = s;
-        } else if (j == 0) {
-            carry_reset(s, tb);
-            entry = s;
-        } else {
-            // second seed: RESET at the chunk's first "anchor" -- the first rising edge from which a
-            // freshly reset machine gets as far as appending a bit (i.e. a plausible message start).
-            // A guess from the chunk's first sample usually lands mid-message, errors, and can stay
-            // out of step with the true run for many messages; the true run, whatever it did before,
-            // is normally idle when a message starts, so from the anchor on the two coincide.
-            u64 er = e;
-            if (tb == 1) er++;                 // edge e falls; the next one rises
-            bool found = false;
-            for (int tries = 0; tries < 96 && er < a.n_edges && a.edges[er] < (u64) end; tries++, er += 2) {
-                SmCarry p;
-                carry_reset(p, 0);
-                SpanOut po;
-                po.slots = nullptr; po.cap = 0; po.n_msgs = 0; po.overflow = nullptr;
-                if (sm_run_span<true>(a, T, p, (i64) a.edges[er], a.out_hi, er, 0, po, start)) {
-                    found = true;
-                    break;
-                }
-            }
-            if (!found) return;
-            pos = (i64) a.edges[er];
-            e = er;
+        } else if (have_anchor) {
+            pos = (i64) a.edges[anchor_e];
+            e = anchor_e;
             tb = 0;
             carry_reset(s, 0);
             entry = s;
-            entry.state = OOKD_TAB_INVALID;
-            if (c == 0) *a.start_slot = 1;       // warm-up chunk: prefer the anchored run
+            entry.state = OOKD_TAB_INVALID;                  // matches no real entry: it is only a source of exits
+        } else {
+            carry_reset(s, tb);
+            entry = s;
         }
-        slot = j;
-        atomicMax(&a.cnt_out[c], j + 1);
+        slot = 0;
+        a.cnt_out[c] = 1;
     } else {
+        if (lane != 0) return;
         if (c == 0) return;
         const uint32_t n_prev = a.cnt_in[c - 1];
         if (j >= n_prev) return;
