@@ -20,6 +20,7 @@ K_INF = 0xFFFFFFFF
 
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_SCREEN = 2
+FLAG_TILE_PER_CTA_SCREEN = 4
 
 # every symbol include/ookd_gpu.h declares
 EXPORTS = [

@@ -14,6 +14,8 @@
 // (m - bit_base) of the bit array.
 #pragma once
 
+#include <climits>
+
 #include "ookd_common.cuh"
 
 namespace ookd {
@@ -240,6 +242,7 @@ struct ScreenArgs {
     uint32_t *work_count;    // number of groups pushed (may exceed work_cap: then the host redoes the range exactly)
     uint32_t work_cap;
     uint32_t tile_offset;    // first (4096-output) tile of this launch, numbered from t.out_lo
+    uint32_t n_tiles;        // tiles of this launch (persistent variant)
 };
 
 __device__ __forceinline__ float sqrt_approx(float x)
@@ -251,6 +254,9 @@ __device__ __forceinline__ float sqrt_approx(float x)
 
 #ifndef OOKD_SCREEN_MINB
 #define OOKD_SCREEN_MINB 5
+#endif
+#ifndef OOKD_SCREEN_PERSIST_MINB
+#define OOKD_SCREEN_PERSIST_MINB 4
 #endif
 
 // prefix sums / sums / range guard of one 16-sample span
@@ -355,13 +361,13 @@ fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp)
         const uint32_t tot1 = s_pre[(span - 1) * 4 + ((3 + ((span - 1) >> 1)) & 3)].w, tot2 = p2[SPT - 1];
         const uint32_t base = tot2 + tot1;
         // window of output j: samples (t-2, j+1) .. (t, j):  E_j = base + pre[j] - p2[j]   (exact in u32)
-        uint32_t emax_lo = 0, emax_hi = 0;
+        int dmax_lo = INT_MIN, dmax_hi = INT_MIN;
 #pragma unroll
         for (int j = 0; j < SPT; j++) {
-            const uint32_t e = base + pre[j] - p2[j];
-            if (j < 8) emax_lo = max(emax_lo, e); else emax_hi = max(emax_hi, e);
+            const int d = (int) (pre[j] - p2[j]);              // all sums < 2^31: signed difference is exact
+            if (j < 8) dmax_lo = max(dmax_lo, d); else dmax_hi = max(dmax_hi, d);
         }
-        const bool off_lo = emax_lo < sp.k0, off_hi = emax_hi < sp.k0;
+        const bool off_lo = (uint32_t) ((int) base + dmax_lo) < sp.k0, off_hi = (uint32_t) ((int) base + dmax_hi) < sp.k0;
         bool on = false;
         if (!(off_lo && off_hi)) {
             const int2 xy1 = s_xy[span - 1], xy2 = s_xy[span - 2];
@@ -411,6 +417,158 @@ fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp)
             const uint32_t s = slot0 + __popc(m_lo) + __popc(m_hi & below);
             if (s < sa.work_cap) sa.work_list[s] = grp0 + 1;
         }
+    }
+}
+
+// Persistent variant of fir1_screen_kernel: each CTA walks a contiguous range of tiles, requests the raw
+// words of tile i+1 (4 x LDG.128 per thread) before it processes tile i, and keeps the span statistics in
+// a two-tile ring in shared memory so that the last two spans of tile i are the history of tile i+1.
+// One CTA barrier per tile; no global-load latency on the critical path.
+template <int T>
+__global__ void __launch_bounds__(256, OOKD_SCREEN_PERSIST_MINB)
+fir1_screen_persist_kernel(const ScreenArgs sa, const ScreenParams sp)
+{
+    static_assert(T == 32, "window = exactly two 16-sample thread spans");
+    constexpr int NT = 256, SPT = 16, L = NT * SPT;
+    constexpr int RING = 2 * NT;
+    __shared__ uint4 s_pre[RING * 4];
+    __shared__ int2 s_xy[RING];
+    __shared__ uint8_t s_flag[RING];
+
+    const TiledArgs &a = sa.t;
+    const uint32_t per = (sa.n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t t_begin = sa.tile_offset + blockIdx.x * per;
+    const uint32_t t_end = min(sa.tile_offset + sa.n_tiles, t_begin + per);
+    if (t_begin >= t_end) return;
+
+    const bool ptr_ok = ((((uintptr_t) a.in) & 15) == 0);
+    auto load_span = [&](i64 g, bool fast, uint32_t (&w)[16]) {
+        if (fast) {
+            const uint4 *src = (const uint4 *) (a.in + (g - a.in_base));
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const uint4 x = __ldg(src + v);
+                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+                const i64 ge = g + e;
+                w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
+            }
+        }
+    };
+    auto tile_fast = [&](uint32_t tile) -> bool {
+        const i64 g0 = a.out_lo + (i64) tile * L;
+        return ptr_ok && (((g0 - a.in_base) & 3) == 0) && g0 >= a.in_base && g0 >= 0 && (g0 + L) <= a.in_valid_end;
+    };
+    auto store_span = [&](int rp, const uint32_t (&p)[16], int xs, int ys, uint32_t gd) {
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            s_pre[rp * 4 + ((v + (rp >> 1)) & 3)] = make_uint4(p[4 * v], p[4 * v + 1], p[4 * v + 2], p[4 * v + 3]);
+        }
+        s_xy[rp] = make_int2(xs, ys);
+        s_flag[rp] = (gd >> 25) ? 1 : 0;
+    };
+
+    // history of the first tile: the two spans in front of it go to the end of the "previous" half of the ring
+    if (threadIdx.x < 2) {
+        const int par0 = (int) (t_begin & 1);
+        const i64 g = a.out_lo + (i64) t_begin * L - 2 * SPT + (i64) threadIdx.x * SPT;
+        uint32_t w[16], p[16], gd;
+        int xs, ys;
+        load_span(g, false, w);
+        screen_span_stats(w, p, xs, ys, gd);
+        store_span((par0 ^ 1) * NT + (NT - 2) + threadIdx.x, p, xs, ys, gd);
+    }
+
+    uint32_t w_cur[16], w_nxt[16];
+    load_span(a.out_lo + (i64) t_begin * L + (i64) threadIdx.x * SPT, tile_fast(t_begin), w_cur);
+
+    for (uint32_t tile = t_begin; tile < t_end; tile++) {
+        const int par = (int) (tile & 1);
+        const i64 o0 = a.out_lo + (i64) tile * L;
+        if (tile + 1 < t_end) {
+            load_span(o0 + L + (i64) threadIdx.x * SPT, tile_fast(tile + 1), w_nxt);
+        }
+        uint32_t pre[SPT], guard;
+        int sx, sy;
+        const int rp = par * NT + threadIdx.x;
+        screen_span_stats(w_cur, pre, sx, sy, guard);
+        store_span(rp, pre, sx, sy, guard);
+        __syncthreads();     // also orders this tile's reads of the other half before the next tile overwrites it
+
+        const int r1 = (rp + RING - 1) & (RING - 1), r2 = (rp + RING - 2) & (RING - 1);
+        uint32_t bits16 = 0;
+        bool undecided_lo = false, undecided_hi = false;
+        const i64 o = o0 + (i64) threadIdx.x * SPT;
+        const bool bad = (guard >> 25) || s_flag[r1] || s_flag[r2];
+        if (!bad) {
+            uint32_t p2[SPT];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const uint4 x = s_pre[r2 * 4 + ((v + (r2 >> 1)) & 3)];
+                p2[4 * v] = x.x; p2[4 * v + 1] = x.y; p2[4 * v + 2] = x.z; p2[4 * v + 3] = x.w;
+            }
+            const uint32_t tot1 = s_pre[r1 * 4 + ((3 + (r1 >> 1)) & 3)].w, tot2 = p2[SPT - 1];
+            const uint32_t base = tot2 + tot1;
+            int dmax_lo = INT_MIN, dmax_hi = INT_MIN;
+#pragma unroll
+            for (int j = 0; j < SPT; j++) {
+                const int d = (int) (pre[j] - p2[j]);          // all sums < 2^31: signed difference is exact
+                if (j < 8) dmax_lo = max(dmax_lo, d); else dmax_hi = max(dmax_hi, d);
+            }
+            const bool off_lo = (uint32_t) ((int) base + dmax_lo) < sp.k0, off_hi = (uint32_t) ((int) base + dmax_hi) < sp.k0;
+            bool on = false;
+            if (!(off_lo && off_hi)) {
+                const int2 xy1 = s_xy[r1], xy2 = s_xy[r2];
+                const float X = (float) (sx + xy1.x + xy2.x), Y = (float) (sy + xy1.y + xy2.y);
+                const float Q = (float) (base + pre[SPT - 1]);
+                const float m2 = fmaf(X, X, Y * Y);
+                const float mu = sqrt_approx(m2) * sp.inv_n;
+                const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
+                const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
+                on = fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi;
+            }
+            if (on) {
+                bits16 = 0xFFFFu;
+            } else {
+                undecided_lo = !off_lo;
+                undecided_hi = !off_hi;
+            }
+        } else {
+            undecided_lo = undecided_hi = true;
+        }
+        const bool in_lo = o < a.out_hi, in_hi = o + 8 < a.out_hi;
+        if (in_lo) {
+            const i64 byte = (o - a.bit_base) >> 3;
+            if (in_hi) {
+                *(uint16_t *) (a.out_bits + byte) = (uint16_t) bits16;
+            } else {
+                a.out_bits[byte] = (uint8_t) bits16;
+            }
+        }
+        const bool push_lo = undecided_lo && in_lo, push_hi = undecided_hi && in_hi;
+        const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, push_lo), m_hi = __ballot_sync(0xFFFFFFFFu, push_hi);
+        const uint32_t n_push = __popc(m_lo) + __popc(m_hi);
+        if (n_push) {
+            const int lane = threadIdx.x & 31;
+            uint32_t slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(sa.work_count, n_push);
+            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+            const uint32_t below = (1u << lane) - 1;
+            const uint32_t grp0 = (uint32_t) ((o - a.bit_base) >> 3);
+            if (push_lo) {
+                const uint32_t sl = slot0 + __popc(m_lo & below);
+                if (sl < sa.work_cap) sa.work_list[sl] = grp0;
+            }
+            if (push_hi) {
+                const uint32_t sl = slot0 + __popc(m_lo) + __popc(m_hi & below);
+                if (sl < sa.work_cap) sa.work_list[sl] = grp0 + 1;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e++) w_cur[e] = w_nxt[e];
     }
 }
 

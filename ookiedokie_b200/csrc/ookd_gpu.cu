@@ -54,6 +54,7 @@ struct ookd_gpu {
     uint32_t chunk_buffers = 64;
     uint32_t flags = 0;
     bool screen = false;
+    bool persist = false;
     unsigned n_sm = 148;
 
     bool have_sm = false;
@@ -222,7 +223,13 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
             sa.tile_offset = (uint32_t) tile0;
             ScreenParams sp;
             make_screen_params(h, sp);
-            fir1_screen_kernel<32><<<(unsigned) stiles, 256, 0, h->s_compute>>>(sa, sp);
+            sa.n_tiles = (uint32_t) stiles;
+            if (h->persist) {
+                const u64 ctas = (u64) h->n_sm * OOKD_SCREEN_PERSIST_MINB;
+                fir1_screen_persist_kernel<32><<<(unsigned) (stiles < ctas ? stiles : ctas), 256, 0, h->s_compute>>>(sa, sp);
+            } else {
+                fir1_screen_kernel<32><<<(unsigned) stiles, 256, 0, h->s_compute>>>(sa, sp);
+            }
         } else {
             TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
             a.out_lo = o_begin; a.out_hi = o_end;
@@ -740,6 +747,7 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
         }
     }
     h->n_sm = (unsigned) prop.multiProcessorCount;
+    h->persist = (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) == 0;
     // the screen needs a finite positive power threshold (thr <= 0 decides 1 everywhere, NaN 0 everywhere;
     // the exact kernels handle those directly)
     h->screen = (h->path == FIR_TILED_1STAGE_32) && !(h->flags & OOKD_FLAG_NO_SCREEN) && h->pstar > 0.0f &&

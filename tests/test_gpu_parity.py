@@ -128,7 +128,7 @@ def test_screen_decisions_equal_exact(filt, levels, sigma, thr, full):
     iq = _piecewise_capture(rng, 300000, levels, sigma, full_range=full)
     stages = O.load_filter(filt)
     ref = O.rx(iq, stages, None, threshold_=thr, samples_per_buffer=8192, want_bits=True)
-    for flags in (0, B.FLAG_NO_SCREEN, B.FLAG_FORCE_GENERIC):
+    for flags in (0, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_FORCE_GENERIC):
         g = B.Gpu(filter_stages=stages, threshold=thr, samples_per_buffer=8192, flags=flags)
         got = g.decode(iq)
         assert np.array_equal(g.bits(), ref["bits"]), (flags, got["refined_blocks"], got["refined_tiles"])
