@@ -617,4 +617,198 @@ __global__ void __launch_bounds__(256) fir1_refine_kernel(const ScreenArgs sa, c
     }
 }
 
+// =======================================================================================
+// 4. Two-stage shape: 16 taps / decimate 2, then 32 taps / decimate 2 (fs128_fs16_dec4).
+//
+//    Final output m is produced when input 4m+3 arrives and depends on the 78 inputs 4m+3-77 .. 4m+3
+//    through the composite response h = t1 (*) upsample2(t2).  The same two proofs as in section 3
+//    apply with ||h||_2, G = sum h and, for the reference's two rounded stages, the absolute composite
+//    habs = |t1| (*) upsample2(|t2|) in the rounding allowance:
+//        |y_ref - y| <= (g1 + g2 + g1 g2) sum_n habs[n] |x[4m+3-n]| <= gamma ||habs||_2 sqrt(E).
+//    Threads own 16 inputs = 4 outputs; a window reaches back into the 5 spans in front, of which it
+//    needs only the prefix sums at elements 1, 5, 9, 13 and the totals.
+// =======================================================================================
+struct Taps2Param {
+    float t1[16];
+    float t2[32];
+    const float *d_t1, *d_t2;       // the same taps in device memory (rolled-loop boundary path)
+};
+
+__global__ void __launch_bounds__(256, 5) fir2_screen_kernel(const ScreenArgs sa, const ScreenParams sp)
+{
+    constexpr int NT = 256, SPT = 16, LIN = NT * SPT;     // 4096 inputs = 1024 outputs per tile
+    constexpr int HT = 5;                                 // history spans in front of the tile (80 samples >= 77)
+    __shared__ uint4 s_a[NT + HT];                        // pre[1], pre[5], pre[9], pre[13]
+    __shared__ uint4 s_b[NT + HT];                        // total, sum I, sum Q, flag
+
+    const TiledArgs &a = sa.t;                            // out_lo / out_hi / bit_base in OUTPUT indices
+    const uint32_t tile = blockIdx.x + sa.tile_offset;
+    const i64 o0 = a.out_lo + (i64) tile * (LIN / 4);     // first output of the tile
+    const i64 g0 = o0 * 4 - HT * SPT;                     // first input of the first history span
+    const bool fast = ((((uintptr_t) a.in) & 15) == 0) && (((g0 - a.in_base) & 3) == 0) && g0 >= a.in_base && g0 >= 0 &&
+                      (g0 + LIN + HT * SPT) <= a.in_valid_end;
+
+    uint32_t pre[SPT], guard = 0;
+    int sx = 0, sy = 0;
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        int span;
+        if (pass == 0) {
+            span = threadIdx.x + HT;
+        } else {
+            if (threadIdx.x >= HT) break;
+            span = threadIdx.x;
+        }
+        const i64 g = g0 + (i64) span * SPT;
+        uint32_t w[SPT];
+        if (fast) {
+            const uint4 *src = (const uint4 *) (a.in + (g - a.in_base));
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const uint4 x = __ldg(src + v);
+                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < SPT; e++) {
+                const i64 ge = g + e;
+                w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
+            }
+        }
+        uint32_t p[SPT], gd;
+        int xs, ys;
+        screen_span_stats(w, p, xs, ys, gd);
+        s_a[span] = make_uint4(p[1], p[5], p[9], p[13]);
+        s_b[span] = make_uint4(p[15], (uint32_t) xs, (uint32_t) ys, (gd >> 25) ? 1u : 0u);
+        if (pass == 0) {
+#pragma unroll
+            for (int e = 0; e < SPT; e++) pre[e] = p[e];
+            sx = xs; sy = ys; guard = gd;
+        }
+    }
+    __syncthreads();
+
+    const int span = threadIdx.x + HT;
+    const uint4 b1 = s_b[span - 1], b2 = s_b[span - 2], b3 = s_b[span - 3], b4 = s_b[span - 4], b5 = s_b[span - 5];
+    const uint4 a4 = s_a[span - 4], a5 = s_a[span - 5];
+    uint32_t bits4 = 0, und = 0;                          // decisions / undecided flags of the 4 outputs
+    const bool bad = (guard >> 25) || b1.w || b2.w || b3.w || b4.w || b5.w;
+    if (!bad) {
+        const uint32_t mid3 = b3.x + b2.x + b1.x;         // spans s-3 .. s-1
+        const uint32_t mid4 = mid3 + b4.x;                // spans s-4 .. s-1
+        // newest sample at element 3, 7, 11: window starts at element 6, 10, 14 of span s-5
+        const uint32_t e0 = (b5.x - a5.y) + mid4 + pre[3];
+        const uint32_t e1 = (b5.x - a5.z) + mid4 + pre[7];
+        const uint32_t e2 = (b5.x - a5.w) + mid4 + pre[11];
+        // newest sample at element 15: window starts at element 2 of span s-4
+        const uint32_t e3 = (b4.x - a4.x) + mid3 + pre[15];
+        und = (e0 < sp.k0 ? 0u : 1u) | (e1 < sp.k0 ? 0u : 2u) | (e2 < sp.k0 ? 0u : 4u) | (e3 < sp.k0 ? 0u : 8u);
+        if (und) {
+            const float X = (float) (sx + (int) b1.y + (int) b2.y + (int) b3.y + (int) b4.y + (int) b5.y);
+            const float Y = (float) (sy + (int) b1.z + (int) b2.z + (int) b3.z + (int) b4.z + (int) b5.z);
+            const float Q = (float) (b5.x + mid4 + pre[15]);
+            const float m2 = fmaf(X, X, Y * Y);
+            const float mu = sqrt_approx(m2) * sp.inv_n;
+            const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
+            const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
+            if (fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi) {
+                bits4 = 0xF;
+                und = 0;
+            }
+        }
+    } else {
+        und = 0xF;
+    }
+    // two threads share a byte of decisions
+    const uint32_t other_bits = __shfl_down_sync(0xFFFFFFFFu, bits4, 1);
+    const uint32_t other_und = __shfl_down_sync(0xFFFFFFFFu, und, 1);
+    const i64 o = o0 + (i64) threadIdx.x * 4;             // first output of this thread
+    const bool even = (threadIdx.x & 1) == 0;
+    const bool in_range = even && o < a.out_hi;
+    const bool push = in_range && ((und | other_und) != 0);
+    if (in_range) {
+        a.out_bits[(o - a.bit_base) >> 3] = (uint8_t) (bits4 | (other_bits << 4));
+    }
+    const uint32_t m_push = __ballot_sync(0xFFFFFFFFu, push);
+    if (m_push) {
+        const int lane = threadIdx.x & 31;
+        uint32_t slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(sa.work_count, (uint32_t) __popc(m_push));
+        slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+        if (push) {
+            const uint32_t sl = slot0 + __popc(m_push & ((1u << lane) - 1));
+            if (sl < sa.work_cap) sa.work_list[sl] = (uint32_t) ((o - a.bit_base) >> 3);
+        }
+    }
+}
+
+// Exact two-stage recomputation of one output per lane (8 lanes per undecided group).
+//   y[m]  = sum_{j<32} t2[j] * s[2m+1-j]          accumulated from j = 0   (src/fir.c:313-318, stage 2)
+//   s[u]  = sum_{i<16} t1[i] * x[2u+1-i]          accumulated from i = 0   (stage 1); s[u<0] = 0, x[g<0] = 0
+// A 16-sample register window slides down by two inputs per stage-1 output (fully unrolled).
+__global__ void __launch_bounds__(256) fir2_refine_kernel(const ScreenArgs sa, const Taps2Param taps)
+{
+    const TiledArgs &a = sa.t;
+    const uint32_t n_groups = min(*sa.work_count, sa.work_cap);
+    const u64 n_items = ((u64) n_groups * 8 + 31) & ~31ull;
+    for (u64 item = (u64) blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (u64) gridDim.x * blockDim.x) {
+        const u64 qi = item >> 3;
+        const uint32_t jj = (uint32_t) (item & 7);
+        bool bit = false;
+        uint32_t grp = 0;
+        if (qi < n_groups) {
+            grp = sa.work_list[qi];
+            const i64 m = a.bit_base + (i64) grp * 8 + jj;
+            const i64 g_new = 4 * m + 3;                   // newest input of output m
+            float re = 0.0f, im = 0.0f;
+            if (g_new - 77 >= a.in_base && g_new - 77 >= 0 && g_new < a.in_valid_end) {
+                const uint32_t *src = a.in + (g_new - a.in_base);
+                float2 w[16];                              // w[k] = x[2u+1-k] for the current u
+#pragma unroll
+                for (int k = 0; k < 16; k++) w[k] = sc16q11_to_float2(__ldg(src - k));
+#pragma unroll
+                for (int j = 0; j < 32; j++) {             // u = 2m+1-j
+                    float sr = 0.0f, si = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        sr = mac_exact(sr, taps.t1[i], w[i].x);
+                        si = mac_exact(si, taps.t1[i], w[i].y);
+                    }
+                    re = mac_exact(re, taps.t2[j], sr);
+                    im = mac_exact(im, taps.t2[j], si);
+                    if (j < 31) {
+#pragma unroll
+                        for (int k = 0; k < 14; k++) w[k] = w[k + 2];
+                        w[14] = sc16q11_to_float2(__ldg(src - (2 * j + 16)));
+                        w[15] = sc16q11_to_float2(__ldg(src - (2 * j + 17)));
+                    }
+                }
+            } else {
+                for (int j = 0; j < 32; j++) {
+                    const i64 u = 2 * m + 1 - j;
+                    float sr = 0.0f, si = 0.0f;
+                    if (u >= 0) {
+                        for (int i = 0; i < 16; i++) {
+                            const i64 g = 2 * u + 1 - i;
+                            const uint32_t wv = (g >= 0 && g >= a.in_base && g < a.in_valid_end) ? __ldg(a.in + (g - a.in_base)) : 0u;
+                            const float2 x = sc16q11_to_float2(wv);
+                            const float t = __ldg(taps.d_t1 + i);
+                            sr = mac_exact(sr, t, x.x);
+                            si = mac_exact(si, t, x.y);
+                        }
+                    }
+                    const float t = __ldg(taps.d_t2 + j);
+                    re = mac_exact(re, t, sr);
+                    im = mac_exact(im, t, si);
+                }
+            }
+            bit = power_exact(re, im) >= a.pstar;
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);
+        if (qi < n_groups && jj == 0) {
+            a.out_bits[grp] = (uint8_t) (ballot >> (threadIdx.x & 24));
+        }
+    }
+}
+
 }  // namespace ookd

@@ -33,7 +33,7 @@ struct Stage {
     float *d_taps = nullptr;
 };
 
-enum FirPath { FIR_GENERIC = 0, FIR_TILED_1STAGE_32 };
+enum FirPath { FIR_GENERIC = 0, FIR_TILED_1STAGE_32, FIR_SCREEN_DEC4 };
 
 }  // namespace
 
@@ -189,6 +189,45 @@ void make_screen_params(const ookd_gpu *h, ScreenParams &sp)
     sp.inv_n = 1.0f / 48.0f;
 }
 
+// Same for the two-stage 16/2 + 32/2 shape: composite response h = t1 (*) upsample2(t2) and its absolute
+// counterpart for the rounding allowance of two rounded stages.
+void make_screen_params_dec4(const ookd_gpu *h, ScreenParams &sp)
+{
+    const Stage &s1 = h->stages[0], &s2 = h->stages[1];
+    const int n = (int) s1.T + (int) s1.D * ((int) s2.T - 1);          // 16 + 2*31 = 78
+    std::vector<double> hc(n, 0.0), ha(n, 0.0);
+    for (uint32_t j = 0; j < s2.T; j++) {
+        for (uint32_t i = 0; i < s1.T; i++) {
+            hc[s1.D * j + i] += (double) s2.taps[j] * (double) s1.taps[i];
+            ha[s1.D * j + i] += fabs((double) s2.taps[j]) * fabs((double) s1.taps[i]);
+        }
+    }
+    double g = 0.0, h2 = 0.0, a2 = 0.0;
+    for (int k = 0; k < n; k++) {
+        g += hc[k];
+        h2 += hc[k] * hc[k];
+        a2 += ha[k] * ha[k];
+    }
+    g = fabs(g);
+    h2 = sqrt(h2);
+    a2 = sqrt(a2);
+    const double u = ldexp(1.0, -24);
+    const double g1 = 2.0 * (s1.T + 2) * u, g2 = 2.0 * (s2.T + 2) * u;
+    const double gamma = g1 + g2 + g1 * g2;
+    const double pstar = (double) h->pstar;
+    const double amp = h2 + gamma * a2;                                 // |y_ref| <= amp * sqrt(E)
+    double k0 = pstar * 2048.0 * 2048.0 / (amp * amp * (1.0 + 3.0 * u));
+    k0 = floor(k0 * (1.0 - 1e-6));
+    if (k0 < 0.0) k0 = 0.0;
+    if (k0 > 4.0e9) k0 = 4.0e9;
+    sp.k0 = (uint32_t) k0;
+    sp.g_lo = nextafterf((float) (g * (1.0 - 1e-6)), 0.0f);
+    sp.t2 = nextafterf((float) (h2 * (1.0 + 1e-6)), INFINITY);
+    sp.cg = nextafterf((float) (gamma * a2 * (1.0 + 1e-6)), INFINITY);
+    sp.theta_hi = nextafterf((float) (sqrt(pstar) * 2048.0 * (1.0 + 1e-5)), INFINITY);
+    sp.inv_n = 1.0f / 96.0f;
+}
+
 TiledArgs tiled_args(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
 {
     TiledArgs a{};
@@ -239,12 +278,38 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
         CU(h, cudaGetLastError());
         return OOKD_OK;
     }
+    if (h->path == FIR_SCREEN_DEC4) {
+        constexpr int L2 = 1024;                                        // outputs per tile of fir2_screen_kernel
+        const u64 tiles = (u64) (o_end - o_begin + L2 - 1) / L2;
+        ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
+        sa.t.out_hi = o_end;
+        sa.tile_offset = (uint32_t) ((u64) (o_begin - h->bit_base) / L2);
+        sa.n_tiles = (uint32_t) tiles;
+        ScreenParams sp;
+        make_screen_params_dec4(h, sp);
+        fir2_screen_kernel<<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, sp);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        return OOKD_OK;
+    }
     return fail(h, OOKD_ERR_STATE, "launch_fir: no tiled path");
 }
 
 // Second pass of the screened path: exact recomputation of the groups the screen left undecided.
 int launch_fir_refine(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
 {
+    if (h->path == FIR_SCREEN_DEC4 && h->out_hi > h->bit_base) {
+        Taps2Param tp;
+        memcpy(tp.t1, h->stages[0].taps.data(), sizeof(tp.t1));
+        memcpy(tp.t2, h->stages[1].taps.data(), sizeof(tp.t2));
+        tp.d_t1 = h->stages[0].d_taps;
+        tp.d_t2 = h->stages[1].d_taps;
+        ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
+        fir2_refine_kernel<<<8 * h->n_sm, 256, 0, h->s_compute>>>(sa, tp);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        return OOKD_OK;
+    }
     if (!(h->path == FIR_TILED_1STAGE_32 && h->screen) || h->out_hi <= h->bit_base) return OOKD_OK;
     TapsParam<32> tp;
     memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
@@ -256,8 +321,16 @@ int launch_fir_refine(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_val
 }
 
 // The work list overflowed (most of the capture is near the threshold): decide the whole range exactly.
+int run_generic_chain(ookd_gpu *h, const void *d_in, bool in_is_i16, i64 in_base, i64 in_valid_end, i64 o_lo, i64 o_hi,
+                      float2 *out_cf, uint32_t *bits, i64 bit_base);
+
 int launch_fir_exact_all(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
 {
+    if (h->path == FIR_SCREEN_DEC4) {
+        h->path = FIR_GENERIC;                                          // stop screening on this handle
+        return run_generic_chain(h, d_in, true, in_base, in_valid_end, h->bit_base, h->out_hi, nullptr,
+                                 (uint32_t *) h->bits.p, h->bit_base);
+    }
     TapsParam<32> tp;
     memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
     TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
@@ -746,6 +819,11 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
             h->path = FIR_TILED_1STAGE_32;
         }
     }
+    const bool pstar_ok = h->pstar > 0.0f && h->pstar < 3.0e38f;
+    if (!(h->flags & (OOKD_FLAG_FORCE_GENERIC | OOKD_FLAG_NO_SCREEN)) && pstar_ok && h->stages.size() == 2 &&
+        h->stages[0].T == 16 && h->stages[0].D == 2 && h->stages[1].T == 32 && h->stages[1].D == 2) {
+        h->path = FIR_SCREEN_DEC4;
+    }
     h->n_sm = (unsigned) prop.multiProcessorCount;
     h->persist = (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) == 0;
     // the screen needs a finite positive power threshold (thr <= 0 decides 1 everywhere, NaN 0 everywhere;
@@ -832,7 +910,7 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     if ((rc = ensure(h, h->bits, (n_bits / 8 + 64 + 8) & ~7ull))) return rc;
 
     CU(h, cudaEventRecord(h->ev_t0, h->s_compute));
-    if (h->screen) {
+    if (h->screen || h->path == FIR_SCREEN_DEC4) {
         // work list for undecided 8-output groups: room for 1/8 of all groups (beyond that the capture is
         // mostly "near the threshold" and screening is pointless)
         const u64 groups = n_bits / 8 + 1;
@@ -933,7 +1011,7 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
         if (res) res->first_bit = (uint32_t) ((((const u64 *) h->h_scalars)[30] >> ((u64) (h->report_lo - h->bit_base) & 63)) & 1);
         h->stat_refined_blocks = ((const uint32_t *) h->h_scalars)[4];
         h->stat_dense_tiles = 0;
-        if (h->screen && h->stat_refined_blocks > h->work_cap) {
+        if ((h->screen || h->path == FIR_SCREEN_DEC4) && h->stat_refined_blocks > h->work_cap) {
             // too many undecided groups for the work list: redo the decisions exactly, recount the edges, and
             // stop screening on this handle (the capture is not in the regime where it pays)
             h->stat_dense_tiles = 1;

@@ -121,11 +121,11 @@ SCREEN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("filt", ["fs32_fs4", "fs64_fs8"])
+@pytest.mark.parametrize("filt", ["fs32_fs4", "fs64_fs8", "fs128_fs16_dec4"])
 @pytest.mark.parametrize("levels,sigma,thr,full", SCREEN_CASES)
 def test_screen_decisions_equal_exact(filt, levels, sigma, thr, full):
     rng = np.random.default_rng(abs(hash((filt, tuple(levels), sigma, thr))) % (2 ** 32))
-    iq = _piecewise_capture(rng, 300000, levels, sigma, full_range=full)
+    iq = _piecewise_capture(rng, 300001 if "dec4" in filt else 300000, levels, sigma, full_range=full)
     stages = O.load_filter(filt)
     ref = O.rx(iq, stages, None, threshold_=thr, samples_per_buffer=8192, want_bits=True)
     for flags in (0, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_FORCE_GENERIC):
@@ -136,12 +136,29 @@ def test_screen_decisions_equal_exact(filt, levels, sigma, thr, full):
         assert fb == ref["first_bit"] and np.array_equal(edges, ref["edges"])
 
 
-def test_screen_actually_screens():
-    # in the benchmark regime nearly every block must be decided without MACs
+@pytest.mark.parametrize("filt,dec", [("fs32_fs4", 1), ("fs128_fs16_dec4", 4)])
+def test_screen_actually_screens(filt, dec):
+    # in the benchmark regime nearly every group of 8 outputs must be decided without MACs
     rng = np.random.default_rng(1)
     iq = _piecewise_capture(rng, 1 << 20, [0.0, 0.95], 41.0, seg=(1500, 12000))
-    g = B.Gpu(filter_stages=O.load_filter("fs32_fs4"), threshold=0.1)
+    g = B.Gpu(filter_stages=O.load_filter(filt), threshold=0.1)
     got = g.decode(iq)
-    blocks = (1 << 20) // 8
+    groups = (1 << 20) // dec // 8
     assert got["refined_tiles"] == 0
-    assert got["refined_blocks"] < 0.1 * blocks, got
+    assert 0 < got["refined_blocks"] < 0.1 * groups, got
+
+
+def test_screen_overflow_falls_back_to_exact_and_stays_correct():
+    # everything near the threshold: the work list overflows, the handle switches to the exact kernels
+    rng = np.random.default_rng(2)
+    iq = _piecewise_capture(rng, 1 << 21, [0.1], 30.0)
+    for filt in ("fs32_fs4", "fs128_fs16_dec4"):
+        stages = O.load_filter(filt)
+        ref = O.rx(iq, stages, None, threshold_=0.1, samples_per_buffer=8192, want_bits=True)
+        g = B.Gpu(filter_stages=stages, threshold=0.1)
+        first = g.decode(iq)
+        # the list holds 1/8 of all groups + 64 Ki: 2^21 fs32_fs4 outputs overflow it, 2^19 dec4 outputs do not
+        assert first["refined_tiles"] == (1 if filt == "fs32_fs4" else 0)
+        assert np.array_equal(g.bits(), ref["bits"])
+        again = g.decode(iq)                      # after an overflow: on the exact path from the start
+        assert again["refined_tiles"] == 0 and np.array_equal(g.bits(), ref["bits"])
