@@ -431,9 +431,13 @@ fir1_screen_persist_kernel(const ScreenArgs sa, const ScreenParams sp)
     static_assert(T == 32, "window = exactly two 16-sample thread spans");
     constexpr int NT = 256, SPT = 16, L = NT * SPT;
     constexpr int RING = 2 * NT;
-    __shared__ uint4 s_pre[RING * 4];
-    __shared__ int2 s_xy[RING];
-    __shared__ uint8_t s_flag[RING];
+    // Rows RING.. : the last two spans of each tile again, in a ring of THREE tiles.  Threads 0 and 1 read
+    // them after the barrier of tile i; a copy living in the two-tile ring would be overwritten by the
+    // stores of tile i+1, which no barrier separates from those reads.
+    constexpr int TAIL = RING, ROWS = RING + 3 * 2;
+    __shared__ uint4 s_pre[ROWS * 4];
+    __shared__ int2 s_xy[ROWS];
+    __shared__ uint8_t s_flag[ROWS];
 
     const TiledArgs &a = sa.t;
     const uint32_t per = (sa.n_tiles + gridDim.x - 1) / gridDim.x;
@@ -473,20 +477,21 @@ fir1_screen_persist_kernel(const ScreenArgs sa, const ScreenParams sp)
 
     // history of the first tile: the two spans in front of it go to the end of the "previous" half of the ring
     if (threadIdx.x < 2) {
-        const int par0 = (int) (t_begin & 1);
         const i64 g = a.out_lo + (i64) t_begin * L - 2 * SPT + (i64) threadIdx.x * SPT;
         uint32_t w[16], p[16], gd;
         int xs, ys;
         load_span(g, false, w);
         screen_span_stats(w, p, xs, ys, gd);
-        store_span((par0 ^ 1) * NT + (NT - 2) + threadIdx.x, p, xs, ys, gd);
+        store_span(TAIL + 2 * 2 + threadIdx.x, p, xs, ys, gd);     // slot 2 = "previous" of slot 0
     }
 
     uint32_t w_cur[16], w_nxt[16];
     load_span(a.out_lo + (i64) t_begin * L + (i64) threadIdx.x * SPT, tile_fast(t_begin), w_cur);
 
+    int slot = 0;                                   // (tile - t_begin) % 3
     for (uint32_t tile = t_begin; tile < t_end; tile++) {
         const int par = (int) (tile & 1);
+        const int prev_slot = (slot == 0) ? 2 : slot - 1;
         const i64 o0 = a.out_lo + (i64) tile * L;
         if (tile + 1 < t_end) {
             load_span(o0 + L + (i64) threadIdx.x * SPT, tile_fast(tile + 1), w_nxt);
@@ -496,9 +501,11 @@ fir1_screen_persist_kernel(const ScreenArgs sa, const ScreenParams sp)
         const int rp = par * NT + threadIdx.x;
         screen_span_stats(w_cur, pre, sx, sy, guard);
         store_span(rp, pre, sx, sy, guard);
-        __syncthreads();     // also orders this tile's reads of the other half before the next tile overwrites it
+        if (threadIdx.x >= NT - 2) store_span(TAIL + 2 * slot + (threadIdx.x - (NT - 2)), pre, sx, sy, guard);
+        __syncthreads();     // rows of this half are next written two tiles (= two barriers) from now
 
-        const int r1 = (rp + RING - 1) & (RING - 1), r2 = (rp + RING - 2) & (RING - 1);
+        const int r1 = (threadIdx.x >= 1) ? rp - 1 : TAIL + 2 * prev_slot + 1;
+        const int r2 = (threadIdx.x >= 2) ? rp - 2 : TAIL + 2 * prev_slot + (int) threadIdx.x;
         uint32_t bits16 = 0;
         bool undecided_lo = false, undecided_hi = false;
         const i64 o = o0 + (i64) threadIdx.x * SPT;
@@ -569,6 +576,7 @@ fir1_screen_persist_kernel(const ScreenArgs sa, const ScreenParams sp)
         }
 #pragma unroll
         for (int e = 0; e < 16; e++) w_cur[e] = w_nxt[e];
+        slot = (slot == 2) ? 0 : slot + 1;
     }
 }
 
