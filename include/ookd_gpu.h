@@ -162,6 +162,8 @@ struct ookd_gpu_config {
 #define OOKD_FLAG_FORCE_GENERIC  1u          /* always use the shape-agnostic FIR kernels       */
 #define OOKD_FLAG_TILE_PER_CTA_SCREEN 4u     /* one-tile-per-CTA form of the screening kernel instead of the
                                                 persistent, register-prefetching default                        */
+#define OOKD_FLAG_NO_TMA         8u          /* persistent screening kernel with register prefetch instead of the
+                                                TMA-staged default                                */
 #define OOKD_FLAG_NO_SCREEN      2u          /* disable the reduced-precision screen (exact MACs
                                                 for every sample)                                */
 

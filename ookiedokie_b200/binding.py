@@ -21,6 +21,7 @@ K_INF = 0xFFFFFFFF
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_SCREEN = 2
 FLAG_TILE_PER_CTA_SCREEN = 4
+FLAG_NO_TMA = 8
 
 # every symbol include/ookd_gpu.h declares
 EXPORTS = [

@@ -14,6 +14,7 @@
 
 #include "ookd_common.cuh"
 #include "fir_kernels.cuh"
+#include "screen_tma.cuh"
 #include "edge_kernels.cuh"
 #include "sm_kernels.cuh"
 #include "synth_kernel.cuh"
@@ -55,6 +56,7 @@ struct ookd_gpu {
     uint32_t flags = 0;
     bool screen = false;
     bool persist = false;
+    bool tma = false;                 // TMA-staged screening kernel (screen_tma.cuh)
     unsigned n_sm = 148;
 
     bool have_sm = false;
@@ -228,6 +230,27 @@ void make_screen_params_dec4(const ookd_gpu *h, ScreenParams &sp)
     sp.inv_n = 1.0f / 96.0f;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time libcuda dependency)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_fn tensor_map_encoder()
+{
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess) {
+            fn = (encode_tiled_fn) p;
+        }
+    }
+    return fn;
+}
+
 TiledArgs tiled_args(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
 {
     TiledArgs a{};
@@ -263,7 +286,39 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
             ScreenParams sp;
             make_screen_params(h, sp);
             sa.n_tiles = (uint32_t) stiles;
-            if (h->persist) {
+            if (h->tma) {
+                // Tensor view: rows of 32 samples starting at row0 (a tile boundary of this decode at or after the
+                // first sample present); only tiles that lie wholly inside complete rows use the copy engine.
+                ScreenTmaArgs ta{};
+                ta.s = sa;
+                const i64 first_present = in_base > 0 ? in_base : 0;
+                i64 row0 = h->bit_base;
+                if (row0 < first_present) row0 += (first_present - row0 + SCREEN_L - 1) / SCREEN_L * SCREEN_L;
+                const uintptr_t addr0 = (uintptr_t) (d_in + (row0 - in_base));
+                const i64 n_rows = (in_valid_end - row0) / 32;
+                CUtensorMap tmap;
+                memset(&tmap, 0, sizeof(tmap));
+                bool ok = (addr0 % 16 == 0) && n_rows >= SCREEN_L / 32 && n_rows < (1ll << 31) && tensor_map_encoder();
+                if (ok) {
+                    const cuuint64_t gdim[2] = {32, (cuuint64_t) n_rows};
+                    const cuuint64_t gstride[1] = {128};
+                    const cuuint32_t box[2] = {32, SCREEN_L / 32};
+                    const cuuint32_t estr[2] = {1, 1};
+                    ok = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *) addr0, gdim, gstride, box, estr,
+                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                }
+                ta.row0_sample = row0;
+                if (ok) {
+                    ta.fast_lo = (uint32_t) ((row0 - h->bit_base) / SCREEN_L);
+                    ta.fast_hi = (uint32_t) ((row0 + n_rows * 32 - h->bit_base) / SCREEN_L);
+                } else {
+                    ta.fast_lo = ta.fast_hi = 0;
+                }
+                const u64 ctas = (u64) h->n_sm * OOKD_STMA_MINB;
+                fir1_screen_tma_kernel<32><<<(unsigned) (stiles < ctas ? stiles : ctas), STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(
+                    tmap, ta, sp);
+            } else if (h->persist) {
                 const u64 ctas = (u64) h->n_sm * OOKD_SCREEN_PERSIST_MINB;
                 fir1_screen_persist_kernel<32><<<(unsigned) (stiles < ctas ? stiles : ctas), 256, 0, h->s_compute>>>(sa, sp);
             } else {
@@ -826,6 +881,14 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     }
     h->n_sm = (unsigned) prop.multiProcessorCount;
     h->persist = (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) == 0;
+    h->tma = h->persist && !(h->flags & OOKD_FLAG_NO_TMA);
+    if (h->tma) {
+        if (cudaFuncSetAttribute(fir1_screen_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STMA_SMEM_BYTES) !=
+            cudaSuccess) {
+            cudaGetLastError();
+            h->tma = false;
+        }
+    }
     // the screen needs a finite positive power threshold (thr <= 0 decides 1 everywhere, NaN 0 everywhere;
     // the exact kernels handle those directly)
     h->screen = (h->path == FIR_TILED_1STAGE_32) && !(h->flags & OOKD_FLAG_NO_SCREEN) && h->pstar > 0.0f &&

@@ -1,0 +1,303 @@
+// screen_tma.cuh -- production form of the one-stage (T = 32, decimation 1) screening kernel.
+//
+// Same decisions as fir1_screen_kernel / fir1_screen_persist_kernel (fir_kernels.cuh, section 3: the
+// Cauchy-Schwarz "off" proof on exact integer window energies, the mean/scatter "on" proof, everything
+// else to the exact refine kernel), different data movement.  ncu on the register-prefetching kernel
+// showed the LSU data pipe at 90 %: a thread owning 16 consecutive samples makes every LDG.128 of a
+// warp touch 16 cache lines.  Here the raw tile (4096 samples = 16 KiB) is brought in by ONE TMA
+// tensor copy per tile into a 3-stage shared-memory ring, with the 128-byte swizzle so that the
+// per-thread 64-byte rows are read (and their prefix sums written back IN PLACE) without bank
+// conflicts:
+//
+//   tensor view of the capture : rows of 32 samples (128 B); box = 128 rows = one tile
+//   smem address of 16-byte chunk c (0..7) of row R :  body + R*128 + ((c ^ (R & 7)) << 4)
+//   thread u owns samples 16u..16u+15 of the tile = chunks 4(u&1)..4(u&1)+3 of row u>>1
+//
+// Per tile and thread: wait for the stage's mbarrier, 4 LDS.128 (own raw words), statistics in
+// registers, 4 STS.128 (running prefix sums of |x|^2 over the own row, in place), one CTA barrier,
+// 4 LDS.128 (prefix row of thread u-2) + one word of thread u-1, decisions.  After the barrier thread 0
+// re-arms the stage freed by the previous tile and issues the copy of tile i+2.
+//
+// The two prefix rows in front of a tile (threads u-2, u-1 for u = 0, 1) live in a 128-byte "row -1" per
+// stage (virtual threads -2, -1, same address formula); the last two threads of tile i write theirs into
+// the history row of stage (i+1) % 3 as well, which nobody reads before the barrier of tile i+1 and
+// nobody rewrites before tile i+3.
+//
+// Tiles the tensor copy cannot serve (capture start/end, input not 16-byte aligned) take guarded
+// scalar loads into the same registers; everything after that is identical.
+#pragma once
+
+#include <cuda.h>
+
+#include "fir_kernels.cuh"
+
+namespace ookd {
+
+struct ScreenTmaArgs {
+    ScreenArgs s;            // s.tile_offset / s.n_tiles: tiles of this launch
+    i64 row0_sample;         // global sample index of tensor row 0
+    uint32_t fast_lo, fast_hi;   // tiles [fast_lo, fast_hi) (numbered like s.tile_offset) can use the tensor copy
+};
+
+constexpr int STMA_NT = 256, STMA_SPT = 16, STMA_L = STMA_NT * STMA_SPT;   // 4096 samples per tile
+constexpr int STMA_STAGES = 3;
+constexpr int STMA_BODY = STMA_L * 4;                           // 16 KiB per stage, 1024-byte aligned (128 B swizzle)
+constexpr int STMA_XY_ROWS = STMA_NT + 2;
+// bodies | history rows (128 B per stage) | (sum I, sum Q) rows | mbarriers, + 1 KiB alignment slack
+constexpr int STMA_SMEM_BYTES = 1024 + STMA_STAGES * STMA_BODY + STMA_STAGES * 128 + STMA_STAGES * STMA_XY_ROWS * 8 + 32;
+static_assert(4 * (STMA_SMEM_BYTES + 1024) <= 228 * 1024, "four CTAs per SM");
+
+#ifndef OOKD_STMA_MINB
+#define OOKD_STMA_MINB 4
+#endif
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t) __cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap *map, int32_t row, uint32_t bar)
+{
+    // streaming data: evict-first in L2 (the capture is read exactly once)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst), "l"((uint64_t) map), "r"(bar), "r"(0), "r"(row),
+        "l"(0x12F0000000000000ull)
+        : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// byte offset (relative to a stage body) of chunk v (0..3) of the row of (virtual) thread u
+__device__ __forceinline__ int stma_chunk_off(int u, int v)
+{
+    const int R = u >> 1;                                  // arithmetic: -1 for the history rows
+    return R * 128 + (((((u & 1) << 2) | v) ^ (R & 7)) << 4);
+}
+
+template <int T>
+__global__ void __launch_bounds__(STMA_NT, OOKD_STMA_MINB)
+fir1_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaArgs ta, const ScreenParams sp)
+{
+    static_assert(T == 32, "window = exactly two 16-sample thread spans");
+    constexpr int NT = STMA_NT, SPT = STMA_SPT, L = STMA_L, NS = STMA_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+
+    const ScreenArgs &sa = ta.s;
+    const TiledArgs &a = sa.t;
+    const uint32_t per = (sa.n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t t_begin = sa.tile_offset + blockIdx.x * per;
+    const uint32_t t_end = min(sa.tile_offset + sa.n_tiles, t_begin + per);
+    if (t_begin >= t_end) return;
+
+    const uint32_t body0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t hist0 = body0 + NS * STMA_BODY + 128u;      // + 128: history rows are "row -1" of their stage
+    const uint32_t xy0 = body0 + NS * STMA_BODY + NS * 128u;
+    const uint32_t bar0 = xy0 + NS * STMA_XY_ROWS * 8;
+
+    const int u = (int) threadIdx.x;
+    if (u == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto tile_fast = [&](uint32_t tile) -> bool { return tile >= ta.fast_lo && tile < ta.fast_hi; };
+    auto tile_row = [&](uint32_t tile) -> int32_t {
+        return (int32_t) ((a.out_lo + (i64) tile * L - ta.row0_sample) >> 5);
+    };
+    auto issue = [&](uint32_t tile, int s) {
+        const uint32_t bar = bar0 + 8 * s;
+        mbar_expect_tx(bar, L * 4);
+        tma_load_tile(body0 + s * STMA_BODY, &tmap, tile_row(tile), bar);
+    };
+    auto load_span_slow = [&](i64 g, uint32_t (&w)[16]) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            const i64 ge = g + e;
+            w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
+        }
+    };
+    // store one span's statistics as the row of virtual thread uu (>= 0: body, < 0: history rows) of stage s
+    auto store_row = [&](int s, int uu, const uint32_t (&p)[16], int xs, int ys) {
+        const uint32_t rb = (uu >= 0) ? body0 + s * STMA_BODY : hist0 + s * 128u;
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            sts128(rb + stma_chunk_off(uu, v), p[4 * v], p[4 * v + 1], p[4 * v + 2], p[4 * v + 3]);
+        }
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(xy0 + (s * STMA_XY_ROWS + uu + 2) * 8), "r"(xs), "r"(ys)
+                     : "memory");
+    };
+
+    // prologue: first two tiles in flight, history of the first tile
+    if (u == 0) {
+        if (tile_fast(t_begin)) issue(t_begin, 0);
+        if (t_begin + 1 < t_end && tile_fast(t_begin + 1)) issue(t_begin + 1, 1);
+    }
+    if (u < 2) {
+        uint32_t w[16], p[16], gd;
+        int xs, ys;
+        load_span_slow(a.out_lo + (i64) t_begin * L - 2 * SPT + (i64) u * SPT, w);
+        screen_span_stats(w, p, xs, ys, gd);
+        if (gd >> 25) p[15] = 0xFFFFFFFFu;
+        store_row(0, u - 2, p, xs, ys);
+    }
+
+    // own-row and neighbour-row offsets inside a stage body
+    int off_own[4], off_p2[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        off_own[v] = stma_chunk_off(u, v);
+        off_p2[v] = stma_chunk_off(u - 2, v);
+    }
+    const int off_tot1 = stma_chunk_off(u - 1, 3) + 12;
+
+    int s = 0;                     // stage of the current tile = (tile - t_begin) % NS
+    uint32_t phases = 0;           // bit s = parity the next wait on stage s uses
+    for (uint32_t tile = t_begin; tile < t_end; tile++) {
+        const uint32_t body = body0 + s * STMA_BODY;
+        const uint32_t hist = hist0 + s * 128u;
+        const i64 o0 = a.out_lo + (i64) tile * L;
+        uint32_t w[16];
+        if (tile_fast(tile)) {
+            mbar_wait(bar0 + 8 * s, (phases >> s) & 1u);
+            phases ^= 1u << s;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const uint4 x = lds128(body + off_own[v]);
+                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
+            }
+        } else {
+            load_span_slow(o0 + (i64) u * SPT, w);
+        }
+        uint32_t pre[SPT], guard;
+        int sx, sy;
+        screen_span_stats(w, pre, sx, sy, guard);
+        const uint32_t tot_own = (guard >> 25) ? 0xFFFFFFFFu : pre[15];     // bit 31 = "span out of range"
+        {
+            uint32_t p[16];
+#pragma unroll
+            for (int e = 0; e < 15; e++) p[e] = pre[e];
+            p[15] = tot_own;
+            store_row(s, u, p, sx, sy);
+            if (u >= NT - 2) {                                   // history rows of the next tile's stage
+                store_row(s == NS - 1 ? 0 : s + 1, u - NT, p, sx, sy);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (u == 0 && tile + 2 < t_end && tile_fast(tile + 2)) {
+            issue(tile + 2, s == 0 ? NS - 1 : s - 1);            // (s + 2) % 3: the stage tile-1 has just left
+        }
+
+        // ---- decisions for the 16 outputs of this thread (two groups of 8) ----
+        uint32_t p2[SPT];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const uint4 x = lds128((u < 2 ? hist : body) + off_p2[v]);
+            p2[4 * v] = x.x; p2[4 * v + 1] = x.y; p2[4 * v + 2] = x.z; p2[4 * v + 3] = x.w;
+        }
+        uint32_t tot1;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tot1) : "r"((u < 1 ? hist : body) + off_tot1));
+        const uint32_t tot2 = p2[SPT - 1];
+        uint32_t bits16 = 0;
+        bool undecided_lo = true, undecided_hi = true;
+        const i64 o = o0 + (i64) u * SPT;
+        if ((int) (tot_own | tot1 | tot2) >= 0) {
+            const uint32_t bsum = tot2 + tot1;
+            int dmax_lo = INT_MIN, dmax_hi = INT_MIN;
+#pragma unroll
+            for (int j = 0; j < SPT; j++) {
+                const int d = (int) (pre[j] - p2[j]);          // all sums < 2^31: signed difference is exact
+                if (j < 8) dmax_lo = max(dmax_lo, d); else dmax_hi = max(dmax_hi, d);
+            }
+            const bool off_lo = (uint32_t) ((int) bsum + dmax_lo) < sp.k0, off_hi = (uint32_t) ((int) bsum + dmax_hi) < sp.k0;
+            bool on = false;
+            if (!(off_lo && off_hi)) {
+                int x1, y1, x2, y2;
+                const uint32_t xy = xy0 + (s * STMA_XY_ROWS + u) * 8;     // rows u-2 (+0) and u-1 (+8)
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x2), "=r"(y2) : "r"(xy));
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x1), "=r"(y1) : "r"(xy + 8));
+                const float X = (float) (sx + x1 + x2), Y = (float) (sy + y1 + y2);
+                const float Q = (float) (bsum + pre[SPT - 1]);
+                const float m2 = fmaf(X, X, Y * Y);
+                const float mu = sqrt_approx(m2) * sp.inv_n;
+                const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
+                const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
+                on = fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi;
+            }
+            if (on) {
+                bits16 = 0xFFFFu;
+                undecided_lo = undecided_hi = false;
+            } else {
+                undecided_lo = !off_lo;
+                undecided_hi = !off_hi;
+            }
+        }
+        const bool in_lo = o < a.out_hi, in_hi = o + 8 < a.out_hi;
+        if (in_lo) {
+            const i64 byte = (o - a.bit_base) >> 3;
+            if (in_hi) {
+                *(uint16_t *) (a.out_bits + byte) = (uint16_t) bits16;
+            } else {
+                a.out_bits[byte] = (uint8_t) bits16;
+            }
+        }
+        const bool push_lo = undecided_lo && in_lo, push_hi = undecided_hi && in_hi;
+        const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, push_lo), m_hi = __ballot_sync(0xFFFFFFFFu, push_hi);
+        if (m_lo | m_hi) {
+            const uint32_t n_push = __popc(m_lo) + __popc(m_hi);
+            const int lane = u & 31;
+            uint32_t slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(sa.work_count, n_push);
+            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+            const uint32_t below = (1u << lane) - 1;
+            const uint32_t grp0 = (uint32_t) ((o - a.bit_base) >> 3);
+            if (push_lo) {
+                const uint32_t sl = slot0 + __popc(m_lo & below);
+                if (sl < sa.work_cap) sa.work_list[sl] = grp0;
+            }
+            if (push_hi) {
+                const uint32_t sl = slot0 + __popc(m_lo) + __popc(m_hi & below);
+                if (sl < sa.work_cap) sa.work_list[sl] = grp0 + 1;
+            }
+        }
+        s = (s == NS - 1) ? 0 : s + 1;
+    }
+}
+
+}  // namespace ookd
