@@ -369,7 +369,11 @@ int launch_fir_refine(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_val
     TapsParam<32> tp;
     memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
     ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
-    fir1_refine_kernel<32><<<8 * h->n_sm, 256, 0, h->s_compute>>>(sa, tp);
+    if (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) {
+        fir1_refine_kernel<32><<<8 * h->n_sm, 256, 0, h->s_compute>>>(sa, tp);      // lane-per-output form
+    } else {
+        fir1_refine_group_kernel<32><<<16 * h->n_sm, 128, 0, h->s_compute>>>(sa, tp);
+    }
     h->launches++;
     CU(h, cudaGetLastError());
     return OOKD_OK;
@@ -575,6 +579,54 @@ int run_state_machine_jacobi(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *
         return finish_messages(h, h->h_msgs_raw.data(), n_msgs, last, rounds_before + rounds, exit_, res);
     }
     return fail(h, OOKD_ERR_OVERFLOW, "message slots overflowed after retries");
+}
+
+// ---- decisions -> ordered edge list, one pass (edge_onepass_kernel); also fetches the scalars the host needs
+// (edge total, decisions around the shard start, number of groups the screen left to the refine kernel) ----
+int extract_edges(ookd_gpu *h, u64 n_bits, ookd_gpu_result *res)
+{
+    int rc;
+    Edge1Args x{};
+    x.e.words = (const u64 *) h->bits.p;
+    x.e.bit_base = h->bit_base;
+    x.e.start_bit = h->pre;
+    x.e.n_bits = (i64) n_bits;
+    const u64 n_words = (n_bits + 63) / 64;
+    const unsigned eg = (unsigned) ((n_words + EDGE1_WPB - 1) / EDGE1_WPB);
+    if ((rc = ensure(h, h->block_counts, sizeof(u64) * (eg + 1)))) return rc;
+    // room for one edge per 128 decisions; a capture with more is handled by growing the list and repeating
+    if ((rc = ensure(h, h->edges, sizeof(u64) * (n_bits / 128 + 65536)))) return rc;
+    h->stat_dense_tiles = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        x.status = (u64 *) h->block_counts.p;
+        x.ticket = (uint32_t *) ((char *) h->scalars.p + 24);
+        x.total = (u64 *) h->scalars.p;
+        x.e.edges = (u64 *) h->edges.p;
+        x.cap = h->edges.cap / sizeof(u64);
+        CU(h, cudaMemsetAsync(x.status, 0, sizeof(u64) * eg, h->s_compute));
+        CU(h, cudaMemsetAsync(x.ticket, 0, 4, h->s_compute));
+        edge_onepass_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(x);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        // scalars[0] = total edges; also the first word of decisions (base_bit), the word holding the shard's
+        // first decision (first_bit) and the refine counters
+        CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 8, h->bits.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 240, (const char *) h->bits.p + (((u64) (h->report_lo - h->bit_base)) >> 6) * 8,
+                              8, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 16, (char *) h->scalars.p + 16, 8, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaStreamSynchronize(h->s_compute));
+        h->n_edges = ((const u64 *) h->h_scalars)[0];
+        if (h->n_edges <= x.cap) break;
+        if (attempt == 1) return fail(h, OOKD_ERR_OVERFLOW, "edge list overflowed after growing");
+        if ((rc = ensure(h, h->edges, sizeof(u64) * (h->n_edges + 2)))) return rc;
+    }
+    const u64 w0 = ((const u64 *) h->h_scalars)[1];
+    // decision preceding the shard (or decision 0 itself at the capture start)
+    h->base_bit = (uint32_t) ((w0 >> (h->pre ? h->pre - 1 : 0)) & 1);
+    if (res) res->first_bit = (uint32_t) ((((const u64 *) h->h_scalars)[30] >> ((u64) (h->report_lo - h->bit_base) & 63)) & 1);
+    h->stat_refined_blocks = ((const uint32_t *) h->h_scalars)[4];
+    return OOKD_OK;
 }
 
 int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gpu_result *res, bool incremental = false)
@@ -1047,58 +1099,15 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     h->n_edges = 0;
     h->base_bit = 0;
     if (n_bits > 0) {
-        EdgeArgs ea{};
-        ea.words = (const u64 *) h->bits.p;
-        ea.bit_base = h->bit_base;
-        ea.start_bit = h->pre;
-        ea.n_bits = (i64) n_bits;
-        const u64 n_words = (n_bits + 63) / 64;
-        const unsigned eg = (unsigned) ((n_words + EDGE_WPB - 1) / EDGE_WPB);
-        if ((rc = ensure(h, h->block_counts, sizeof(uint32_t) * (eg + 1)))) return rc;
-        ea.block_counts = (uint32_t *) h->block_counts.p;
-        edge_count_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(ea);
-        scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>(ea.block_counts, eg, (u64 *) h->scalars.p);
-        h->launches += 2;
-        CU(h, cudaGetLastError());
-        // scalars[0] = total edges; also fetch the first word of decisions for first_bit/base_bit
-        CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
-        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 8, h->bits.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
-        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 240, (const char *) h->bits.p + (((u64) (h->report_lo - h->bit_base)) >> 6) * 8,
-                              8, cudaMemcpyDeviceToHost, h->s_compute));
-        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 16, (char *) h->scalars.p + 16, 12, cudaMemcpyDeviceToHost, h->s_compute));
-        CU(h, cudaStreamSynchronize(h->s_compute));
-        h->n_edges = ((const u64 *) h->h_scalars)[0];
-        const u64 w0 = ((const u64 *) h->h_scalars)[1];
-        // decision preceding the shard (or decision 0 itself at the capture start)
-        h->base_bit = (uint32_t) ((w0 >> (h->pre ? h->pre - 1 : 0)) & 1);
-        if (res) res->first_bit = (uint32_t) ((((const u64 *) h->h_scalars)[30] >> ((u64) (h->report_lo - h->bit_base) & 63)) & 1);
-        h->stat_refined_blocks = ((const uint32_t *) h->h_scalars)[4];
-        h->stat_dense_tiles = 0;
+        if ((rc = extract_edges(h, n_bits, res))) return rc;
         if ((h->screen || h->path == FIR_SCREEN_DEC4) && h->stat_refined_blocks > h->work_cap) {
-            // too many undecided groups for the work list: redo the decisions exactly, recount the edges, and
-            // stop screening on this handle (the capture is not in the regime where it pays)
+            // too many undecided groups for the work list: redo the decisions exactly, extract the edges again,
+            // and stop screening on this handle (the capture is not in the regime where it pays)
             h->stat_dense_tiles = 1;
             h->screen = false;
             if ((rc = launch_fir_exact_all(h, d_in, in_base, in_valid_end))) return rc;
-            edge_count_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(ea);
-            scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>(ea.block_counts, eg, (u64 *) h->scalars.p);
-            h->launches += 2;
-            CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
-            CU(h, cudaMemcpyAsync((char *) h->h_scalars + 8, h->bits.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
-            CU(h, cudaMemcpyAsync((char *) h->h_scalars + 240, (const char *) h->bits.p + (((u64) (h->report_lo - h->bit_base)) >> 6) * 8,
-                                  8, cudaMemcpyDeviceToHost, h->s_compute));
-            CU(h, cudaStreamSynchronize(h->s_compute));
-            h->n_edges = ((const u64 *) h->h_scalars)[0];
-            const u64 w0b = ((const u64 *) h->h_scalars)[1];
-            h->base_bit = (uint32_t) ((w0b >> (h->pre ? h->pre - 1 : 0)) & 1);
-            if (res) res->first_bit = (uint32_t) ((((const u64 *) h->h_scalars)[30] >> ((u64) (h->report_lo - h->bit_base) & 63)) & 1);
-        }
-        if ((rc = ensure(h, h->edges, sizeof(u64) * (h->n_edges + 2)))) return rc;
-        if (h->n_edges) {
-            ea.edges = (u64 *) h->edges.p;
-            edge_write_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(ea);
-            h->launches++;
-            CU(h, cudaGetLastError());
+            if ((rc = extract_edges(h, n_bits, res))) return rc;
+            h->stat_dense_tiles = 1;
         }
     } else {
         if ((rc = ensure(h, h->edges, 16))) return rc;
