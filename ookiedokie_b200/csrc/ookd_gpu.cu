@@ -65,7 +65,7 @@ struct ookd_gpu {
 
     // workspaces
     DevBuf in, bits, inter[2], block_counts, edges, scalars, chunk_exit[2], chunk_ran, slots, slot_count,
-           slot_off, msgs_dev, dense_list, final_entry, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
+           slot_off, msgs_dev, dense_list, chunk_e, final_entry, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
     uint32_t slot_cap = 8;
     bool tables_valid = false;       // entry/exit tables of the last decode can be extended by resolve
     int tab_cur = 0;
@@ -507,6 +507,7 @@ SmArgs base_sm_args(ookd_gpu *h, const SmCarry &entry0)
     a.overflow = (uint32_t *) ((char *) h->scalars.p + 32);
     a.warm = h->warm ? 1u : 0u;
     a.first_chunk = 0;
+    a.chunk_e = (u64 *) h->chunk_e.p;
     return a;
 }
 
@@ -661,6 +662,13 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
 
     if (!(incremental && h->tables_valid)) incremental = false;
     h->tables_valid = false;
+    if (!incremental) {
+        if ((rc = ensure(h, h->chunk_e, sizeof(u64) * nc))) return rc;
+        SmArgs ia = base_sm_args(h, entry0);
+        sm_chunk_index_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(ia);
+        h->launches++;
+        CU(h, cudaGetLastError());
+    }
     // With warm-up history chunk 0 lies in front of the shard.  A decode walks from its anchored seed and
     // reports the state it reaches at the shard's first output; a resolve (explicit entry) bypasses it.
     h->first_chunk = (h->warm && incremental) ? 1u : 0u;
@@ -722,6 +730,14 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
                 h->launches++;
                 CU(h, cudaGetLastError());
                 rounds++;
+                if (burst == 3 && r == 1) {
+                    // rounds 0+1 resolve the common case: link and walk now, so that round 2 (and the second
+                    // link/walk) return at once instead of costing another chunk-long latency
+                    a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
+                    sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
+                    sm_walk_kernel<<<1, 1024, 0, h->s_compute>>>(a);
+                    h->launches += 2;
+                }
             }
             a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
             sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
@@ -820,7 +836,7 @@ void ookd_gpu_destroy(ookd_gpu *h)
     if (h->d_tab) cudaFree(h->d_tab);
     DevBuf *all[] = {&h->in, &h->bits, &h->inter[0], &h->inter[1], &h->block_counts, &h->edges, &h->scalars,
                      &h->chunk_exit[0], &h->chunk_exit[1], &h->chunk_ran, &h->slots, &h->slot_count,
-                     &h->slot_off, &h->msgs_dev, &h->dense_list, &h->final_entry, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
+                     &h->slot_off, &h->msgs_dev, &h->dense_list, &h->chunk_e, &h->final_entry, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
                      &h->tab_cnt[1], &h->tab_link, &h->tab_chosen};
     for (DevBuf *b : all) release(*b);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);

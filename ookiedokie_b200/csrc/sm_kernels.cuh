@@ -73,6 +73,7 @@ struct SmArgs {
     uint32_t first_chunk;     // chunk the walk starts at (1 when chunk 0 is a warm-up chunk being bypassed)
     uint32_t warm;            // chunk 0 is a warm-up chunk in front of the shard: it has no true entry
     SmCarry  *final_entry;    // warm: state at the shard's first output = exit of chunk 0's chosen pair
+    u64 *chunk_e;             // [n_chunks] index of the first edge at or after each chunk's start (sm_chunk_index_kernel)
 };
 
 __device__ __forceinline__ i64 first_output_of_buffer(const SmArgs &a, u64 b)
@@ -112,10 +113,12 @@ __device__ __forceinline__ int sm_apply(const SmTable &T, SmCarry &s, const ookd
         if (s.num_bits <= T.max_bits && s.num_bits < 256) {
             const u64 m = 1ull << (s.num_bits & 63);
             const uint32_t w = s.num_bits >> 6;
-            if (t.action == OOKD_ACT_APPEND_1) {
-                s.data[w] |= m;
-            } else {
-                s.data[w] &= ~m;
+            const u64 set = (t.action == OOKD_ACT_APPEND_1) ? m : 0ull;
+            // no dynamic indexing: the carry must stay in registers (a local-memory carry costs an L1 round
+            // trip per field access, dozens per step)
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) {
+                if (i == w) s.data[i] = (s.data[i] & ~m) | set;
             }
         }
         s.num_bits++;
@@ -238,6 +241,22 @@ __device__ __forceinline__ u64 edge_lower_bound(const u64 *edges, u64 n, u64 pos
 }
 
 
+// Same, for a position expected to lie only a few edges ahead (the next buffer after an ERROR): gallop, then bisect.
+__device__ __forceinline__ u64 edge_lower_bound_near(const u64 *edges, u64 n, u64 pos)
+{
+    u64 lo = 0, step = 1;
+    while (lo + step <= n && edges[lo + step - 1] < pos) {
+        lo += step;
+        step <<= 1;
+    }
+    u64 hi = (lo + step - 1 < n) ? lo + step - 1 : n;      // edges[hi] >= pos (or hi == n); edges[lo-1] < pos
+    while (lo < hi) {
+        const u64 mid = (lo + hi) >> 1;
+        if (edges[mid] < pos) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 struct SpanOut {
     SmMsg   *slots;
     uint32_t cap;
@@ -297,7 +316,7 @@ __device__ __forceinline__ int sm_run_span(const SmArgs &a, const SmTable &T, Sm
                 if (nb > end) nb = end;
                 if (nb > pos) {
                     if (next_edge < (u64) nb) {
-                        const u64 e2 = e + edge_lower_bound(a.edges + e, a.n_edges - e, (u64) nb);
+                        const u64 e2 = e + edge_lower_bound_near(a.edges + e, a.n_edges - e, (u64) nb);
                         tb ^= (uint32_t) ((e2 - e) & 1);
                         e = e2;
                         next_edge = (e < a.n_edges) ? a.edges[e] : INF;
@@ -337,6 +356,213 @@ __device__ __forceinline__ int sm_run_span(const SmArgs &a, const SmTable &T, Sm
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Warp-cooperative form of the same machine (machines with <= 32 triggers and <= 32 states).
+//
+// A run is one chain of dependent steps, so its cost is latency per step.  The per-thread form above
+// walks the state's trigger list with shared-memory loads and data-dependent branches (~200 instructions
+// and ~2500 cycles per edge).  Here lane j owns trigger j of the compiled machine in REGISTERS, the carry is
+// replicated in every lane, and one evaluation is: every lane tests its own trigger, a ballot picks the
+// first eligible one in list order (= lowest lane), a shuffle broadcasts its action.  No loop, no
+// shared memory, no divergence; the first quiet firing count is a warp min-reduction.  Semantics are
+// those of sm_eval / sm_step / sm_next_quiet_fire / sm_run_span<false> line by line.
+// ---------------------------------------------------------------------------------------
+struct WarpSm {
+    uint32_t t_state;         // state owning this lane's trigger (0xFFFFFFFF: lane has no trigger)
+    uint32_t t_cond, t_pack;  // condition; action | next_state << 8
+    uint32_t t_kmin, t_kmax;
+    uint32_t s_dmin, s_dmax, s_ktimeout;   // of that state
+    uint32_t ksat_by_state;   // lane s: ksat of state s
+    uint32_t max_bits;
+};
+
+__device__ __forceinline__ bool warp_sm_supported(const SmTable *tab)
+{
+    return tab->num_triggers <= 32 && tab->num_states <= 32;
+}
+
+__device__ __forceinline__ void warp_sm_load(WarpSm &W, const SmTable *tab, uint32_t lane)
+{
+    W.max_bits = tab->max_bits;
+    W.t_state = 0xFFFFFFFFu;
+    W.t_cond = 0; W.t_pack = 0; W.t_kmin = 1; W.t_kmax = 0;
+    W.s_dmin = 0; W.s_dmax = 0; W.s_ktimeout = OOKD_K_INF;
+    W.ksat_by_state = (lane < tab->num_states) ? tab->states[lane].ksat : 0u;
+    if (lane < tab->num_triggers) {
+        const ookd_sm_trigger_k t = tab->triggers[lane];
+        W.t_cond = (uint32_t) t.cond;
+        W.t_pack = (uint32_t) t.action | (t.next_state << 8);
+        W.t_kmin = t.kmin; W.t_kmax = t.kmax;
+        for (uint32_t st = 0; st < tab->num_states; st++) {
+            const ookd_sm_state_k x = tab->states[st];
+            if (lane >= x.first_trigger && lane < x.first_trigger + x.num_triggers) {
+                W.t_state = st;
+                W.s_dmin = x.dmin; W.s_dmax = x.dmax; W.s_ktimeout = x.ktimeout;
+            }
+        }
+    }
+}
+
+// sm_apply with the fired trigger's packed (action, next)
+__device__ __forceinline__ int warp_sm_apply(const WarpSm &W, SmCarry &s, uint32_t pack)
+{
+    const uint32_t action = pack & 0xFFu;
+    int result = 0;
+    if (action == OOKD_ACT_APPEND_0 || action == OOKD_ACT_APPEND_1) {
+        if (s.num_bits <= W.max_bits && s.num_bits < 256) {
+            const u64 m = 1ull << (s.num_bits & 63);
+            const uint32_t w = s.num_bits >> 6;
+            const u64 set = (action == OOKD_ACT_APPEND_1) ? m : 0ull;
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++) {
+                if (i == w) s.data[i] = (s.data[i] & ~m) | set;
+            }
+        }
+        s.num_bits++;
+    } else if (action == OOKD_ACT_OUTPUT_DATA) {
+        result = 1;
+    }
+    s.state = pack >> 8;
+    return result;
+}
+
+// sm_eval: one trigger evaluation on sample value b
+__device__ __forceinline__ int warp_sm_eval(const WarpSm &W, SmCarry &s, uint32_t b)
+{
+    const uint32_t k = s.k;
+    const bool rise = !s.prev && b, fall = s.prev && !b;
+    const bool cond_ok = (W.t_cond == OOKD_COND_ALWAYS) || (W.t_cond == OOKD_COND_PULSE_START && rise) ||
+                         (W.t_cond == OOKD_COND_PULSE_END && fall) ||
+                         (W.t_cond == OOKD_COND_TIMEOUT && W.s_ktimeout != OOKD_K_INF && k >= W.s_ktimeout) ||
+                         (W.t_cond == OOKD_COND_MSG_COMPLETE && s.num_bits >= W.max_bits);
+    const bool elig = (W.t_state == s.state) && k >= W.t_kmin && k <= W.t_kmax && cond_ok;
+    const uint32_t mask = __ballot_sync(0xFFFFFFFFu, elig);
+    if (mask == 0) {
+        const uint32_t ksat = __shfl_sync(0xFFFFFFFFu, W.ksat_by_state, (int) s.state);
+        s.k = (k + 1 < ksat) ? k + 1 : ksat;
+        return 0;
+    }
+    const int f = __ffs(mask) - 1;
+    const bool is_edge = (W.t_cond == OOKD_COND_PULSE_START || W.t_cond == OOKD_COND_PULSE_END);
+    const uint32_t dur = __ballot_sync(0xFFFFFFFFu, !is_edge || (k >= W.s_dmin && k <= W.s_dmax));
+    const uint32_t pack = __shfl_sync(0xFFFFFFFFu, W.t_pack, f);
+    int result;
+    if ((dur >> f) & 1u) {
+        result = warp_sm_apply(W, s, pack);
+    } else {
+        result = -1;
+        s.state = 0;
+    }
+    s.k = 0;
+    return result;
+}
+
+// sm_step: process() + the prev_bit update
+__device__ __forceinline__ int warp_sm_step(const WarpSm &W, SmCarry &s, uint32_t b)
+{
+    int r = 0;
+    if (s.state == 0) {
+        s.num_bits = 0;
+        const uint32_t nbytes = (W.max_bits + 7) >> 3;
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const uint32_t lo = 8u * w;
+            if (nbytes >= lo + 8) {
+                s.data[w] = 0;
+            } else if (nbytes > lo) {
+                s.data[w] &= ~((1ull << (8 * (nbytes - lo))) - 1);
+            }
+        }
+        r = warp_sm_eval(W, s, b);
+    }
+    if (r == 0) {
+        r = warp_sm_eval(W, s, b);
+    }
+    s.prev = b;
+    return r;
+}
+
+// sm_next_quiet_fire: first count >= s.k at which a trigger that needs no edge fires; lane of that trigger or -1
+__device__ __forceinline__ int warp_sm_next_quiet_fire(const WarpSm &W, const SmCarry &s, uint32_t *k_fire)
+{
+    bool applicable = (W.t_state == s.state);
+    uint32_t lo = W.t_kmin;
+    if (W.t_cond == OOKD_COND_TIMEOUT) {
+        applicable = applicable && (W.s_ktimeout != OOKD_K_INF);
+        lo = max(lo, W.s_ktimeout);
+    } else if (W.t_cond == OOKD_COND_MSG_COMPLETE) {
+        applicable = applicable && (s.num_bits >= W.max_bits);
+    } else if (W.t_cond != OOKD_COND_ALWAYS) {
+        applicable = false;
+    }
+    uint32_t kk = max(lo, s.k);
+    if (!applicable || kk > W.t_kmax) kk = OOKD_K_INF;
+    const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, kk);
+    *k_fire = m;
+    if (m == OOKD_K_INF) return -1;
+    return __ffs(__ballot_sync(0xFFFFFFFFu, kk == m)) - 1;     // earlier list position wins ties
+}
+
+// sm_run_span<false>, executed by a whole warp with uniform control flow; lane 0 emits the messages.
+__device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const WarpSm &W, SmCarry &s, i64 pos, i64 end, u64 e,
+                                                 uint32_t tb, SpanOut &o, i64 chunk_lo, uint32_t lane)
+{
+    const u64 INF = ~0ull;
+    u64 next_edge = (e < a.n_edges) ? a.edges[e] : INF;
+    u64 after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;   // one-ahead prefetch
+
+    while (pos < end) {
+        const bool at_edge = (next_edge == (u64) pos);
+        if (s.state == 0 || s.prev != tb || at_edge) {
+            const uint32_t b = at_edge ? (tb ^ 1u) : tb;
+            const int r = warp_sm_step(W, s, b);
+            if (at_edge) {
+                tb ^= 1u;
+                e++;
+                next_edge = after_edge;
+                after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;
+            }
+            pos++;
+            if (r > 0) {
+                if (lane == 0) sm_emit(o, s, pos - 1); else o.n_msgs++;
+            } else if (r < 0) {
+                i64 nb = next_buffer_start(a, pos - 1, chunk_lo);
+                if (nb > end) nb = end;
+                if (nb > pos) {
+                    if (next_edge < (u64) nb) {
+                        const u64 e2 = e + edge_lower_bound_near(a.edges + e, a.n_edges - e, (u64) nb);
+                        tb ^= (uint32_t) ((e2 - e) & 1);
+                        e = e2;
+                        next_edge = (e < a.n_edges) ? a.edges[e] : INF;
+                        after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;
+                    }
+                    pos = nb;
+                }
+            }
+            continue;
+        }
+        const u64 limit = (next_edge < (u64) end) ? next_edge : (u64) end;
+        const u64 gap = limit - (u64) pos;
+        uint32_t k_fire;
+        const int tf = warp_sm_next_quiet_fire(W, s, &k_fire);
+        if (tf >= 0 && (u64) (k_fire - s.k) < gap) {
+            pos += (i64) (k_fire - s.k);
+            const uint32_t pack = __shfl_sync(0xFFFFFFFFu, W.t_pack, tf);
+            const int r = warp_sm_apply(W, s, pack);
+            s.k = 0;
+            pos++;
+            if (r > 0) {
+                if (lane == 0) sm_emit(o, s, pos - 1); else o.n_msgs++;
+            }
+        } else {
+            const uint32_t ksat = __shfl_sync(0xFFFFFFFFu, W.ksat_by_state, (int) s.state);
+            const u64 kk = (u64) s.k + gap;
+            s.k = (kk < (u64) ksat) ? (uint32_t) kk : ksat;
+            pos = (i64) limit;
+        }
+    }
+}
+
 // Copy the used part of the compiled machine into shared memory (header, states, triggers).
 __device__ __forceinline__ void load_table(SmTable &T, const SmTable *src_tab)
 {
@@ -356,6 +582,16 @@ __device__ __forceinline__ void chunk_bounds(const SmArgs &a, uint32_t c, i64 &s
     start = (c == 0) ? a.out_lo : first_output_of_buffer(a, a.first_buffer + (u64) c * a.chunk_buffers);
     end = first_output_of_buffer(a, a.first_buffer + (u64) (c + 1) * a.chunk_buffers);
     if (end > a.out_hi || c == a.n_chunks - 1) end = a.out_hi;
+}
+
+// e_start[c] for every chunk, once per decode: the rounds then start without a binary search.
+__global__ void __launch_bounds__(128) sm_chunk_index_kernel(const SmArgs a)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chunks) return;
+    i64 start, end;
+    chunk_bounds(a, c, start, end);
+    a.chunk_e[c] = edge_lower_bound(a.edges, a.n_edges, (u64) start);
 }
 
 __device__ __forceinline__ void carry_reset(SmCarry &s, uint32_t prev)
@@ -381,15 +617,19 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
     const uint32_t gid = blockIdx.x;
     const uint32_t c = gid / KR, j = gid % KR;
     if (c >= a.n_chunks) return;
+    if (a.round >= 2 && a.walk_status[1]) return;            // an earlier walk of this burst already resolved the chain
     if (a.round != 0) {
         // cheap rejection before anything is staged: most (chunk, slot) pairs have nothing new to run
         if (c == 0 || j >= a.cnt_in[c - 1]) return;
     }
     load_table(T, a.tab);
+    const bool warp_ok = warp_sm_supported(a.tab);
+    WarpSm W;
+    if (warp_ok) warp_sm_load(W, &T, lane);
 
     i64 start, end;
     chunk_bounds(a, c, start, end);
-    u64 e = edge_lower_bound(a.edges, a.n_edges, (u64) start);
+    u64 e = a.chunk_e[c];
     uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);           // true decision at start-1
 
     SmCarry s, entry;
@@ -427,7 +667,7 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
                 if (m_cand != 0xFFFFFFFFu) break;            // ran out of rising edges in this chunk
             }
         }
-        if (lane != 0) return;
+        if (!warp_ok && lane != 0) return;
         if (c == 0 && !a.warm) {
             s = a.entry0;
             entry = s;
@@ -443,9 +683,9 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
             entry = s;
         }
         slot = 0;
-        a.cnt_out[c] = 1;
+        if (lane == 0) a.cnt_out[c] = 1;
     } else {
-        if (lane != 0) return;
+        if (!warp_ok && lane != 0) return;
         if (c == 0) return;
         const uint32_t n_prev = a.cnt_in[c - 1];
         if (j >= n_prev) return;
@@ -457,21 +697,28 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
         for (uint32_t i = 0; i < n_here; i++) {            // already an entry of this chunk
             if (carry_equal(s, a.tab_entry[(u64) c * K + i])) return;
         }
-        slot = atomicAdd(&a.cnt_out[c], 1u);
+        slot = 0;
+        if (lane == 0) slot = atomicAdd(&a.cnt_out[c], 1u);
+        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);            // (warp_ok: all lanes are here; else only lane 0)
         if (slot >= K) {
-            atomicExch(a.overflow, 2u);                     // table full: host falls back
+            if (lane == 0) atomicExch(a.overflow, 2u);      // table full: host falls back
             return;
         }
         entry = s;
     }
-    atomicAdd(&a.n_ran[a.counter_idx], 1u);
+    if (lane == 0) atomicAdd(&a.n_ran[a.counter_idx], 1u);
 
     SpanOut o;
     o.slots = a.slots + ((u64) c * K + slot) * a.slot_cap;
     o.cap = a.slot_cap;
     o.n_msgs = 0;
     o.overflow = a.overflow;
-    sm_run_span<false>(a, T, s, pos, end, e, tb, o, start);
+    if (warp_ok) {
+        warp_sm_run_span(a, W, s, pos, end, e, tb, o, start, lane);
+        if (lane != 0) return;
+    } else {
+        sm_run_span<false>(a, T, s, pos, end, e, tb, o, start);
+    }
 
     a.tab_entry[(u64) c * K + slot] = entry;
     a.tab_exit[(u64) c * K + slot] = s;
@@ -496,7 +743,7 @@ __global__ void __launch_bounds__(32) sm_table_add_entry_kernel(const SmArgs a)
     if (n_here >= K) { atomicExch(a.overflow, 2u); return; }
     i64 start, end;
     chunk_bounds(a, c, start, end);
-    const u64 e = edge_lower_bound(a.edges, a.n_edges, (u64) start);
+    const u64 e = a.chunk_e[c];
     const uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);
     SpanOut o;
     o.slots = a.slots + ((u64) c * K + n_here) * a.slot_cap;
@@ -519,6 +766,7 @@ __global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t c = gid / K, i = gid % K;
     if (c >= a.n_chunks) return;
+    if (a.walk_status[1]) return;                            // already resolved: keep the links the walk used
     uint8_t l = 0xFF;
     if (c + 1 < a.n_chunks && i < a.cnt_in[c]) {
         const SmCarry x = a.tab_exit[(u64) c * K + i];
@@ -541,6 +789,7 @@ __global__ void __launch_bounds__(1024) sm_walk_kernel(const SmArgs a)
     __shared__ uint8_t s_in[1024];                           // entry slot of each segment (0xFF = unreachable)
     __shared__ uint32_t s_carry, s_max;
     const uint32_t K = a.tab_k;                              // == 8 (one 8-byte link row per chunk)
+    if (a.walk_status[1]) return;                            // resolved by an earlier walk of this burst
     if (threadIdx.x == 0) { s_carry = *a.start_slot; s_max = 0; }
     __syncthreads();
     uint32_t done = 0;
