@@ -164,6 +164,8 @@ struct ookd_gpu_config {
                                                 persistent, register-prefetching default                        */
 #define OOKD_FLAG_NO_TMA         8u          /* persistent screening kernel with register prefetch instead of the
                                                 TMA-staged default                                */
+#define OOKD_FLAG_SYNC_TAIL      16u         /* edges / state machine with a host synchronisation between the
+                                                stages instead of the single-synchronisation default */
 #define OOKD_FLAG_NO_SCREEN      2u          /* disable the reduced-precision screen (exact MACs
                                                 for every sample)                                */
 

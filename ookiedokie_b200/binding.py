@@ -22,6 +22,7 @@ FLAG_FORCE_GENERIC = 1
 FLAG_NO_SCREEN = 2
 FLAG_TILE_PER_CTA_SCREEN = 4
 FLAG_NO_TMA = 8
+FLAG_SYNC_TAIL = 16
 
 # every symbol include/ookd_gpu.h declares
 EXPORTS = [

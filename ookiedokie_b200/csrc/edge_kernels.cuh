@@ -113,114 +113,169 @@ __global__ void __launch_bounds__(EDGE_NT) edge_write_kernel(const EdgeArgs a)
 }
 
 // ---------------------------------------------------------------------------------------
-// One-pass form: count, scan and ordered write in a single sweep over the decisions (chained scan with
-// decoupled look-back).  CTAs take their position from a ticket counter, so a CTA only ever waits for
-// CTAs that started before it.  status[i] = flag << 62 | value, flag 1 = CTA i's own count,
-// flag 2 = inclusive count of CTAs 0..i.  Edges beyond `cap` are counted but not written (the host then
-// grows the list and repeats the pass).
+// Production form: tile-local extraction + flatten.
+//   edge_local   : persistent CTAs stream the decisions once (coalesced 16-byte loads, next tile prefetched
+//                  into registers), keep the transition masks in registers and write each 32 KiB tile's edges,
+//                  in order, into that tile's own fixed-size region.  No inter-CTA dependency.
+//   scan_u32     : exclusive scan of the per-tile counts (+ total)
+//   edge_flatten : copies the regions to their final positions; also leaves the header the state-machine
+//                  kernels / the host's single read-back need.
+// A tile with more edges than its region holds (1 per 128 decisions) sets the overflow flag; the host then
+// uses the count / scan / write kernels above.
 // ---------------------------------------------------------------------------------------
-constexpr int EDGE1_WPT = 8;                         // words per thread (64 B)
-constexpr int EDGE1_WPB = EDGE_NT * EDGE1_WPT;       // words per CTA (16 KiB of decisions)
+constexpr int EDGE1_ROWS = 8;                        // rows per warp; a row = 32 lanes x 2 words (512 B, coalesced)
+constexpr int EDGE1_WPW = EDGE1_ROWS * 64;           // words per warp (4 KiB of decisions)
+constexpr int EDGE1_WPB = (EDGE_NT / 32) * EDGE1_WPW;   // words per tile (32 KiB)
+constexpr int EDGE1_CAP = EDGE1_WPB * 64 / 128;      // edges a tile's region holds (2048)
 
 struct Edge1Args {
-    EdgeArgs e;
-    u64 *status;             // [gridDim.x], zeroed before the launch
-    uint32_t *ticket;        // zeroed before the launch
-    u64 *total;              // out: number of edges
+    EdgeArgs e;              // e.block_counts: [n_tiles] counts (local) / exclusive offsets (flatten); e.edges: final list
+    u64 *tmp;                // [n_tiles * EDGE1_CAP] tile regions
+    uint32_t n_tiles;
+    uint32_t *overflow;      // set to 1 if a tile overflowed its region
+    const u64 *total;        // (flatten) total edge count from the scan
     u64 cap;                 // capacity of e.edges
+    u64 *hdr;                // (flatten) [0] = min(total, cap), [1] = decision in front of the shard (low 32 bits),
+                             // [2] = first word of decisions, [3] = word holding the shard's first decision
+    i64 report_word;         // index of that word
 };
 
-__global__ void __launch_bounds__(EDGE_NT) edge_onepass_kernel(const Edge1Args x)
+__global__ void __launch_bounds__(EDGE_NT) edge_local_kernel(const Edge1Args x)
 {
     const EdgeArgs &a = x.e;
-    __shared__ uint32_t s_bid;
-    __shared__ u64 s_prefix;
-    if (threadIdx.x == 0) s_bid = atomicAdd(x.ticket, 1u);
-    __syncthreads();
-    const uint32_t bid = s_bid;
-    const i64 w0 = ((i64) bid * EDGE_NT + threadIdx.x) * EDGE1_WPT;
+    __shared__ uint32_t s_warp_cnt[2][EDGE_NT / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const i64 n_words = (a.n_bits + 63) >> 6;
 
-    u64 w[EDGE1_WPT], t[EDGE1_WPT];
-    if (w0 + EDGE1_WPT <= n_words) {
-        const ulonglong2 *src = (const ulonglong2 *) (a.words + w0);      // bits buffer is 16-byte aligned, w0 % 8 == 0
+    auto load_tile = [&](uint32_t tile, u64 (&w)[EDGE1_ROWS][2], u64 &carry) {
+        const i64 wbase = ((i64) tile * (EDGE_NT / 32) + warp) * EDGE1_WPW;
+        const bool full = (wbase + EDGE1_WPW) <= n_words;
 #pragma unroll
-        for (int q = 0; q < EDGE1_WPT / 2; q++) {
-            const ulonglong2 v = src[q];
-            w[2 * q] = v.x;
-            w[2 * q + 1] = v.y;
+        for (int r = 0; r < EDGE1_ROWS; r++) {
+            const i64 wi = wbase + r * 64 + 2 * lane;
+            if (full) {
+                const ulonglong2 v = *(const ulonglong2 *) (a.words + wi);      // 16-byte aligned: wi is even
+                w[r][0] = v.x; w[r][1] = v.y;
+            } else {
+                w[r][0] = (wi < n_words) ? a.words[wi] : 0ull;
+                w[r][1] = (wi + 1 < n_words) ? a.words[wi + 1] : 0ull;
+            }
         }
-    } else {
-#pragma unroll
-        for (int q = 0; q < EDGE1_WPT; q++) w[q] = (w0 + q < n_words) ? a.words[w0 + q] : 0ull;
-    }
-    u64 prev = (w0 == 0) ? (w[0] & 1) : ((w0 <= n_words) ? (a.words[w0 - 1] >> 63) : 0ull);
-    uint32_t c = 0;
-#pragma unroll
-    for (int q = 0; q < EDGE1_WPT; q++) {
-        const i64 lo = (w0 + q) * 64;
-        u64 m = w[q] ^ ((w[q] << 1) | prev);
-        prev = w[q] >> 63;
-        if (lo < a.start_bit) {
-            const i64 sh = a.start_bit - lo;
-            m = (sh >= 64) ? 0 : (m >> sh) << sh;
-        }
-        if (lo + 64 > a.n_bits) {
-            const i64 keep = a.n_bits - lo;
-            m = (keep <= 0) ? 0 : (m & ((keep >= 64) ? ~0ull : ((1ull << keep) - 1)));
-        }
-        t[q] = m;
-        c += __popcll(m);
-    }
-    uint32_t total;
-    const uint32_t excl = block_exclusive_scan_256(c, &total);
+        carry = 0;                                        // top bit of the word in front of the warp's first row
+        if (wbase < n_words) carry = (wbase == 0) ? (a.words[0] & 1) : (a.words[wbase - 1] >> 63);
+    };
 
-    if (threadIdx.x < 32) {
-        const uint32_t lane = threadIdx.x;
-        volatile u64 *st = x.status;
-        if (lane == 0) {
-            st[bid] = ((bid == 0 ? 2ull : 1ull) << 62) | (u64) total;
-            __threadfence();
-        }
-        u64 run = 0;
-        if (bid > 0) {
-            i64 top = (i64) bid - 1;                   // nearest predecessor not yet accounted for
-            for (;;) {
-                const i64 i = top - lane;
-                u64 v;
-                do {
-                    v = (i >= 0) ? st[i] : (2ull << 62);            // before CTA 0: inclusive prefix 0
-                } while (__any_sync(0xFFFFFFFFu, (v >> 62) == 0));
-                const uint32_t incl = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
-                const uint32_t upto = incl ? (uint32_t) (__ffs(incl) - 1) : 31u;   // lanes 0..upto contribute
-                u64 part = (lane <= upto) ? (v & ((1ull << 62) - 1)) : 0ull;
+    u64 w[EDGE1_ROWS][2], wn[EDGE1_ROWS][2], carry, carry_n = 0;
+    uint32_t tile = blockIdx.x;
+    if (tile >= x.n_tiles) return;
+    load_tile(tile, w, carry);
+    for (uint32_t it = 0; tile < x.n_tiles; tile += gridDim.x, it++) {
+        const uint32_t nxt = tile + gridDim.x;
+        if (nxt < x.n_tiles) load_tile(nxt, wn, carry_n);
+        const i64 wbase = ((i64) tile * (EDGE_NT / 32) + warp) * EDGE1_WPW;
+        const bool interior = wbase > 0 && (wbase * 64 >= a.start_bit) && ((wbase + EDGE1_WPW) * 64 <= a.n_bits);
+        uint32_t c = 0;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, d);
-                run += part;
-                if (incl) break;
-                top -= 32;
+        for (int r = 0; r < EDGE1_ROWS; r++) {
+            const u64 w0 = w[r][0], w1 = w[r][1];
+            u64 prev = __shfl_up_sync(0xFFFFFFFFu, w1 >> 63, 1);
+            if (lane == 0) prev = carry;
+            carry = __shfl_sync(0xFFFFFFFFu, w1 >> 63, 31);
+            u64 t0 = w0 ^ ((w0 << 1) | prev);
+            u64 t1 = w1 ^ ((w1 << 1) | (w0 >> 63));
+            if (!interior) {
+                const i64 wi = wbase + r * 64 + 2 * lane;
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    u64 &t = h ? t1 : t0;
+                    const i64 lo = (wi + h) * 64;
+                    if (lo < a.start_bit) {
+                        const i64 sh = a.start_bit - lo;
+                        t = (sh >= 64) ? 0 : (t >> sh) << sh;
+                    }
+                    if (lo + 64 > a.n_bits) {
+                        const i64 keep = a.n_bits - lo;
+                        t = (keep <= 0) ? 0 : (t & ((keep >= 64) ? ~0ull : ((1ull << keep) - 1)));
+                    }
+                }
             }
-            if (lane == 0) {
-                st[bid] = (2ull << 62) | (run + total);
-                __threadfence();
+            w[r][0] = t0;                                 // the masks replace the words
+            w[r][1] = t1;
+            c += __popcll(t0) + __popcll(t1);
+        }
+        const uint32_t warp_cnt = __reduce_add_sync(0xFFFFFFFFu, c);
+        uint32_t *cnt = s_warp_cnt[it & 1];               // double buffered: one barrier per tile
+        if (lane == 0) cnt[warp] = warp_cnt;
+        __syncthreads();
+        uint32_t total = 0, warp_off = 0;
+#pragma unroll
+        for (int q = 0; q < EDGE_NT / 32; q++) {
+            if (q < (int) warp) warp_off += cnt[q];
+            total += cnt[q];
+        }
+        if (threadIdx.x == 0) {
+            a.block_counts[tile] = total;
+            if (total > EDGE1_CAP) atomicExch(x.overflow, 1u);
+        }
+        if (warp_cnt != 0) {
+            // ordered write: rows in order, lanes in order inside a row; rows without a transition cost one ballot
+            u64 *out = x.tmp + (u64) tile * EDGE1_CAP;
+            uint32_t dst = warp_off;
+#pragma unroll
+            for (int r = 0; r < EDGE1_ROWS; r++) {
+                const uint32_t n = __popcll(w[r][0]) + __popcll(w[r][1]);
+                const uint32_t have = __ballot_sync(0xFFFFFFFFu, n != 0);
+                if (have == 0) continue;
+                uint32_t inc = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                    if (lane >= (uint32_t) d) inc += up;
+                }
+                uint32_t my = dst + (inc - n);
+                dst += __shfl_sync(0xFFFFFFFFu, inc, 31);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    u64 t = w[r][h];
+                    const i64 lo = (wbase + r * 64 + 2 * lane + h) * 64;
+                    while (t) {
+                        const int b = __ffsll((long long) t) - 1;
+                        t &= t - 1;
+                        if (my < EDGE1_CAP) out[my] = (u64) (a.bit_base + lo + b);
+                        my++;
+                    }
+                }
             }
         }
-        if (lane == 0) {
-            s_prefix = run;
-            if (bid == gridDim.x - 1) *x.total = run + total;
+#pragma unroll
+        for (int r = 0; r < EDGE1_ROWS; r++) {
+            w[r][0] = wn[r][0];
+            w[r][1] = wn[r][1];
         }
+        carry = carry_n;
     }
-    __syncthreads();
-    u64 dst = s_prefix + excl;
-#pragma unroll
-    for (int q = 0; q < EDGE1_WPT; q++) {
-        u64 m = t[q];
-        while (m) {
-            const int b = __ffsll((long long) m) - 1;
-            m &= m - 1;
-            if (dst < x.cap) a.edges[dst] = (u64) (a.bit_base + (w0 + q) * 64 + b);
-            dst++;
-        }
+}
+
+// block b copies tile b's region to its final position (block_counts now holds the exclusive offsets)
+__global__ void __launch_bounds__(128) edge_flatten_kernel(const Edge1Args x)
+{
+    const EdgeArgs &a = x.e;
+    const uint32_t tile = blockIdx.x;
+    const u64 all = *x.total;
+    const u64 off = a.block_counts[tile];
+    const u64 nxt = (tile + 1 < x.n_tiles) ? (u64) a.block_counts[tile + 1] : all;
+    uint32_t n = (uint32_t) (nxt - off);
+    if (n > EDGE1_CAP) n = EDGE1_CAP;
+    const u64 *src = x.tmp + (u64) tile * EDGE1_CAP;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        if (off + i < x.cap) a.edges[off + i] = src[i];
+    }
+    if (tile == 0 && threadIdx.x == 0 && x.hdr) {
+        const u64 word0 = a.words[0];
+        x.hdr[0] = all < x.cap ? all : x.cap;
+        x.hdr[1] = (word0 >> (a.start_bit ? a.start_bit - 1 : 0)) & 1;
+        x.hdr[2] = word0;
+        x.hdr[3] = a.words[x.report_word];
     }
 }
 

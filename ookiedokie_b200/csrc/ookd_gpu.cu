@@ -65,7 +65,7 @@ struct ookd_gpu {
 
     // workspaces
     DevBuf in, bits, inter[2], block_counts, edges, scalars, chunk_exit[2], chunk_ran, slots, slot_count,
-           slot_off, msgs_dev, dense_list, chunk_e, final_entry, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
+           slot_off, msgs_dev, dense_list, chunk_e, edge_tmp, final_entry, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
     uint32_t slot_cap = 8;
     bool tables_valid = false;       // entry/exit tables of the last decode can be extended by resolve
     int tab_cur = 0;
@@ -75,7 +75,11 @@ struct ookd_gpu {
     i64 report_lo = 0;               // first output that belongs to the shard (out_lo may start earlier)
     SmCarry entry_used{};
     uint32_t first_chunk = 0;
-    void *h_scalars = nullptr;        // pinned, 256 B
+    void *h_scalars = nullptr;        // pinned, 512 B
+    SmMsg *h_msgs_pin = nullptr;      // pinned message staging of the single-synchronisation path
+    size_t h_msgs_pin_cap = 0;        // in messages
+    u64 last_n_msgs = 0;
+    uint32_t stat_syncs = 0;
     std::vector<ookd_msg> h_msgs;
     std::vector<SmMsg> h_msgs_raw;
     std::vector<u64> h_edges;
@@ -582,51 +586,48 @@ int run_state_machine_jacobi(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *
     return fail(h, OOKD_ERR_OVERFLOW, "message slots overflowed after retries");
 }
 
-// ---- decisions -> ordered edge list, one pass (edge_onepass_kernel); also fetches the scalars the host needs
-// (edge total, decisions around the shard start, number of groups the screen left to the refine kernel) ----
+// ---- decisions -> ordered edge list on the synchronous path (count / scan / write: any edge density); also
+// fetches the scalars the host needs (edge total, decisions around the shard start, number of groups the
+// screen left to the refine kernel) ----
 int extract_edges(ookd_gpu *h, u64 n_bits, ookd_gpu_result *res)
 {
     int rc;
-    Edge1Args x{};
-    x.e.words = (const u64 *) h->bits.p;
-    x.e.bit_base = h->bit_base;
-    x.e.start_bit = h->pre;
-    x.e.n_bits = (i64) n_bits;
+    EdgeArgs ea{};
+    ea.words = (const u64 *) h->bits.p;
+    ea.bit_base = h->bit_base;
+    ea.start_bit = h->pre;
+    ea.n_bits = (i64) n_bits;
     const u64 n_words = (n_bits + 63) / 64;
-    const unsigned eg = (unsigned) ((n_words + EDGE1_WPB - 1) / EDGE1_WPB);
-    if ((rc = ensure(h, h->block_counts, sizeof(u64) * (eg + 1)))) return rc;
-    // room for one edge per 128 decisions; a capture with more is handled by growing the list and repeating
-    if ((rc = ensure(h, h->edges, sizeof(u64) * (n_bits / 128 + 65536)))) return rc;
+    const unsigned eg = (unsigned) ((n_words + EDGE_WPB - 1) / EDGE_WPB);
+    if ((rc = ensure(h, h->block_counts, sizeof(uint32_t) * (eg + 1)))) return rc;
+    ea.block_counts = (uint32_t *) h->block_counts.p;
     h->stat_dense_tiles = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        x.status = (u64 *) h->block_counts.p;
-        x.ticket = (uint32_t *) ((char *) h->scalars.p + 24);
-        x.total = (u64 *) h->scalars.p;
-        x.e.edges = (u64 *) h->edges.p;
-        x.cap = h->edges.cap / sizeof(u64);
-        CU(h, cudaMemsetAsync(x.status, 0, sizeof(u64) * eg, h->s_compute));
-        CU(h, cudaMemsetAsync(x.ticket, 0, 4, h->s_compute));
-        edge_onepass_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(x);
-        h->launches++;
-        CU(h, cudaGetLastError());
-        // scalars[0] = total edges; also the first word of decisions (base_bit), the word holding the shard's
-        // first decision (first_bit) and the refine counters
-        CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
-        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 8, h->bits.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
-        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 240, (const char *) h->bits.p + (((u64) (h->report_lo - h->bit_base)) >> 6) * 8,
-                              8, cudaMemcpyDeviceToHost, h->s_compute));
-        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 16, (char *) h->scalars.p + 16, 8, cudaMemcpyDeviceToHost, h->s_compute));
-        CU(h, cudaStreamSynchronize(h->s_compute));
-        h->n_edges = ((const u64 *) h->h_scalars)[0];
-        if (h->n_edges <= x.cap) break;
-        if (attempt == 1) return fail(h, OOKD_ERR_OVERFLOW, "edge list overflowed after growing");
-        if ((rc = ensure(h, h->edges, sizeof(u64) * (h->n_edges + 2)))) return rc;
-    }
+    edge_count_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(ea);
+    scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>(ea.block_counts, eg, (u64 *) h->scalars.p);
+    h->launches += 2;
+    CU(h, cudaGetLastError());
+    // scalars[0] = total edges; also the first word of decisions (base_bit), the word holding the shard's
+    // first decision (first_bit) and the refine counters
+    CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
+    CU(h, cudaMemcpyAsync((char *) h->h_scalars + 8, h->bits.p, 8, cudaMemcpyDeviceToHost, h->s_compute));
+    CU(h, cudaMemcpyAsync((char *) h->h_scalars + 240, (const char *) h->bits.p + (((u64) (h->report_lo - h->bit_base)) >> 6) * 8,
+                          8, cudaMemcpyDeviceToHost, h->s_compute));
+    CU(h, cudaMemcpyAsync((char *) h->h_scalars + 16, (char *) h->scalars.p + 16, 8, cudaMemcpyDeviceToHost, h->s_compute));
+    CU(h, cudaStreamSynchronize(h->s_compute));
+    h->stat_syncs++;
+    h->n_edges = ((const u64 *) h->h_scalars)[0];
     const u64 w0 = ((const u64 *) h->h_scalars)[1];
     // decision preceding the shard (or decision 0 itself at the capture start)
     h->base_bit = (uint32_t) ((w0 >> (h->pre ? h->pre - 1 : 0)) & 1);
     if (res) res->first_bit = (uint32_t) ((((const u64 *) h->h_scalars)[30] >> ((u64) (h->report_lo - h->bit_base) & 63)) & 1);
     h->stat_refined_blocks = ((const uint32_t *) h->h_scalars)[4];
+    if ((rc = ensure(h, h->edges, sizeof(u64) * (h->n_edges + 2)))) return rc;
+    if (h->n_edges) {
+        ea.edges = (u64 *) h->edges.p;
+        edge_write_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(ea);
+        h->launches++;
+        CU(h, cudaGetLastError());
+    }
     return OOKD_OK;
 }
 
@@ -785,7 +786,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
     if (n_msgs) {
         if ((rc = ensure(h, h->msgs_dev, sizeof(SmMsg) * n_msgs))) return rc;
         sm_gather_table_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a, (const uint32_t *) h->slot_off.p,
-                                                                           (SmMsg *) h->msgs_dev.p);
+                                                                           (SmMsg *) h->msgs_dev.p, n_msgs);
         h->launches++;
         h->h_msgs_raw.resize(n_msgs);
         CU(h, cudaMemcpyAsync(h->h_msgs_raw.data(), h->msgs_dev.p, sizeof(SmMsg) * n_msgs, cudaMemcpyDeviceToHost,
@@ -794,6 +795,185 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
     }
     h->tables_valid = true;
     return finish_messages(h, h->h_msgs_raw.data(), n_msgs, last, rounds, exit_, res);
+}
+
+// ---- single-synchronisation tail ----
+// Edge pass, state-machine burst (rounds 0-2 with link/walk in between), message scan and gather are all
+// enqueued behind the FIR kernels; the kernels take the edge count and the decision in front of the shard
+// from device memory (SmDevHdr), so the host synchronises ONCE and then validates what it got.  Anything
+// that did not fit or resolve (edge list / work list / message slots too small, chain not resolved after
+// three rounds) sets *done = false and the caller repeats the tail on the synchronous path, which handles
+// every such case.
+int decode_tail_fast(ookd_gpu *h, u64 n_bits, SmCarry entry0, ookd_sm_carry *exit_, ookd_gpu_result *res, bool *done)
+{
+    *done = false;
+    int rc;
+    if (entry0.state < h->smc.num_states && entry0.k > h->smc.states[entry0.state].ksat) {
+        entry0.k = h->smc.states[entry0.state].ksat;
+    }
+    const uint32_t nc = h->n_chunks;
+    // ---- workspaces (grow-only; sizes depend on geometry only) ----
+    const u64 n_words = (n_bits + 63) / 64;
+    const unsigned eg = (unsigned) ((n_words + EDGE1_WPB - 1) / EDGE1_WPB);
+    if ((rc = ensure(h, h->block_counts, sizeof(u64) * (eg + 1)))) return rc;
+    if ((rc = ensure(h, h->edges, sizeof(u64) * (n_bits / 128 + 65536)))) return rc;
+    if ((rc = ensure(h, h->edge_tmp, sizeof(u64) * (size_t) eg * EDGE1_CAP))) return rc;
+    if ((rc = ensure(h, h->slot_count, sizeof(uint32_t) * (nc + 1)))) return rc;
+    if ((rc = ensure(h, h->slot_off, sizeof(uint32_t) * (nc + 1)))) return rc;
+    if ((rc = ensure(h, h->tab_entry, sizeof(SmCarry) * (size_t) nc * TAB_K))) return rc;
+    if ((rc = ensure(h, h->tab_exit, sizeof(SmCarry) * (size_t) nc * TAB_K))) return rc;
+    if ((rc = ensure(h, h->tab_nmsg, sizeof(uint32_t) * (size_t) nc * TAB_K))) return rc;
+    if ((rc = ensure(h, h->tab_cnt[0], sizeof(uint32_t) * nc))) return rc;
+    if ((rc = ensure(h, h->tab_cnt[1], sizeof(uint32_t) * nc))) return rc;
+    if ((rc = ensure(h, h->tab_link, (size_t) nc * TAB_K + 16))) return rc;
+    if ((rc = ensure(h, h->tab_chosen, (size_t) nc + 16))) return rc;
+    if ((rc = ensure(h, h->final_entry, sizeof(SmCarry)))) return rc;
+    if ((rc = ensure(h, h->chunk_e, sizeof(u64) * nc))) return rc;
+    if ((rc = ensure(h, h->slots, sizeof(SmMsg) * (size_t) nc * TAB_K * h->slot_cap))) return rc;
+    const u64 msg_cap = (u64) nc * h->slot_cap;                       // at most slot_cap messages per chunk are kept
+    if ((rc = ensure(h, h->msgs_dev, sizeof(SmMsg) * msg_cap))) return rc;
+    u64 n_copy = h->last_n_msgs + h->last_n_msgs / 4 + 1024;         // messages copied back speculatively
+    if (n_copy > msg_cap) n_copy = msg_cap;
+    if (h->h_msgs_pin_cap < n_copy) {
+        if (h->h_msgs_pin) cudaFreeHost(h->h_msgs_pin);
+        h->h_msgs_pin = nullptr;
+        h->h_msgs_pin_cap = 0;
+        CU(h, cudaHostAlloc((void **) &h->h_msgs_pin, sizeof(SmMsg) * n_copy, cudaHostAllocDefault));
+        h->h_msgs_pin_cap = n_copy;
+    }
+
+    // ---- edge pass: tile-local extraction, scan of the tile counts, flatten ----
+    Edge1Args x{};
+    x.e.words = (const u64 *) h->bits.p;
+    x.e.bit_base = h->bit_base;
+    x.e.start_bit = h->pre;
+    x.e.n_bits = (i64) n_bits;
+    x.e.edges = (u64 *) h->edges.p;
+    x.e.block_counts = (uint32_t *) h->block_counts.p;
+    x.tmp = (u64 *) h->edge_tmp.p;
+    x.n_tiles = eg;
+    x.overflow = (uint32_t *) ((char *) h->scalars.p + 28);
+    x.total = (const u64 *) h->scalars.p;
+    x.cap = h->edges.cap / sizeof(u64);
+    x.hdr = (u64 *) ((char *) h->scalars.p + 256);
+    x.report_word = (i64) (((u64) (h->report_lo - h->bit_base)) >> 6);
+    CU(h, cudaMemsetAsync((char *) h->scalars.p + 24, 0, 232, h->s_compute));      // [24, 256): keeps the refine counters
+    {
+        const unsigned ctas = h->n_sm * 2;
+        edge_local_kernel<<<eg < ctas ? eg : ctas, EDGE_NT, 0, h->s_compute>>>(x);
+        scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>(x.e.block_counts, eg, (u64 *) h->scalars.p);
+        edge_flatten_kernel<<<eg, 128, 0, h->s_compute>>>(x);
+        h->launches += 3;
+        CU(h, cudaGetLastError());
+    }
+
+    // ---- state machine burst ----
+    h->tables_valid = false;
+    h->first_chunk = 0;
+    h->entry_used = entry0;
+    h->n_edges = 0;
+    h->base_bit = 0;
+    SmArgs a = base_sm_args(h, entry0);
+    a.hdr = (const SmDevHdr *) ((char *) h->scalars.p + 256);
+    a.start_slot = (uint32_t *) ((char *) h->scalars.p + 48);
+    a.first_chunk = 0;
+    a.final_entry = (SmCarry *) h->final_entry.p;
+    a.tab_k = TAB_K;
+    a.tab_entry = (SmCarry *) h->tab_entry.p;
+    a.tab_exit = (SmCarry *) h->tab_exit.p;
+    a.tab_nmsg = (uint32_t *) h->tab_nmsg.p;
+    a.link = (uint8_t *) h->tab_link.p;
+    a.chosen = (uint8_t *) h->tab_chosen.p;
+    a.walk_status = (uint32_t *) ((char *) h->scalars.p + 40);
+    a.msg_counts = (uint32_t *) h->slot_count.p;
+    a.final_exit = (SmCarry *) ((char *) h->scalars.p + 192);
+    sm_chunk_index_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a);
+    h->launches++;
+    CU(h, cudaMemsetAsync(h->tab_cnt[0].p, 0, sizeof(uint32_t) * nc, h->s_compute));
+    int cur = 0;
+    uint32_t rounds = 0;
+    for (uint32_t r = 0; r < 3; r++) {
+        a.round = rounds;
+        a.counter_idx = rounds & 31;
+        if (rounds == 0) {
+            a.cnt_in = (const uint32_t *) h->tab_cnt[0].p;
+            a.cnt_out = (uint32_t *) h->tab_cnt[0].p;
+        } else {
+            CU(h, cudaMemcpyAsync(h->tab_cnt[cur ^ 1].p, h->tab_cnt[cur].p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice,
+                                  h->s_compute));
+            a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
+            a.cnt_out = (uint32_t *) h->tab_cnt[cur ^ 1].p;
+            cur ^= 1;
+        }
+        const u64 warps = (u64) nc * (rounds == 0 ? 1 : TAB_K);
+        sm_table_round_kernel<<<(unsigned) warps, 32, 0, h->s_compute>>>(a);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        rounds++;
+        if (r >= 1) {
+            a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
+            sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
+            sm_walk_kernel<<<1, 1024, 0, h->s_compute>>>(a);
+            h->launches += 2;
+        }
+    }
+    // ---- ordered gather of the chosen pairs' messages ----
+    CU(h, cudaMemcpyAsync(h->slot_off.p, h->slot_count.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice, h->s_compute));
+    scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
+    sm_gather_table_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a, (const uint32_t *) h->slot_off.p,
+                                                                       (SmMsg *) h->msgs_dev.p, msg_cap);
+    h->launches += 2;
+    CU(h, cudaGetLastError());
+    CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 512, cudaMemcpyDeviceToHost, h->s_compute));
+    if (n_copy) {
+        CU(h, cudaMemcpyAsync(h->h_msgs_pin, h->msgs_dev.p, sizeof(SmMsg) * n_copy, cudaMemcpyDeviceToHost, h->s_compute));
+    }
+    if (h->warm) {
+        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 288, h->final_entry.p, sizeof(SmCarry), cudaMemcpyDeviceToHost, h->s_compute));
+    }
+    CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
+    CU(h, cudaStreamSynchronize(h->s_compute));
+    h->stat_syncs++;
+
+    // ---- validate ----
+    const char *hs = (const char *) h->h_scalars;
+    const u64 n_edges_total = *(const u64 *) hs;
+    const u64 n_msgs = *(const u64 *) (hs + 8);
+    const uint32_t refined = *(const uint32_t *) (hs + 16);
+    const uint32_t overflow = *(const uint32_t *) (hs + 32);
+    const uint32_t walk_complete = *(const uint32_t *) (hs + 44);
+    h->stat_refined_blocks = refined;
+    h->stat_dense_tiles = 0;
+    if ((h->screen || h->path == FIR_SCREEN_DEC4) && refined > h->work_cap) return OOKD_OK;      // work list overflowed
+    if (n_edges_total > x.cap || *(const uint32_t *) (hs + 28) != 0) return OOKD_OK;      // edge list / a tile region too small
+    if (overflow != 0 || walk_complete != 1 || n_msgs > msg_cap) {
+        if (overflow == 1) h->slot_cap *= 4;
+        return OOKD_OK;
+    }
+    h->n_edges = n_edges_total;
+    h->base_bit = *(const uint32_t *) (hs + 264);
+    if (res) res->first_bit = (uint32_t) ((*(const u64 *) (hs + 280) >> ((u64) (h->report_lo - h->bit_base) & 63)) & 1);
+    if (n_msgs > n_copy) {
+        // more messages than the speculative copy carried: fetch them all (first decode on a handle, or a burst)
+        if (h->h_msgs_pin_cap < n_msgs) {
+            cudaFreeHost(h->h_msgs_pin);
+            h->h_msgs_pin = nullptr;
+            h->h_msgs_pin_cap = 0;
+            CU(h, cudaHostAlloc((void **) &h->h_msgs_pin, sizeof(SmMsg) * n_msgs, cudaHostAllocDefault));
+            h->h_msgs_pin_cap = n_msgs;
+        }
+        CU(h, cudaMemcpyAsync(h->h_msgs_pin, h->msgs_dev.p, sizeof(SmMsg) * n_msgs, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaStreamSynchronize(h->s_compute));
+        h->stat_syncs++;
+    }
+    h->last_n_msgs = n_msgs;
+    h->tab_cur = cur;
+    h->tables_valid = true;
+    SmCarry last;
+    memcpy(&last, hs + 192, sizeof(SmCarry));
+    if (h->warm) memcpy(&h->entry_used, hs + 288, sizeof(SmCarry));
+    *done = true;
+    return finish_messages(h, h->h_msgs_pin, n_msgs, last, rounds, exit_, res);
 }
 
 }  // namespace
@@ -836,10 +1016,11 @@ void ookd_gpu_destroy(ookd_gpu *h)
     if (h->d_tab) cudaFree(h->d_tab);
     DevBuf *all[] = {&h->in, &h->bits, &h->inter[0], &h->inter[1], &h->block_counts, &h->edges, &h->scalars,
                      &h->chunk_exit[0], &h->chunk_exit[1], &h->chunk_ran, &h->slots, &h->slot_count,
-                     &h->slot_off, &h->msgs_dev, &h->dense_list, &h->chunk_e, &h->final_entry, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
+                     &h->slot_off, &h->msgs_dev, &h->dense_list, &h->chunk_e, &h->edge_tmp, &h->final_entry, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
                      &h->tab_cnt[1], &h->tab_link, &h->tab_chosen};
     for (DevBuf *b : all) release(*b);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
+    if (h->h_msgs_pin) cudaFreeHost(h->h_msgs_pin);
     for (auto e : h->ev_piece) cudaEventDestroy(e);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
@@ -887,8 +1068,8 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     CUC(cudaEventCreate(&h->ev_t1));
     CUC(cudaEventCreate(&h->ev_f0));
     CUC(cudaEventCreate(&h->ev_f1));
-    CUC(cudaHostAlloc(&h->h_scalars, 256, cudaHostAllocDefault));
-    if (ensure(h, h->scalars, 256) != OOKD_OK) CREATE_FAIL(OOKD_ERR_NOMEM);
+    CUC(cudaHostAlloc(&h->h_scalars, 512, cudaHostAllocDefault));
+    if (ensure(h, h->scalars, 512) != OOKD_OK) CREATE_FAIL(OOKD_ERR_NOMEM);
 
     // ---- filter ----
     const ookd_filter_desc *f = cfg->filter;
@@ -1111,10 +1292,19 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     if ((rc = launch_fir_refine(h, d_in, in_base, in_valid_end))) return rc;
     CU(h, cudaEventRecord(h->ev_f1, h->s_compute));
 
-    // ---- edges ----
+    // ---- edges + state machine ----
     h->n_edges = 0;
     h->base_bit = 0;
-    if (n_bits > 0) {
+    SmCarry e0{};
+    if (entry) carry_to_dev(*entry, e0);
+    bool fast_done = false;
+    if (n_bits > 0 && h->have_sm && h->out_hi > h->out_lo && !(h->flags & OOKD_FLAG_SYNC_TAIL)) {
+        h->have_last = true;
+        if ((rc = decode_tail_fast(h, n_bits, e0, exit_, res, &fast_done))) return rc;
+    }
+    if (fast_done) {
+        // everything fit and resolved behind a single synchronisation
+    } else if (n_bits > 0) {
         if ((rc = extract_edges(h, n_bits, res))) return rc;
         if ((h->screen || h->path == FIR_SCREEN_DEC4) && h->stat_refined_blocks > h->work_cap) {
             // too many undecided groups for the work list: redo the decisions exactly, extract the edges again,
@@ -1130,14 +1320,13 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     }
 
     // ---- state machine ----
-    SmCarry e0{};
-    if (entry) carry_to_dev(*entry, e0);
     h->have_last = true;
-    rc = run_state_machine(h, e0, exit_, res);
-    if (rc) return rc;
-
-    CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
-    CU(h, cudaEventSynchronize(h->ev_t1));
+    if (!fast_done) {
+        rc = run_state_machine(h, e0, exit_, res);
+        if (rc) return rc;
+        CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
+        CU(h, cudaEventSynchronize(h->ev_t1));
+    }
     if (res) {
         res->n_in = n_eff;
         res->n_out = n_out;

@@ -34,7 +34,15 @@
 
 namespace ookd {
 
+// Edge count and the decision in front of the shard as the edge pass left them in device memory: lets
+// the state-machine kernels be enqueued behind the edge pass without a host round trip.
+struct SmDevHdr {
+    u64 n_edges;
+    uint32_t base_bit, pad;
+};
+
 struct SmArgs {
+    const SmDevHdr *hdr;      // non-null: n_edges / base_bit below are placeholders, read them from here
     const SmTable *tab;
     const u64 *edges;
     u64  n_edges;
@@ -283,13 +291,13 @@ __device__ __forceinline__ void sm_emit(SpanOut &o, const SmCarry &s, i64 pos)
 // pos, tb = true decision at pos-1.  PROBE: stop early and report whether a machine started in
 // RESET at pos gets as far as appending a bit / emitting a message (1) or falls back to RESET (0).
 template <bool PROBE>
-__device__ __forceinline__ int sm_run_span(const SmArgs &a, const SmTable &T, SmCarry &s, i64 pos, i64 end,
+__device__ __forceinline__ int sm_run_span(const SmArgs &a, const u64 n_edges, const SmTable &T, SmCarry &s, i64 pos, i64 end,
                                            u64 e, uint32_t tb, SpanOut &o, i64 chunk_lo)
 {
     bool left_reset = false;
     const u64 INF = ~0ull;
-    u64 next_edge = (e < a.n_edges) ? a.edges[e] : INF;
-    u64 after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;   // one-ahead prefetch
+    u64 next_edge = (e < n_edges) ? a.edges[e] : INF;
+    u64 after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;   // one-ahead prefetch
 
     while (pos < end) {
         const bool at_edge = (next_edge == (u64) pos);
@@ -300,7 +308,7 @@ __device__ __forceinline__ int sm_run_span(const SmArgs &a, const SmTable &T, Sm
                 tb ^= 1u;
                 e++;
                 next_edge = after_edge;
-                after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;
+                after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;
             }
             pos++;
             if (PROBE) {
@@ -316,11 +324,11 @@ __device__ __forceinline__ int sm_run_span(const SmArgs &a, const SmTable &T, Sm
                 if (nb > end) nb = end;
                 if (nb > pos) {
                     if (next_edge < (u64) nb) {
-                        const u64 e2 = e + edge_lower_bound_near(a.edges + e, a.n_edges - e, (u64) nb);
+                        const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb);
                         tb ^= (uint32_t) ((e2 - e) & 1);
                         e = e2;
-                        next_edge = (e < a.n_edges) ? a.edges[e] : INF;
-                        after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;
+                        next_edge = (e < n_edges) ? a.edges[e] : INF;
+                        after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;
                     }
                     pos = nb;
                 }
@@ -504,12 +512,12 @@ __device__ __forceinline__ int warp_sm_next_quiet_fire(const WarpSm &W, const Sm
 }
 
 // sm_run_span<false>, executed by a whole warp with uniform control flow; lane 0 emits the messages.
-__device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const WarpSm &W, SmCarry &s, i64 pos, i64 end, u64 e,
-                                                 uint32_t tb, SpanOut &o, i64 chunk_lo, uint32_t lane)
+__device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_edges, const WarpSm &W, SmCarry &s, i64 pos,
+                                                 i64 end, u64 e, uint32_t tb, SpanOut &o, i64 chunk_lo, uint32_t lane)
 {
     const u64 INF = ~0ull;
-    u64 next_edge = (e < a.n_edges) ? a.edges[e] : INF;
-    u64 after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;   // one-ahead prefetch
+    u64 next_edge = (e < n_edges) ? a.edges[e] : INF;
+    u64 after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;   // one-ahead prefetch
 
     while (pos < end) {
         const bool at_edge = (next_edge == (u64) pos);
@@ -520,7 +528,7 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const WarpSm &
                 tb ^= 1u;
                 e++;
                 next_edge = after_edge;
-                after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;
+                after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;
             }
             pos++;
             if (r > 0) {
@@ -530,11 +538,11 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const WarpSm &
                 if (nb > end) nb = end;
                 if (nb > pos) {
                     if (next_edge < (u64) nb) {
-                        const u64 e2 = e + edge_lower_bound_near(a.edges + e, a.n_edges - e, (u64) nb);
+                        const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb);
                         tb ^= (uint32_t) ((e2 - e) & 1);
                         e = e2;
-                        next_edge = (e < a.n_edges) ? a.edges[e] : INF;
-                        after_edge = (e + 1 < a.n_edges) ? a.edges[e + 1] : INF;
+                        next_edge = (e < n_edges) ? a.edges[e] : INF;
+                        after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;
                     }
                     pos = nb;
                 }
@@ -585,13 +593,20 @@ __device__ __forceinline__ void chunk_bounds(const SmArgs &a, uint32_t c, i64 &s
 }
 
 // e_start[c] for every chunk, once per decode: the rounds then start without a binary search.
+// edge count / decision in front of the shard: by value, or from the header the edge pass wrote
+#define OOKD_SM_EDGE_HDR(a)                                                                     \
+    const u64 n_edges = (a).hdr ? (a).hdr->n_edges : (a).n_edges;                               \
+    const uint32_t base_bit = (a).hdr ? (a).hdr->base_bit : (a).base_bit;
+
 __global__ void __launch_bounds__(128) sm_chunk_index_kernel(const SmArgs a)
 {
+    OOKD_SM_EDGE_HDR(a)
+    (void) base_bit;
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_chunks) return;
     i64 start, end;
     chunk_bounds(a, c, start, end);
-    a.chunk_e[c] = edge_lower_bound(a.edges, a.n_edges, (u64) start);
+    a.chunk_e[c] = edge_lower_bound(a.edges, n_edges, (u64) start);
 }
 
 __device__ __forceinline__ void carry_reset(SmCarry &s, uint32_t prev)
@@ -610,6 +625,7 @@ __device__ __forceinline__ void carry_reset(SmCarry &s, uint32_t prev)
 // serialising each other through divergence (8 runs sharing a warp cost ~8x the latency).
 __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
 {
+    OOKD_SM_EDGE_HDR(a)
     __shared__ SmTable T;
     const uint32_t K = a.tab_k;
     const uint32_t lane = threadIdx.x & 31;
@@ -630,7 +646,7 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
     i64 start, end;
     chunk_bounds(a, c, start, end);
     u64 e = a.chunk_e[c];
-    uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);           // true decision at start-1
+    uint32_t tb = base_bit ^ (uint32_t) (e & 1);             // true decision at start-1
 
     SmCarry s, entry;
     i64 pos = start;
@@ -649,14 +665,14 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
             const u64 er0 = e + (tb == 1 ? 1 : 0);          // edge e falls when tb == 1; the next one rises
             for (int batch = 0; batch < 3 && !have_anchor; batch++) {
                 const u64 er = er0 + 2 * (u64) (batch * 32 + lane);
-                const bool cand = er < a.n_edges && a.edges[er] < (u64) end;
+                const bool cand = er < n_edges && a.edges[er] < (u64) end;
                 bool alive = false;
                 if (cand) {
                     SmCarry p;
                     carry_reset(p, 0);
                     SpanOut po;
                     po.slots = nullptr; po.cap = 0; po.n_msgs = 0; po.overflow = nullptr;
-                    alive = sm_run_span<true>(a, T, p, (i64) a.edges[er], a.out_hi, er, 0, po, start) != 0;
+                    alive = sm_run_span<true>(a, n_edges, T, p, (i64) a.edges[er], a.out_hi, er, 0, po, start) != 0;
                 }
                 const uint32_t m_alive = __ballot_sync(0xFFFFFFFFu, alive);
                 const uint32_t m_cand = __ballot_sync(0xFFFFFFFFu, cand);
@@ -714,10 +730,10 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
     o.n_msgs = 0;
     o.overflow = a.overflow;
     if (warp_ok) {
-        warp_sm_run_span(a, W, s, pos, end, e, tb, o, start, lane);
+        warp_sm_run_span(a, n_edges, W, s, pos, end, e, tb, o, start, lane);
         if (lane != 0) return;
     } else {
-        sm_run_span<false>(a, T, s, pos, end, e, tb, o, start);
+        sm_run_span<false>(a, n_edges, T, s, pos, end, e, tb, o, start);
     }
 
     a.tab_entry[(u64) c * K + slot] = entry;
@@ -751,7 +767,7 @@ __global__ void __launch_bounds__(32) sm_table_add_entry_kernel(const SmArgs a)
     o.n_msgs = 0;
     o.overflow = a.overflow;
     const SmCarry entry = s;
-    sm_run_span<false>(a, T, s, start, end, e, tb, o, start);
+    sm_run_span<false>(a, a.n_edges, T, s, start, end, e, tb, o, start);
     a.tab_entry[(u64) c * K + n_here] = entry;
     a.tab_exit[(u64) c * K + n_here] = s;
     a.tab_nmsg[(u64) c * K + n_here] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
@@ -860,13 +876,16 @@ __global__ void __launch_bounds__(1024) sm_walk_kernel(const SmArgs a)
     }
 }
 
-__global__ void sm_gather_table_kernel(const SmArgs a, const uint32_t *offsets, SmMsg *out)
+__global__ void sm_gather_table_kernel(const SmArgs a, const uint32_t *offsets, SmMsg *out, u64 out_cap)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_chunks) return;
     const uint32_t n = a.msg_counts[c];
+    if (n == 0) return;
     const SmMsg *src = a.slots + ((u64) c * a.tab_k + a.chosen[c]) * a.slot_cap;
-    for (uint32_t i = 0; i < n; i++) out[offsets[c] + i] = src[i];
+    for (uint32_t i = 0; i < n; i++) {
+        if ((u64) offsets[c] + i < out_cap) out[offsets[c] + i] = src[i];
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -905,7 +924,7 @@ __global__ void __launch_bounds__(32) sm_round_kernel(const SmArgs a)
     o.cap = a.slot_cap;
     o.n_msgs = 0;
     o.overflow = a.overflow;
-    sm_run_span<false>(a, T, s, start, end, e, tb, o, start);
+    sm_run_span<false>(a, a.n_edges, T, s, start, end, e, tb, o, start);
 
     a.exit_cur[c] = s;
     a.slot_count[c] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
