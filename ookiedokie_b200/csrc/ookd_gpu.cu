@@ -937,6 +937,11 @@ int decode_tail_fast(ookd_gpu *h, u64 n_bits, SmCarry entry0, ookd_sm_carry *exi
 
     // ---- validate ----
     const char *hs = (const char *) h->h_scalars;
+    if (getenv("OOKD_DEBUG")) {
+        const uint32_t *nr = (const uint32_t *) (hs + 64);
+        fprintf(stderr, "[ookd] fast tail: ran %u/%u/%u pairs in rounds 0/1/2, walk resolved %u then %u of %u chunks, overflow %u\n",
+                nr[0], nr[1], nr[2], nr[16 + 1], nr[16 + 2], nc, *(const uint32_t *) (hs + 32));
+    }
     const u64 n_edges_total = *(const u64 *) hs;
     const u64 n_msgs = *(const u64 *) (hs + 8);
     const uint32_t refined = *(const uint32_t *) (hs + 16);

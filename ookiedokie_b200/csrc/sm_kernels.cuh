@@ -379,7 +379,7 @@ struct WarpSm {
     uint32_t t_state;         // state owning this lane's trigger (0xFFFFFFFF: lane has no trigger)
     uint32_t t_cond, t_pack;  // condition; action | next_state << 8
     uint32_t t_kmin, t_kmax;
-    uint32_t s_dmin, s_dmax, s_ktimeout;   // of that state
+    uint32_t s_dmin, s_dmax, s_ktimeout, s_ksat;   // of that state
     uint32_t ksat_by_state;   // lane s: ksat of state s
     uint32_t max_bits;
 };
@@ -394,7 +394,7 @@ __device__ __forceinline__ void warp_sm_load(WarpSm &W, const SmTable *tab, uint
     W.max_bits = tab->max_bits;
     W.t_state = 0xFFFFFFFFu;
     W.t_cond = 0; W.t_pack = 0; W.t_kmin = 1; W.t_kmax = 0;
-    W.s_dmin = 0; W.s_dmax = 0; W.s_ktimeout = OOKD_K_INF;
+    W.s_dmin = 0; W.s_dmax = 0; W.s_ktimeout = OOKD_K_INF; W.s_ksat = 0;
     W.ksat_by_state = (lane < tab->num_states) ? tab->states[lane].ksat : 0u;
     if (lane < tab->num_triggers) {
         const ookd_sm_trigger_k t = tab->triggers[lane];
@@ -405,7 +405,7 @@ __device__ __forceinline__ void warp_sm_load(WarpSm &W, const SmTable *tab, uint
             const ookd_sm_state_k x = tab->states[st];
             if (lane >= x.first_trigger && lane < x.first_trigger + x.num_triggers) {
                 W.t_state = st;
-                W.s_dmin = x.dmin; W.s_dmax = x.dmax; W.s_ktimeout = x.ktimeout;
+                W.s_dmin = x.dmin; W.s_dmax = x.dmax; W.s_ktimeout = x.ktimeout; W.s_ksat = x.ksat;
             }
         }
     }
@@ -512,61 +512,175 @@ __device__ __forceinline__ int warp_sm_next_quiet_fire(const WarpSm &W, const Sm
 }
 
 // sm_run_span<false>, executed by a whole warp with uniform control flow; lane 0 emits the messages.
-__device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_edges, const WarpSm &W, SmCarry &s, i64 pos,
-                                                 i64 end, u64 e, uint32_t tb, SpanOut &o, i64 chunk_lo, uint32_t lane)
+// Positions are 32-bit offsets from chunk_lo (the caller guarantees end - chunk_lo < 2^31), and the edge list
+// is consumed through a register window: lane j holds edge ebase + j of the current batch of 32 and of the
+// next one, so the dependent chain sees a shuffle (~25 cycles) instead of an L2 round trip per edge.
+struct WarpEdges {
+    const u64 *edges;
+    u64 n_edges, ebase, org;      // org = chunk_lo as an edge value
+    uint32_t cur, nxt;            // offsets of edges ebase + lane / ebase + 32 + lane (0xFFFFFFFF: none / beyond range)
+    uint32_t lane;
+
+    __device__ __forceinline__ uint32_t fetch(u64 idx) const
+    {
+        if (idx >= n_edges) return 0xFFFFFFFFu;
+        const u64 d = edges[idx] - org;
+        return d < 0xFFFFFFFFull ? (uint32_t) d : 0xFFFFFFFFu;
+    }
+    __device__ __forceinline__ void reset(u64 e)
+    {
+        ebase = e;
+        cur = fetch(e + lane);
+        nxt = fetch(e + 32 + lane);
+    }
+    // offset of edge e (e >= ebase); slides the window when e has left the current batch
+    __device__ __forceinline__ uint32_t at(u64 e)
+    {
+        if (e - ebase >= 32) {
+            if (e - ebase >= 64) {
+                reset(e);
+            } else {
+                cur = nxt;
+                ebase += 32;
+                nxt = fetch(ebase + 32 + lane);
+            }
+        }
+        return __shfl_sync(0xFFFFFFFFu, cur, (int) (e - ebase));
+    }
+};
+
+__device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_edges, const WarpSm &W, SmCarry &s, i64 pos64,
+                                                 i64 end64, u64 e, uint32_t tb, SpanOut &o, i64 chunk_lo, uint32_t lane)
 {
-    const u64 INF = ~0ull;
-    u64 next_edge = (e < n_edges) ? a.edges[e] : INF;
-    u64 after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;   // one-ahead prefetch
+    const uint32_t NONE = 0xFFFFFFFFu;
+    uint32_t pos = (uint32_t) (pos64 - chunk_lo);
+    const uint32_t end = (uint32_t) (end64 - chunk_lo);
+    WarpEdges E;
+    E.edges = a.edges; E.n_edges = n_edges; E.org = (u64) chunk_lo; E.lane = lane;
+    E.reset(e);
+    uint32_t next_edge = E.at(e);                                       // NONE: no further edge in range
 
     while (pos < end) {
-        const bool at_edge = (next_edge == (u64) pos);
-        if (s.state == 0 || s.prev != tb || at_edge) {
+        const bool at_edge = (next_edge == pos);
+        if (s.state == 0 || s.prev != tb) {
+            // single-sample path: RESET (evaluated twice) and the first sample after a dropped buffer tail
             const uint32_t b = at_edge ? (tb ^ 1u) : tb;
             const int r = warp_sm_step(W, s, b);
             if (at_edge) {
                 tb ^= 1u;
                 e++;
-                next_edge = after_edge;
-                after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;
+                next_edge = E.at(e);
             }
             pos++;
             if (r > 0) {
-                if (lane == 0) sm_emit(o, s, pos - 1); else o.n_msgs++;
+                if (lane == 0) sm_emit(o, s, chunk_lo + (i64) pos - 1); else o.n_msgs++;
             } else if (r < 0) {
-                i64 nb = next_buffer_start(a, pos - 1, chunk_lo);
-                if (nb > end) nb = end;
+                // device_process gives up on this buffer: resume at the next buffer's first output
+                i64 nb64 = next_buffer_start(a, chunk_lo + (i64) pos - 1, chunk_lo);
+                if (nb64 > end64) nb64 = end64;
+                const uint32_t nb = (uint32_t) (nb64 - chunk_lo);
                 if (nb > pos) {
-                    if (next_edge < (u64) nb) {
-                        const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb);
+                    if (next_edge < nb) {
+                        const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb64);
                         tb ^= (uint32_t) ((e2 - e) & 1);
                         e = e2;
-                        next_edge = (e < n_edges) ? a.edges[e] : INF;
-                        after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;
+                        next_edge = E.at(e);
                     }
                     pos = nb;
                 }
             }
             continue;
         }
-        const u64 limit = (next_edge < (u64) end) ? next_edge : (u64) end;
-        const u64 gap = limit - (u64) pos;
-        uint32_t k_fire;
-        const int tf = warp_sm_next_quiet_fire(W, s, &k_fire);
-        if (tf >= 0 && (u64) (k_fire - s.k) < gap) {
-            pos += (i64) (k_fire - s.k);
-            const uint32_t pack = __shfl_sync(0xFFFFFFFFu, W.t_pack, tf);
+
+        // ---- fused step: the quiet stretch up to the next edge AND the edge sample itself, in one evaluation ----
+        // machine not in RESET, prev_bit == true bit, samples [pos, limit) constant.  Every lane computes the
+        // offset (from pos) at which ITS trigger would be the first to fire: a trigger that needs no edge at the
+        // first count inside its window, any trigger at the edge sample (offset g) if eligible there with the
+        // count the machine has by then; the earliest offset wins, list order (lowest lane) breaks ties --
+        // exactly what sm_next_quiet_fire followed by sm_eval on the edge sample compute in two iterations.
+        const bool have_edge = next_edge < end;
+        const uint32_t limit = have_edge ? next_edge : end;
+        const uint32_t g = limit - pos;
+        const uint32_t k = s.k;
+        const uint32_t b = tb ^ 1u;                                     // value of the edge sample
+        const bool in_state = (W.t_state == s.state);
+        const u64 ke64 = (u64) k + g;
+        const uint32_t k_e = (ke64 < (u64) W.s_ksat) ? (uint32_t) ke64 : W.s_ksat;      // count at the edge sample
+        const bool mc = s.num_bits >= W.max_bits;
+        const bool is_to = W.t_cond == OOKD_COND_TIMEOUT, is_mc = W.t_cond == OOKD_COND_MSG_COMPLETE;
+        const bool is_quiet = W.t_cond == OOKD_COND_ALWAYS || is_to || is_mc;
+        // (1) first quiet firing count
+        uint32_t lo = W.t_kmin;
+        if (is_to) lo = max(lo, W.s_ktimeout);
+        const uint32_t kk = max(lo, k);
+        const bool q_ok = in_state && is_quiet && (!is_mc || mc) && (!is_to || W.s_ktimeout != OOKD_K_INF) && kk <= W.t_kmax;
+        const uint32_t tau_q = q_ok ? kk - k : OOKD_K_INF;
+        // (2) eligibility at the edge sample
+        const bool cond_e = (W.t_cond == OOKD_COND_ALWAYS) || (W.t_cond == OOKD_COND_PULSE_START && b) ||
+                            (W.t_cond == OOKD_COND_PULSE_END && !b) ||
+                            (is_to && W.s_ktimeout != OOKD_K_INF && k_e >= W.s_ktimeout) || (is_mc && mc);
+        const bool e_ok = in_state && have_edge && k_e >= W.t_kmin && k_e <= W.t_kmax && cond_e;
+        const uint32_t tau = (tau_q < g) ? tau_q : (e_ok ? g : OOKD_K_INF);
+        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, tau);
+        if (m == OOKD_K_INF) {
+            // nothing fires up to and including the edge sample
+            const uint32_t ksat = __shfl_sync(0xFFFFFFFFu, W.ksat_by_state, (int) s.state);
+            const u64 kn = (u64) k + g + (have_edge ? 1u : 0u);
+            s.k = (kn < (u64) ksat) ? (uint32_t) kn : ksat;
+            pos = limit;
+            if (have_edge) {
+                s.prev = b;
+                tb ^= 1u;
+                e++;
+                next_edge = E.at(e);
+                pos++;
+            }
+            continue;
+        }
+        const int f = __ffs(__ballot_sync(0xFFFFFFFFu, tau == m)) - 1;
+        const uint32_t pack = __shfl_sync(0xFFFFFFFFu, W.t_pack, f);
+        if (m < g) {
+            // a trigger that needs no edge fires inside the quiet stretch
+            pos += m;
             const int r = warp_sm_apply(W, s, pack);
             s.k = 0;
             pos++;
             if (r > 0) {
-                if (lane == 0) sm_emit(o, s, pos - 1); else o.n_msgs++;
+                if (lane == 0) sm_emit(o, s, chunk_lo + (i64) pos - 1); else o.n_msgs++;
             }
+            continue;
+        }
+        // fires on the edge sample, with count k_e
+        const bool is_edge = (W.t_cond == OOKD_COND_PULSE_START || W.t_cond == OOKD_COND_PULSE_END);
+        const uint32_t dur = __ballot_sync(0xFFFFFFFFu, !is_edge || (k_e >= W.s_dmin && k_e <= W.s_dmax));
+        int r;
+        if ((dur >> f) & 1u) {
+            r = warp_sm_apply(W, s, pack);
         } else {
-            const uint32_t ksat = __shfl_sync(0xFFFFFFFFu, W.ksat_by_state, (int) s.state);
-            const u64 kk = (u64) s.k + gap;
-            s.k = (kk < (u64) ksat) ? (uint32_t) kk : ksat;
-            pos = (i64) limit;
+            r = -1;
+            s.state = 0;
+        }
+        s.k = 0;
+        s.prev = b;
+        tb ^= 1u;
+        e++;
+        next_edge = E.at(e);
+        pos = limit + 1;
+        if (r > 0) {
+            if (lane == 0) sm_emit(o, s, chunk_lo + (i64) pos - 1); else o.n_msgs++;
+        } else if (r < 0) {
+            i64 nb64 = next_buffer_start(a, chunk_lo + (i64) pos - 1, chunk_lo);
+            if (nb64 > end64) nb64 = end64;
+            const uint32_t nb = (uint32_t) (nb64 - chunk_lo);
+            if (nb > pos) {
+                if (next_edge < nb) {
+                    const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb64);
+                    tb ^= (uint32_t) ((e2 - e) & 1);
+                    e = e2;
+                    next_edge = E.at(e);
+                }
+                pos = nb;
+            }
         }
     }
 }
@@ -639,12 +753,12 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
         if (c == 0 || j >= a.cnt_in[c - 1]) return;
     }
     load_table(T, a.tab);
-    const bool warp_ok = warp_sm_supported(a.tab);
+    i64 start, end;
+    chunk_bounds(a, c, start, end);
+    const bool warp_ok = warp_sm_supported(a.tab) && (end - start) < (1ll << 31);
     WarpSm W;
     if (warp_ok) warp_sm_load(W, &T, lane);
 
-    i64 start, end;
-    chunk_bounds(a, c, start, end);
     u64 e = a.chunk_e[c];
     uint32_t tb = base_bit ^ (uint32_t) (e & 1);             // true decision at start-1
 
@@ -864,6 +978,7 @@ __global__ void __launch_bounds__(1024) sm_walk_kernel(const SmArgs a)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        a.n_ran[16 + (a.round & 15)] = done;                 // diagnostics: chunks resolved after round a.round
         a.walk_status[0] = done;
         a.walk_status[1] = (done == a.n_chunks) ? 1u : 0u;
         if (done == a.n_chunks) {
