@@ -187,6 +187,10 @@ struct ookd_gpu_result {
     uint32_t entry_is_provisional;           /* 1: entry_used was derived from the warm-up history and must
                                                 be checked against the previous shard's exit              */
     struct ookd_sm_carry entry_used;         /* state-machine state the shard was entered with            */
+    float    screen_ms;                      /* device time of the dominant kernel alone (first FIR/threshold
+                                                launch .. last, before the exact refine pass); with host input
+                                                this span also contains waiting for the H2D pieces            */
+    uint32_t host_syncs;                     /* host<->device synchronisations the call needed            */
 };
 
 typedef struct ookd_gpu ookd_gpu;
@@ -223,6 +227,37 @@ int  ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr,
                            struct ookd_gpu_result *res);
 int  ookd_gpu_resolve(ookd_gpu *h, const struct ookd_sm_carry *entry,
                       struct ookd_sm_carry *exit_, struct ookd_gpu_result *res);
+
+/* The same decode in two halves: _begin enqueues every stage on the handle's
+ * streams and returns without waiting, _end waits (one synchronisation in the
+ * common case), validates and fills the results.  ookd_gpu_decode_shard is
+ * _begin followed by _end.  iq must stay valid until _end returns.  One decode
+ * per handle can be in flight; decodes on different handles overlap on the
+ * device. */
+int  ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr,
+                           uint64_t first_sample, uint64_t n_samples, int last,
+                           const struct ookd_sm_carry *entry);
+int  ookd_gpu_decode_end(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd_gpu_result *res);
+
+/* Batch of independent captures (each one a whole file: the loop of
+ * ookiedokie_rx(), src/ookiedokie.c:238-290, run once per capture).  Capture i
+ * is decoded by handles[caps[i].handle] -- handles may differ in device
+ * description, filter and CUDA device -- with up to one capture in flight per
+ * handle.  Messages of all captures are written to msgs_out in capture order;
+ * capture i owns msgs_out[msg_first[i] .. msg_first[i+1]).  If msgs_cap is too
+ * small OOKD_ERR_OVERFLOW is returned and msg_first[n_caps] holds the number
+ * of messages.  results (nullable) receives per-capture statistics (its msgs
+ * pointers are NULL). */
+struct ookd_capture {
+    const int16_t *iq;
+    uint64_t n_samples;
+    int32_t  iq_is_device_ptr;
+    uint32_t handle;                         /* index into handles[]                   */
+};
+int  ookd_gpu_batch_decode(ookd_gpu *const *handles, uint32_t n_handles,
+                           const struct ookd_capture *caps, uint32_t n_caps,
+                           struct ookd_msg *msgs_out, uint64_t msgs_cap, uint64_t *msg_first,
+                           struct ookd_gpu_result *results);
 uint32_t ookd_gpu_halo(const ookd_gpu *h);               /* input samples of FIR history  */
 uint32_t ookd_gpu_total_decimation(const ookd_gpu *h);
 void ookd_gpu_initial_carry(const ookd_gpu *h, struct ookd_sm_carry *c);  /* RESET, k=0 */

@@ -29,6 +29,7 @@ EXPORTS = [
     "ookd_sm_compile", "ookd_sm_compiled_free", "ookd_power_threshold",
     "ookd_gpu_device_count", "ookd_gpu_strerror", "ookd_gpu_last_error",
     "ookd_gpu_create", "ookd_gpu_destroy", "ookd_gpu_decode", "ookd_gpu_decode_shard",
+    "ookd_gpu_decode_begin", "ookd_gpu_decode_end", "ookd_gpu_batch_decode",
     "ookd_gpu_resolve", "ookd_gpu_halo", "ookd_gpu_total_decimation", "ookd_gpu_initial_carry",
     "ookd_gpu_edges", "ookd_gpu_bits", "ookd_gpu_filtered", "ookd_gpu_filter_cf", "ookd_gpu_synth",
     "ookd_gpu_host_alloc", "ookd_gpu_host_free", "ookd_gpu_dev_alloc", "ookd_gpu_dev_free",
@@ -121,7 +122,12 @@ class GpuResult(C.Structure):
                 ("n_edges", C.c_uint64), ("n_msgs", C.c_uint64), ("msgs", C.POINTER(Msg)),
                 ("first_bit", C.c_uint32), ("sm_rounds", C.c_uint32), ("kernel_ms", C.c_float),
                 ("fir_ms", C.c_float), ("gpu_launches", C.c_uint32), ("refined_tiles", C.c_uint32),
-                ("refined_blocks", C.c_uint32), ("entry_is_provisional", C.c_uint32), ("entry_used", SmCarry)]
+                ("refined_blocks", C.c_uint32), ("entry_is_provisional", C.c_uint32), ("entry_used", SmCarry),
+                ("screen_ms", C.c_float), ("host_syncs", C.c_uint32)]
+
+
+class Capture(C.Structure):
+    _fields_ = [("iq", C.c_void_p), ("n_samples", C.c_uint64), ("iq_is_device_ptr", C.c_int32), ("handle", C.c_uint32)]
 
 
 def build_library():
@@ -156,6 +162,14 @@ def lib():
         L.ookd_gpu_decode_shard.restype = C.c_int
         L.ookd_gpu_decode_shard.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int,
                                             C.POINTER(SmCarry), C.POINTER(SmCarry), C.POINTER(GpuResult)]
+        L.ookd_gpu_decode_begin.restype = C.c_int
+        L.ookd_gpu_decode_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int,
+                                            C.POINTER(SmCarry)]
+        L.ookd_gpu_decode_end.restype = C.c_int
+        L.ookd_gpu_decode_end.argtypes = [C.c_void_p, C.POINTER(SmCarry), C.POINTER(GpuResult)]
+        L.ookd_gpu_batch_decode.restype = C.c_int
+        L.ookd_gpu_batch_decode.argtypes = [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(Capture), C.c_uint32,
+                                            C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(GpuResult)]
         L.ookd_gpu_resolve.restype = C.c_int
         L.ookd_gpu_resolve.argtypes = [C.c_void_p, C.POINTER(SmCarry), C.POINTER(SmCarry), C.POINTER(GpuResult)]
         L.ookd_gpu_halo.restype = C.c_uint32
@@ -302,7 +316,8 @@ class Gpu:
         self.want_list = True        # build res["msgs"] (list of tuples) besides res["msgs_raw"]
 
     def close(self):
-        if getattr(self, "h", None):
+        # (at interpreter shutdown module globals may already be gone: then the process is exiting anyway)
+        if getattr(self, "h", None) and lib is not None:
             lib().ookd_gpu_destroy(self.h)
             self.h = None
 
@@ -324,6 +339,7 @@ class Gpu:
         return dict(msgs_raw=rec, n_in=int(res.n_in), n_out=int(res.n_out), n_buffers=int(res.n_buffers),
                     n_edges=int(res.n_edges), msgs=msgs, first_bit=int(res.first_bit),
                     sm_rounds=int(res.sm_rounds), kernel_ms=float(res.kernel_ms), fir_ms=float(res.fir_ms),
+                    screen_ms=float(res.screen_ms), host_syncs=int(res.host_syncs),
                     gpu_launches=int(res.gpu_launches), refined_tiles=int(res.refined_tiles),
                     refined_blocks=int(res.refined_blocks), entry_is_provisional=int(res.entry_is_provisional),
                     entry_used=res.entry_used.astuple())
@@ -414,3 +430,37 @@ def synth(n_samples, toggles, i_on, q_on, noise_scale, seed, first_sample=0, dev
     if rc != 0:
         raise OokdError(f"ookd_gpu_synth: {lib().ookd_gpu_strerror(rc).decode()}")
     return out
+
+
+def batch_decode(gpus, captures, msgs_cap=None):
+    """Independent captures through ookd_gpu_batch_decode.  gpus: list of Gpu handles; captures: list of
+    (iq, handle_index) with iq a numpy int16 array (host) or (device_ptr, n_samples).
+    -> list of structured message arrays (MSG_DTYPE), one per capture, plus the per-capture statistics."""
+    n = len(captures)
+    caps = (Capture * max(n, 1))()
+    keep = []
+    for i, (iq, hi) in enumerate(captures):
+        if isinstance(iq, tuple):
+            caps[i].iq, caps[i].n_samples, caps[i].iq_is_device_ptr = int(iq[0]), int(iq[1]), 1
+        else:
+            a = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+            keep.append(a)
+            caps[i].iq, caps[i].n_samples, caps[i].iq_is_device_ptr = a.ctypes.data, a.size // 2, 0
+        caps[i].handle = hi
+    handles = (C.c_void_p * len(gpus))(*[g.h for g in gpus])
+    first = (C.c_uint64 * (n + 1))()
+    results = (GpuResult * max(n, 1))()
+    cap = int(msgs_cap) if msgs_cap is not None else 4096
+    while True:
+        out = np.zeros(cap, dtype=MSG_DTYPE)
+        rc = lib().ookd_gpu_batch_decode(handles, len(gpus), caps, n, out.ctypes.data, cap, first, results)
+        if rc == -5 and msgs_cap is None and first[n] > cap:       # OOKD_ERR_OVERFLOW: decode again with room for all
+            cap = int(first[n])
+            continue
+        if rc != 0:
+            raise OokdError(f"ookd_gpu_batch_decode: {lib().ookd_gpu_strerror(rc).decode()}")
+        break
+    msgs = [out[first[i]:first[i + 1]].copy() for i in range(n)]
+    stats = [dict(n_in=int(results[i].n_in), n_edges=int(results[i].n_edges), kernel_ms=float(results[i].kernel_ms),
+                  host_syncs=int(results[i].host_syncs), gpu_launches=int(results[i].gpu_launches)) for i in range(n)]
+    return msgs, stats

@@ -41,7 +41,7 @@ enum FirPath { FIR_GENERIC = 0, FIR_TILED_1STAGE_32, FIR_SCREEN_DEC4 };
 struct ookd_gpu {
     int device = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_s1 = nullptr;
     std::vector<cudaEvent_t> ev_piece;
 
     std::vector<Stage> stages;        // empty => no filter (treated as the 1-tap unity stage)
@@ -95,6 +95,18 @@ struct ookd_gpu {
     uint32_t launches = 0;
     uint32_t stat_refined_blocks = 0, stat_dense_tiles = 0;
     uint32_t work_cap = 0;
+
+    // a decode between ookd_gpu_decode_begin and ookd_gpu_decode_end
+    struct Pending {
+        bool active = false, fast = false;
+        const uint32_t *d_in = nullptr;
+        i64 in_base = 0, in_valid_end = 0;
+        u64 n_bits = 0, n_out = 0, n_eff = 0;
+        SmCarry e0{};
+        u64 edge_cap = 0, msg_cap = 0, n_copy = 0;
+        uint32_t rounds = 0;
+        int cur = 0;
+    } pend;
 
     char err[256] = {0};
 };
@@ -553,6 +565,7 @@ int run_state_machine_jacobi(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *
             }
             CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
             CU(h, cudaStreamSynchronize(h->s_compute));
+            h->stat_syncs++;
             if (h_nran[burst - 1] == 0) break;          // a round that re-ran nothing: fixed point
             if (rounds > nc + 8) return fail(h, OOKD_ERR_STATE, "state machine stitch did not converge");
         }
@@ -566,6 +579,7 @@ int run_state_machine_jacobi(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *
         h->launches++;
         CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
         CU(h, cudaStreamSynchronize(h->s_compute));
+        h->stat_syncs++;
         const u64 n_msgs = ((const u64 *) h->h_scalars)[1];
         if (n_msgs) {
             if ((rc = ensure(h, h->msgs_dev, sizeof(SmMsg) * n_msgs))) return rc;
@@ -581,6 +595,7 @@ int run_state_machine_jacobi(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *
         CU(h, cudaMemcpyAsync(&last, (SmCarry *) h->chunk_exit[cur].p + (nc - 1), sizeof(SmCarry),
                               cudaMemcpyDeviceToHost, h->s_compute));
         CU(h, cudaStreamSynchronize(h->s_compute));
+        h->stat_syncs++;
         return finish_messages(h, h->h_msgs_raw.data(), n_msgs, last, rounds_before + rounds, exit_, res);
     }
     return fail(h, OOKD_ERR_OVERFLOW, "message slots overflowed after retries");
@@ -747,6 +762,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
             CU(h, cudaGetLastError());
             CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
             CU(h, cudaStreamSynchronize(h->s_compute));
+            h->stat_syncs++;
             if (getenv("OOKD_DEBUG")) fprintf(stderr, "[ookd] sm rounds=%u resolved=%u/%u overflow=%u\n", rounds, h_walk[0], nc, *h_overflow);
             if (*h_overflow == 1) break;                    // message slots too small: grow and redo
             if (h_walk[1] == 1) { resolved = true; h->tab_cur = cur; break; }
@@ -776,6 +792,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
     h->launches++;
     CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
     CU(h, cudaStreamSynchronize(h->s_compute));
+    h->stat_syncs++;
     const u64 n_msgs = ((const u64 *) h->h_scalars)[1];
     SmCarry last;
     memcpy(&last, (const char *) h->h_scalars + 192, sizeof(SmCarry));
@@ -792,6 +809,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
         CU(h, cudaMemcpyAsync(h->h_msgs_raw.data(), h->msgs_dev.p, sizeof(SmMsg) * n_msgs, cudaMemcpyDeviceToHost,
                               h->s_compute));
         CU(h, cudaStreamSynchronize(h->s_compute));
+        h->stat_syncs++;
     }
     h->tables_valid = true;
     return finish_messages(h, h->h_msgs_raw.data(), n_msgs, last, rounds, exit_, res);
@@ -804,9 +822,8 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
 // that did not fit or resolve (edge list / work list / message slots too small, chain not resolved after
 // three rounds) sets *done = false and the caller repeats the tail on the synchronous path, which handles
 // every such case.
-int decode_tail_fast(ookd_gpu *h, u64 n_bits, SmCarry entry0, ookd_sm_carry *exit_, ookd_gpu_result *res, bool *done)
+int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
 {
-    *done = false;
     int rc;
     if (entry0.state < h->smc.num_states && entry0.k > h->smc.states[entry0.state].ksat) {
         entry0.k = h->smc.states[entry0.state].ksat;
@@ -932,6 +949,21 @@ int decode_tail_fast(ookd_gpu *h, u64 n_bits, SmCarry entry0, ookd_sm_carry *exi
         CU(h, cudaMemcpyAsync((char *) h->h_scalars + 288, h->final_entry.p, sizeof(SmCarry), cudaMemcpyDeviceToHost, h->s_compute));
     }
     CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
+    h->pend.edge_cap = x.cap;
+    h->pend.msg_cap = msg_cap;
+    h->pend.n_copy = n_copy;
+    h->pend.rounds = rounds;
+    h->pend.cur = cur;
+    return OOKD_OK;
+}
+
+int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *res, bool *done)
+{
+    *done = false;
+    const uint32_t nc = h->n_chunks;
+    const u64 msg_cap = h->pend.msg_cap, n_copy = h->pend.n_copy;
+    const uint32_t rounds = h->pend.rounds;
+    const int cur = h->pend.cur;
     CU(h, cudaStreamSynchronize(h->s_compute));
     h->stat_syncs++;
 
@@ -950,7 +982,7 @@ int decode_tail_fast(ookd_gpu *h, u64 n_bits, SmCarry entry0, ookd_sm_carry *exi
     h->stat_refined_blocks = refined;
     h->stat_dense_tiles = 0;
     if ((h->screen || h->path == FIR_SCREEN_DEC4) && refined > h->work_cap) return OOKD_OK;      // work list overflowed
-    if (n_edges_total > x.cap || *(const uint32_t *) (hs + 28) != 0) return OOKD_OK;      // edge list / a tile region too small
+    if (n_edges_total > h->pend.edge_cap || *(const uint32_t *) (hs + 28) != 0) return OOKD_OK;   // edge list / a tile region too small
     if (overflow != 0 || walk_complete != 1 || n_msgs > msg_cap) {
         if (overflow == 1) h->slot_cap *= 4;
         return OOKD_OK;
@@ -1031,6 +1063,7 @@ void ookd_gpu_destroy(ookd_gpu *h)
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->ev_f0) cudaEventDestroy(h->ev_f0);
     if (h->ev_f1) cudaEventDestroy(h->ev_f1);
+    if (h->ev_s1) cudaEventDestroy(h->ev_s1);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
     ookd_sm_compiled_free(&h->smc);
@@ -1073,6 +1106,7 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     CUC(cudaEventCreate(&h->ev_t1));
     CUC(cudaEventCreate(&h->ev_f0));
     CUC(cudaEventCreate(&h->ev_f1));
+    CUC(cudaEventCreate(&h->ev_s1));
     CUC(cudaHostAlloc(&h->h_scalars, 512, cudaHostAllocDefault));
     if (ensure(h, h->scalars, 512) != OOKD_OK) CREATE_FAIL(OOKD_ERR_NOMEM);
 
@@ -1184,18 +1218,18 @@ void ookd_gpu_initial_carry(const ookd_gpu *h, struct ookd_sm_carry *c)
     memset(c, 0, sizeof(*c));
 }
 
-int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, uint64_t first_sample,
-                          uint64_t n_samples, int last, const struct ookd_sm_carry *entry,
-                          struct ookd_sm_carry *exit_, struct ookd_gpu_result *res)
+int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, uint64_t first_sample,
+                          uint64_t n_samples, int last, const struct ookd_sm_carry *entry)
 {
     if (!h) return OOKD_ERR_ARG;
+    if (h->pend.active) return fail(h, OOKD_ERR_STATE, "decode_begin: the previous decode has not been ended");
     if (!iq && n_samples) return fail(h, OOKD_ERR_ARG, "null input");
     CU(h, cudaSetDevice(h->device));
     h->have_last = false;
     h->tables_valid = false;
     h->h_edges_valid = false;
     h->launches = 0;
-    if (res) memset(res, 0, sizeof(*res));
+    h->stat_syncs = 0;
 
     const u64 D = h->total_dec, spb = h->spb;
     const u64 align = spb / gcd64(spb, D) * D;                 // lcm(spb, D)
@@ -1294,18 +1328,47 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
                                         (uint32_t *) h->bits.p, h->bit_base))) return rc;
         }
     }
+    CU(h, cudaEventRecord(h->ev_s1, h->s_compute));
     if ((rc = launch_fir_refine(h, d_in, in_base, in_valid_end))) return rc;
     CU(h, cudaEventRecord(h->ev_f1, h->s_compute));
 
-    // ---- edges + state machine ----
+    // ---- edges + state machine: enqueued behind the FIR kernels when the single-synchronisation tail applies ----
     h->n_edges = 0;
     h->base_bit = 0;
     SmCarry e0{};
     if (entry) carry_to_dev(*entry, e0);
-    bool fast_done = false;
+    h->pend.d_in = d_in;
+    h->pend.in_base = in_base;
+    h->pend.in_valid_end = in_valid_end;
+    h->pend.n_bits = n_bits;
+    h->pend.n_out = n_out;
+    h->pend.n_eff = n_eff;
+    h->pend.e0 = e0;
+    h->pend.fast = false;
     if (n_bits > 0 && h->have_sm && h->out_hi > h->out_lo && !(h->flags & OOKD_FLAG_SYNC_TAIL)) {
         h->have_last = true;
-        if ((rc = decode_tail_fast(h, n_bits, e0, exit_, res, &fast_done))) return rc;
+        if ((rc = decode_tail_fast_enqueue(h, n_bits, e0))) return rc;
+        h->pend.fast = true;
+    }
+    h->pend.active = true;
+    return OOKD_OK;
+}
+
+int ookd_gpu_decode_end(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd_gpu_result *res)
+{
+    if (!h) return OOKD_ERR_ARG;
+    if (!h->pend.active) return fail(h, OOKD_ERR_STATE, "decode_end without decode_begin");
+    CU(h, cudaSetDevice(h->device));
+    h->pend.active = false;
+    if (res) memset(res, 0, sizeof(*res));
+    const uint32_t *d_in = h->pend.d_in;
+    const i64 in_base = h->pend.in_base, in_valid_end = h->pend.in_valid_end;
+    const u64 n_bits = h->pend.n_bits, n_out = h->pend.n_out, n_eff = h->pend.n_eff;
+    const SmCarry e0 = h->pend.e0;
+    int rc;
+    bool fast_done = false;
+    if (h->pend.fast) {
+        if ((rc = decode_tail_fast_finish(h, exit_, res, &fast_done))) return rc;
     }
     if (fast_done) {
         // everything fit and resolved behind a single synchronisation
@@ -1331,6 +1394,7 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
         if (rc) return rc;
         CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
         CU(h, cudaEventSynchronize(h->ev_t1));
+        h->stat_syncs++;
     }
     if (res) {
         res->n_in = n_eff;
@@ -1342,6 +1406,70 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
         res->refined_blocks = h->stat_refined_blocks;
         cudaEventElapsedTime(&res->kernel_ms, h->ev_t0, h->ev_t1);
         cudaEventElapsedTime(&res->fir_ms, h->ev_f0, h->ev_f1);
+        cudaEventElapsedTime(&res->screen_ms, h->ev_f0, h->ev_s1);
+        res->host_syncs = h->stat_syncs;
+    }
+    return OOKD_OK;
+}
+
+int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, uint64_t first_sample,
+                          uint64_t n_samples, int last, const struct ookd_sm_carry *entry,
+                          struct ookd_sm_carry *exit_, struct ookd_gpu_result *res)
+{
+    if (res) memset(res, 0, sizeof(*res));
+    const int rc = ookd_gpu_decode_begin(h, iq, iq_is_device_ptr, first_sample, n_samples, last, entry);
+    if (rc) return rc;
+    return ookd_gpu_decode_end(h, exit_, res);
+}
+
+// Independent captures: capture i is decoded whole (first sample 0, EOF padding) by
+// handles[caps[i].handle].  Up to one decode per handle is in flight: while the host waits for one handle's
+// single synchronisation the kernels of the others keep the device busy, so the latency-bound stages
+// (edge scan, state-machine rounds) of different captures overlap.
+int ookd_gpu_batch_decode(ookd_gpu *const *handles, uint32_t n_handles, const struct ookd_capture *caps, uint32_t n_caps,
+                          struct ookd_msg *msgs_out, uint64_t msgs_cap, uint64_t *msg_first, struct ookd_gpu_result *results)
+{
+    if (!handles || !n_handles || (!caps && n_caps) || !msg_first) return OOKD_ERR_ARG;
+    std::vector<int64_t> in_flight(n_handles, -1);
+    std::vector<u64> counts(n_caps, 0);
+    std::vector<std::vector<ookd_msg>> held(n_caps);
+    auto finish = [&](uint32_t hi) -> int {
+        const int64_t ci = in_flight[hi];
+        if (ci < 0) return OOKD_OK;
+        in_flight[hi] = -1;
+        ookd_gpu_result r;
+        const int rc = ookd_gpu_decode_end(handles[hi], nullptr, &r);
+        if (rc) return rc;
+        counts[ci] = r.n_msgs;
+        held[ci].assign(r.msgs, r.msgs + r.n_msgs);          // the handle's list is reused by its next decode
+        if (results) {
+            results[ci] = r;
+            results[ci].msgs = nullptr;
+        }
+        return OOKD_OK;
+    };
+    int rc = OOKD_OK;
+    for (uint32_t i = 0; i < n_caps && !rc; i++) {
+        const uint32_t hi = caps[i].handle;
+        if (hi >= n_handles || !handles[hi]) { rc = OOKD_ERR_ARG; break; }
+        if ((rc = finish(hi))) break;
+        rc = ookd_gpu_decode_begin(handles[hi], caps[i].iq, caps[i].iq_is_device_ptr, 0, caps[i].n_samples, 1, nullptr);
+        if (!rc) in_flight[hi] = i;
+    }
+    for (uint32_t hi = 0; hi < n_handles; hi++) {
+        const int rc2 = finish(hi);
+        if (!rc) rc = rc2;
+    }
+    if (rc) return rc;
+    u64 total = 0;
+    for (uint32_t i = 0; i < n_caps; i++) {
+        msg_first[i] = total;
+        total += counts[i];
+    }
+    msg_first[n_caps] = total;
+    if (total > msgs_cap || (total && !msgs_out)) return OOKD_ERR_OVERFLOW;     // msg_first[n_caps] tells how much is needed
+    for (uint32_t i = 0; i < n_caps; i++) {
+        if (counts[i]) memcpy(msgs_out + msg_first[i], held[i].data(), sizeof(ookd_msg) * counts[i]);
     }
     return OOKD_OK;
 }
@@ -1388,6 +1516,7 @@ int ookd_gpu_edges(ookd_gpu *h, const uint64_t **edges, uint64_t *n_edges, uint3
             CU(h, cudaMemcpyAsync(h->h_edges.data(), h->edges.p, sizeof(u64) * h->n_edges, cudaMemcpyDeviceToHost,
                                   h->s_compute));
             CU(h, cudaStreamSynchronize(h->s_compute));
+            h->stat_syncs++;
         }
         h->h_edges_valid = true;
     }

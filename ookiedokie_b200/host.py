@@ -106,7 +106,8 @@ class Fir:
                        for i in range(d.num_stages)]
 
     def __del__(self):
-        if getattr(self, "h", None):
+        # at interpreter shutdown module globals may already be gone: then the process is exiting anyway
+        if getattr(self, "h", None) and lib is not None:
             lib().ookd_fir_deinit(self.h)
             self.h = None
 
@@ -124,7 +125,7 @@ class Device:
         self.name = lib().ookd_device_name(self.h).decode()
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib().ookd_device_deinit(self.h)
             self.h = None
 

@@ -44,10 +44,30 @@ def _dev():
 REC_BYTES = 112         # exit carry (48) | entry used (48) | changed flag (4) | message count (4) | pad (8)
 
 
-def stitch_and_gather(runner, rank, world, msg_cap=4096):
+class _StitchBuffers:
+    """Pinned host and device staging reused across steps (one collective, one synchronisation per step)."""
+
+    def __init__(self, world, cap, isz, dev):
+        self.cap = cap
+        self.nbytes = REC_BYTES + cap * isz
+        pin = dev.type == "cuda"
+        self.h_mine = torch.zeros(self.nbytes, dtype=torch.uint8, pin_memory=pin)
+        self.h_all = torch.zeros(world * self.nbytes, dtype=torch.uint8, pin_memory=pin)
+        self.d_mine = torch.zeros(self.nbytes, dtype=torch.uint8, device=dev)
+        self.d_all = torch.zeros(world * self.nbytes, dtype=torch.uint8, device=dev)
+        self.np_mine = self.h_mine.numpy()
+        self.np_all = self.h_all.numpy()
+
+
+_stitch_cache = {}
+_stitch_cap = {}
+
+
+def stitch_and_gather(runner, rank, world, msg_cap=None):
     """stitch() + gather_messages_raw() with ONE collective in the common case: every rank ships its
     carry record together with its (padded) message block; if the records are consistent the job is done.
-    Returns (result, exit, rounds, messages on rank 0 | None)."""
+    The block is sized from the largest per-rank message count of the previous call (every rank saw the same
+    counts, so every rank picks the same size).  Returns (result, exit, rounds, messages on rank 0 | None)."""
     from .binding import MSG_DTYPE
     res, exit_c = runner.decode(None)
     if world == 1:
@@ -56,27 +76,43 @@ def stitch_and_gather(runner, rank, world, msg_cap=4096):
     dev = _dev()
     isz = MSG_DTYPE.itemsize
     rec = res["msgs_raw"]
-    if len(rec) <= msg_cap:
-        buf = np.zeros(REC_BYTES + msg_cap * isz, dtype=np.uint8)
-        buf[:REC_BYTES] = np.frombuffer(carry_to_bytes(exit_c) + carry_to_bytes(entry_used) +
-                                        np.array([0, len(rec), 0, 0], dtype=np.uint32).tobytes(), dtype=np.uint8)
-        buf[REC_BYTES:REC_BYTES + len(rec) * isz] = rec.view(np.uint8).reshape(-1)
-        mine = torch.from_numpy(buf).to(dev)
-        allb = torch.empty(world * buf.size, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(allb, mine)
-        g = allb.cpu().numpy().reshape(world, buf.size)
-        counts = g[:, 100:104].copy().view(np.uint32).reshape(-1).tolist()
-        ok = all(g[r, 48:96].tobytes() == g[r - 1, :48].tobytes() for r in range(1, world)) and max(counts) <= msg_cap
-        if ok:
-            msgs = None
-            if rank == 0:
-                msgs = np.concatenate([g[r, REC_BYTES:REC_BYTES + counts[r] * isz].copy().view(MSG_DTYPE)
-                                       for r in range(world)])
-            return res, exit_c, 1, msgs
-    # inconsistent entries (or an oversized message list): fall back to the round protocol
-    res, exit_c, rounds = _stitch_rounds(runner, rank, world, res, exit_c, entry_used, dev)
-    msgs = gather_messages_raw(res["msgs_raw"], rank, world, res.get("_counts"))
-    return res, exit_c, rounds + 1, msgs
+    cap = msg_cap if msg_cap is not None else _stitch_cap.get(world, 1024)
+    key = (world, cap, dev.type, dev.index)
+    sb = _stitch_cache.get(key)
+    if sb is None:
+        sb = _stitch_cache[key] = _StitchBuffers(world, cap, isz, dev)
+    n_ship = min(len(rec), cap)
+    hdr = carry_to_bytes(exit_c) + carry_to_bytes(entry_used) + np.array([0, len(rec), 0, 0], dtype=np.uint32).tobytes()
+    sb.np_mine[:REC_BYTES] = np.frombuffer(hdr, dtype=np.uint8)
+    if n_ship:
+        sb.np_mine[REC_BYTES:REC_BYTES + n_ship * isz] = rec[:n_ship].view(np.uint8).reshape(-1)
+    sb.d_mine.copy_(sb.h_mine, non_blocking=True)
+    dist.all_gather_into_tensor(sb.d_all, sb.d_mine)
+    sb.h_all.copy_(sb.d_all, non_blocking=True)
+    if dev.type == "cuda":
+        torch.cuda.current_stream().synchronize()
+    g = sb.np_all.reshape(world, sb.nbytes)
+    counts = g[:, 100:104].copy().view(np.uint32).reshape(-1).tolist()
+    if msg_cap is None:
+        want = 1024
+        while want < max(counts) + max(counts) // 4 + 64:
+            want *= 2
+        _stitch_cap[world] = want                      # same on every rank: derived from the gathered counts
+    ok = all(g[r, 48:96].tobytes() == g[r - 1, :48].tobytes() for r in range(1, world))
+    if ok and max(counts) <= cap:
+        msgs = None
+        if rank == 0:
+            msgs = np.concatenate([g[r, REC_BYTES:REC_BYTES + counts[r] * isz].copy().view(MSG_DTYPE)
+                                   for r in range(world)])
+        return res, exit_c, 1, msgs
+    if not ok:
+        # inconsistent entries: the round protocol re-runs the state-machine stage of the shards that guessed wrong
+        res, exit_c, rounds = _stitch_rounds(runner, rank, world, res, exit_c, entry_used, dev)
+        msgs = gather_messages_raw(res["msgs_raw"], rank, world, res.get("_counts"))
+        return res, exit_c, rounds + 1, msgs
+    # consistent, but a message list did not fit the block (first call, or a burst): fetch the lists separately
+    msgs = gather_messages_raw(res["msgs_raw"], rank, world, counts)
+    return res, exit_c, 1, msgs
 
 
 def stitch(runner, rank, world, guess=None):
@@ -165,11 +201,15 @@ class GpuShardRunner:
         self.gpu, self.iq, self.first, self.n, self.last = gpu, iq, first_sample, n_samples, last
         self.launches = 0
         self.fir_ms = 0.0
+        self.screen_ms = 0.0
         self.kernel_ms = 0.0
+        self.host_syncs = 0
 
     def _acc(self, res):
         self.launches += res["gpu_launches"]
         self.fir_ms += res["fir_ms"]
+        self.screen_ms += res.get("screen_ms", 0.0)
+        self.host_syncs += res.get("host_syncs", 0)
         self.kernel_ms += res["kernel_ms"]
 
     def decode(self, entry):

@@ -37,7 +37,12 @@ class OracleShardRunner:
                 if r == 1:
                     m = self.out_lo + b0 + total - 1
                     msgs.append((m, (m + 1 - 1) // self.opb, sm.get_state()[2], sm.data()[:nbytes]))
-        return dict(msgs=msgs, entry_used=entry if entry is not None else S.INITIAL_CARRY), sm.get_state()
+        from ookiedokie_b200.binding import MSG_DTYPE
+        raw = np.zeros(len(msgs), dtype=MSG_DTYPE)
+        for i, (m, b, nb, data) in enumerate(msgs):
+            raw[i]["out_sample"], raw[i]["buffer_idx"], raw[i]["num_bits"] = m, b, nb
+            raw[i]["data"][:len(data)] = np.frombuffer(bytes(data), dtype=np.uint8)
+        return dict(msgs=msgs, msgs_raw=raw, entry_used=entry if entry is not None else S.INITIAL_CARRY), sm.get_state()
 
     def decode(self, entry):
         self.calls.append("decode")
@@ -61,8 +66,19 @@ def main():
     per = (n_buf + world - 1) // world
     lo, hi = rank * per * spb, min((rank + 1) * per * spb, len(full["bits"]))
     runner = OracleShardRunner(dev, 3000000, full["bits"][lo:hi], lo, spb)
-    res, exit_c, rounds = S.stitch(runner, rank, world)
-    msgs = S.gather_messages(res["msgs"], rank, world, (dev["num_bits"] + 7) // 8)
+    nbytes = (dev["num_bits"] + 7) // 8
+    if len(sys.argv) > 2 and sys.argv[2] == "fused":
+        # the single-collective form bench.py uses; twice, so that the adaptive block size is exercised, and once
+        # with a block too small for the message lists (falls back to the separate gather)
+        from ookiedokie_b200.binding import msgs_to_tuples
+        for cap in (None, None, 1):
+            res, exit_c, rounds, raw = S.stitch_and_gather(runner, rank, world, msg_cap=cap)
+            msgs = msgs_to_tuples(raw, nbytes) if rank == 0 else None
+            if rank == 0:
+                assert [tuple(m) for m in msgs] == [tuple(m) for m in full["msgs"]], cap
+    else:
+        res, exit_c, rounds = S.stitch(runner, rank, world)
+        msgs = S.gather_messages(res["msgs"], rank, world, nbytes)
     if rank == 0:
         ok = [tuple(m) for m in msgs] == [tuple(m) for m in full["msgs"]]
         json.dump(dict(ok=ok, n=len(msgs), want=len(full["msgs"]), rounds=rounds), open(out_path, "w"))

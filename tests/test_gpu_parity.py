@@ -194,3 +194,35 @@ def test_large_capture_paths_agree_and_are_deterministic():
                 assert len(cur[2]) > 600
             assert cur[0] == ref[0] and np.array_equal(cur[1], ref[1]) and np.array_equal(cur[2], ref[2]), flags
         g.close()
+
+
+def test_batch_of_independent_captures_matches_oracle():
+    """BASELINE configs[4] in miniature: mixed devices through fs64_fs8, several captures in flight on several
+    handles (ookd_gpu_batch_decode); every capture must decode exactly like the oracle run on it alone."""
+    stages = O.load_filter("fs64_fs8")
+    devs = [O.load_device("p3l-nexa2012"), O.load_device("unknown-remote1")]
+    gpus = []
+    for d in devs:
+        for _ in range(2):                       # two handles per device description: two captures of a kind in flight
+            gpus.append(B.Gpu(filter_stages=stages, sm=util.sm_spec(d, stages), threshold=0.1, samples_per_buffer=8192))
+    captures, want = [], []
+    for i in range(10):
+        kind = i % 2
+        dev = devs[kind]
+        sigma = [0.0, 0.02, 0.05][i % 3]
+        fields = util.nexa_fields if kind == 0 else None
+        iq, sent, _ = util.capture(dev, 2 + i % 3, sigma=sigma, phase=0.3 * i, seed=100 + i, fields=fields)
+        captures.append((iq, 2 * kind + (i // 2) % 2))
+        want.append(O.rx(iq, stages, dev, samples_per_buffer=8192)["msgs"])
+    msgs, stats = B.batch_decode(gpus, captures)
+    for i in range(10):
+        nbytes = (devs[i % 2]["num_bits"] + 7) // 8
+        assert B.msgs_to_tuples(msgs[i], nbytes) == [tuple(m) for m in want[i]], i
+        assert stats[i]["gpu_launches"] > 0
+    assert sum(len(m) for m in msgs) > 0
+    # a second batch on the same handles, device-resident inputs this time
+    import torch
+    d_caps = [torch.from_numpy(np.ascontiguousarray(c[0]).reshape(-1)).cuda() for c in captures[:4]]
+    msgs2, _ = B.batch_decode(gpus, [((t.data_ptr(), t.numel() // 2), captures[i][1]) for i, t in enumerate(d_caps)])
+    for i in range(4):
+        assert np.array_equal(msgs2[i], msgs[i])

@@ -35,3 +35,18 @@ def test_time_shard_stitch_matches_sequential(world, tmp_path):
     for r in range(1, world):
         calls = json.load(open(out + f".rank{r}"))["calls"]
         assert calls[0] == "decode" and all(c == "resolve" for c in calls[1:])
+
+
+@pytest.mark.parametrize("world", [2])
+def test_fused_stitch_and_gather(world, tmp_path):
+    """stitch_and_gather (one collective carrying records and message blocks) gives the sequential decode."""
+    out = str(tmp_path / "result.json")
+    port = _free_port()
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_shard_worker.py"), out, "fused"], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    res = json.load(open(out))
+    assert res["ok"] and res["n"] == res["want"] == 5, res

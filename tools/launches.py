@@ -1,11 +1,38 @@
-"""Print the kernels of the last bench step from an ncu --csv launch list (gpu__time_duration.sum)."""
-import csv, sys
+"""Summarise an ncu --csv launch list (gpu__time_duration.sum) of bench.py: one decode step = the launches up
+to and including sm_gather_table_kernel.  Prints the second step (shard resident in HBM) launch by launch and
+the last step (host input: one screening launch per 64 MiB piece) aggregated by kernel."""
+import collections
+import csv
+import sys
+
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
-h = rows[hdr]; ki = h.index('Kernel Name'); vi = h.index('Metric Value')
-seq = [(r[ki][:60], float(r[vi].replace(',', ''))) for r in rows[hdr + 2:]]
-idx = [i for i, (n, v) in enumerate(seq) if 'screen' in n]
-tot = 0
-for n, v in seq[idx[-1]:]:
-    print(f"{v / 1000:9.1f} us  {n}"); tot += v
+h = rows[hdr]
+ki, vi = h.index('Kernel Name'), h.index('Metric Value')
+seq = [(r[ki].split('(')[0].replace('void ', ''), float(r[vi].replace(',', ''))) for r in rows[hdr + 2:] if len(r) > vi]
+steps, cur = [], []
+for n, v in seq:
+    if 'synth' in n:
+        continue
+    cur.append((n, v))
+    if 'sm_gather' in n:
+        steps.append(cur)
+        cur = []
+print(f"{len(steps)} decode steps in the list")
+dev_step = steps[1] if len(steps) > 1 else steps[0]
+tot = sum(v for _, v in dev_step)
+print("-- device-resident step --")
+for n, v in dev_step:
+    print(f"{v / 1000:9.1f} us  {100 * v / tot:5.1f} %  {n}")
 print(f"{tot / 1000:9.1f} us  total")
+if len(steps) > 2:
+    agg = collections.OrderedDict()
+    for n, v in steps[-1]:
+        a = agg.setdefault(n, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print("-- host-input (e2e) step, aggregated --")
+    for n, (c, v) in agg.items():
+        print(f"{v / 1000:9.1f} us  {100 * v / tot:5.1f} %  x{c:<3d} {n}")
+    print(f"{tot / 1000:9.1f} us  total")
