@@ -145,6 +145,10 @@ struct ookd_sm_carry {
     uint8_t  data[OOKD_MSG_BYTES];
 };
 
+/* State the compiled machine settles in on a constant-0 input from RESET (the stitcher's speculative
+ * seed at a plausible message start). */
+void ookd_sm_idle_carry(const struct ookd_sm_compiled *c, struct ookd_sm_carry *out);
+
 struct ookd_gpu_config {
     const struct ookd_filter_desc *filter;   /* NULL or num_stages==0 => no filter     */
     const struct ookd_sm_desc *sm;           /* NULL => thresholds/edges only          */

@@ -61,11 +61,12 @@ struct ookd_gpu {
 
     bool have_sm = false;
     ookd_sm_compiled smc{};
+    SmCarry canon{};                  // idle state of the machine: seed assumed at anchors
     SmTable *d_tab = nullptr;
 
     // workspaces
     DevBuf in, bits, inter[2], block_counts, edges, scalars, chunk_exit[2], chunk_ran, slots, slot_count,
-           slot_off, msgs_dev, dense_list, chunk_e, edge_tmp, final_entry, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
+           slot_off, msgs_dev, dense_list, chunk_e, bound_pos, seed_pos, seed_e, seed_kind, edge_tmp, final_entry, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
     uint32_t slot_cap = 8;
     bool tables_valid = false;       // entry/exit tables of the last decode can be extended by resolve
     int tab_cur = 0;
@@ -524,6 +525,11 @@ SmArgs base_sm_args(ookd_gpu *h, const SmCarry &entry0)
     a.warm = h->warm ? 1u : 0u;
     a.first_chunk = 0;
     a.chunk_e = (u64 *) h->chunk_e.p;
+    a.bound_pos = (i64 *) h->bound_pos.p;
+    a.seed_pos = (i64 *) h->seed_pos.p;
+    a.seed_e = (u64 *) h->seed_e.p;
+    a.seed_kind = (uint8_t *) h->seed_kind.p;
+    a.canon = h->canon;
     return a;
 }
 
@@ -543,6 +549,7 @@ int run_state_machine_jacobi(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *
     for (int attempt = 0; attempt < 12; attempt++) {
         if ((rc = ensure(h, h->slots, sizeof(SmMsg) * (size_t) nc * TAB_K * h->slot_cap))) return rc;
         SmArgs a = base_sm_args(h, entry0);
+        a.bound_pos = nullptr;                              // fixed buffer boundaries
         CU(h, cudaMemsetAsync(a.overflow, 0, 4, h->s_compute));
         a.ran_with = (SmCarry *) h->chunk_ran.p;
         a.slot_count = (uint32_t *) h->slot_count.p;
@@ -680,8 +687,12 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
     h->tables_valid = false;
     if (!incremental) {
         if ((rc = ensure(h, h->chunk_e, sizeof(u64) * nc))) return rc;
+        if ((rc = ensure(h, h->bound_pos, sizeof(i64) * nc))) return rc;
+        if ((rc = ensure(h, h->seed_pos, sizeof(i64) * nc))) return rc;
+        if ((rc = ensure(h, h->seed_e, sizeof(u64) * nc))) return rc;
+        if ((rc = ensure(h, h->seed_kind, nc + 16))) return rc;
         SmArgs ia = base_sm_args(h, entry0);
-        sm_chunk_index_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(ia);
+        sm_anchor_kernel<<<nc, 32, 0, h->s_compute>>>(ia);
         h->launches++;
         CU(h, cudaGetLastError());
     }
@@ -746,9 +757,10 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
                 h->launches++;
                 CU(h, cudaGetLastError());
                 rounds++;
-                if (burst == 3 && r == 1) {
-                    // rounds 0+1 resolve the common case: link and walk now, so that round 2 (and the second
-                    // link/walk) return at once instead of costing another chunk-long latency
+                if (burst == 3 && r <= 1) {
+                    // round 0 resolves the common case (boundaries sit on anchors): link and walk after every
+                    // round, so that later rounds (and link/walks) return at once instead of costing another
+                    // chunk-long latency
                     a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
                     sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
                     sm_walk_kernel<<<1, 1024, 0, h->s_compute>>>(a);
@@ -846,6 +858,10 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     if ((rc = ensure(h, h->tab_chosen, (size_t) nc + 16))) return rc;
     if ((rc = ensure(h, h->final_entry, sizeof(SmCarry)))) return rc;
     if ((rc = ensure(h, h->chunk_e, sizeof(u64) * nc))) return rc;
+    if ((rc = ensure(h, h->bound_pos, sizeof(i64) * nc))) return rc;
+    if ((rc = ensure(h, h->seed_pos, sizeof(i64) * nc))) return rc;
+    if ((rc = ensure(h, h->seed_e, sizeof(u64) * nc))) return rc;
+    if ((rc = ensure(h, h->seed_kind, nc + 16))) return rc;
     if ((rc = ensure(h, h->slots, sizeof(SmMsg) * (size_t) nc * TAB_K * h->slot_cap))) return rc;
     const u64 msg_cap = (u64) nc * h->slot_cap;                       // at most slot_cap messages per chunk are kept
     if ((rc = ensure(h, h->msgs_dev, sizeof(SmMsg) * msg_cap))) return rc;
@@ -904,7 +920,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     a.walk_status = (uint32_t *) ((char *) h->scalars.p + 40);
     a.msg_counts = (uint32_t *) h->slot_count.p;
     a.final_exit = (SmCarry *) ((char *) h->scalars.p + 192);
-    sm_chunk_index_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a);
+    sm_anchor_kernel<<<nc, 32, 0, h->s_compute>>>(a);
     h->launches++;
     CU(h, cudaMemsetAsync(h->tab_cnt[0].p, 0, sizeof(uint32_t) * nc, h->s_compute));
     int cur = 0;
@@ -927,7 +943,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
         h->launches++;
         CU(h, cudaGetLastError());
         rounds++;
-        if (r >= 1) {
+        {
             a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
             sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
             sm_walk_kernel<<<1, 1024, 0, h->s_compute>>>(a);
@@ -971,8 +987,8 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
     const char *hs = (const char *) h->h_scalars;
     if (getenv("OOKD_DEBUG")) {
         const uint32_t *nr = (const uint32_t *) (hs + 64);
-        fprintf(stderr, "[ookd] fast tail: ran %u/%u/%u pairs in rounds 0/1/2, walk resolved %u then %u of %u chunks, overflow %u\n",
-                nr[0], nr[1], nr[2], nr[16 + 1], nr[16 + 2], nc, *(const uint32_t *) (hs + 32));
+        fprintf(stderr, "[ookd] fast tail: ran %u/%u/%u pairs in rounds 0/1/2, walks resolved %u, %u, %u of %u chunks, overflow %u\n",
+                nr[0], nr[1], nr[2], nr[16 + 0], nr[16 + 1], nr[16 + 2], nc, *(const uint32_t *) (hs + 32));
     }
     const u64 n_edges_total = *(const u64 *) hs;
     const u64 n_msgs = *(const u64 *) (hs + 8);
@@ -1053,7 +1069,8 @@ void ookd_gpu_destroy(ookd_gpu *h)
     if (h->d_tab) cudaFree(h->d_tab);
     DevBuf *all[] = {&h->in, &h->bits, &h->inter[0], &h->inter[1], &h->block_counts, &h->edges, &h->scalars,
                      &h->chunk_exit[0], &h->chunk_exit[1], &h->chunk_ran, &h->slots, &h->slot_count,
-                     &h->slot_off, &h->msgs_dev, &h->dense_list, &h->chunk_e, &h->edge_tmp, &h->final_entry, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
+                     &h->slot_off, &h->msgs_dev, &h->dense_list, &h->chunk_e, &h->bound_pos, &h->seed_pos, &h->seed_e, &h->seed_kind, &h->edge_tmp,
+                     &h->final_entry, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
                      &h->tab_cnt[1], &h->tab_link, &h->tab_chosen};
     for (DevBuf *b : all) release(*b);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -1201,6 +1218,9 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
         if (e == cudaSuccess) e = cudaMemcpy(h->d_tab, tab, sizeof(SmTable), cudaMemcpyHostToDevice);
         delete tab;
         if (e != cudaSuccess) CREATE_FAIL(OOKD_ERR_CUDA);
+        ookd_sm_carry idle;
+        ookd_sm_idle_carry(&h->smc, &idle);
+        carry_to_dev(idle, h->canon);
         h->have_sm = true;
     }
 #undef CUC

@@ -260,3 +260,78 @@ float ookd_power_threshold(float thr)
     }
     return p;
 }
+
+
+/*
+ * State the compiled machine settles in when it is fed a constant 0 from RESET: the entry state the
+ * parallel stitcher assumes at a plausible message start ("anchor").  Plain per-sample interpretation of
+ * the compiled tables, the host twin of sm_eval / sm_step in sm_kernels.cuh (reference
+ * src/state_machine.c:421-556).  It is only ever used as a SPECULATIVE seed: a wrong answer costs extra
+ * rounds, never correctness.
+ */
+static int idle_eval(const struct ookd_sm_compiled *c, struct ookd_sm_carry *s, uint32_t b)
+{
+    const struct ookd_sm_state_k *st = &c->states[s->state];
+    int fired = -1, check = 0;
+    for (uint32_t i = 0; i < st->num_triggers && fired < 0; i++) {
+        const struct ookd_sm_trigger_k *t = &c->triggers[st->first_trigger + i];
+        if (s->k < t->kmin || s->k > t->kmax) {
+            continue;
+        }
+        switch (t->cond) {
+            case OOKD_COND_ALWAYS:       fired = (int) i; break;
+            case OOKD_COND_PULSE_START:  if (!s->prev_bit && b) { fired = (int) i; check = 1; } break;
+            case OOKD_COND_PULSE_END:    if (s->prev_bit && !b) { fired = (int) i; check = 1; } break;
+            case OOKD_COND_TIMEOUT:      if (st->ktimeout != OOKD_K_INF && s->k >= st->ktimeout) fired = (int) i; break;
+            case OOKD_COND_MSG_COMPLETE: if (s->num_bits >= c->max_bits) fired = (int) i; break;
+            default: break;
+        }
+    }
+    if (fired < 0) {
+        s->k = (s->k + 1 < st->ksat) ? s->k + 1 : st->ksat;
+        return 0;
+    }
+    int result = 0;
+    if (!check || (s->k >= st->dmin && s->k <= st->dmax)) {
+        const struct ookd_sm_trigger_k *t = &c->triggers[st->first_trigger + fired];
+        if (t->action == OOKD_ACT_APPEND_0 || t->action == OOKD_ACT_APPEND_1) {
+            if (s->num_bits <= c->max_bits && s->num_bits < 8 * OOKD_MSG_BYTES) {
+                const uint32_t byte = s->num_bits >> 3, bit = s->num_bits & 7;
+                if (t->action == OOKD_ACT_APPEND_1) s->data[byte] |= (uint8_t) (1u << bit);
+                else s->data[byte] &= (uint8_t) ~(1u << bit);
+            }
+            s->num_bits++;
+        } else if (t->action == OOKD_ACT_OUTPUT_DATA) {
+            result = 1;
+        }
+        s->state = t->next_state;
+    } else {
+        result = -1;
+        s->state = 0;
+    }
+    s->k = 0;
+    return result;
+}
+
+void ookd_sm_idle_carry(const struct ookd_sm_compiled *c, struct ookd_sm_carry *out)
+{
+    struct ookd_sm_carry s;
+    memset(&s, 0, sizeof(s));
+    if (c && c->num_states) {
+        uint64_t n = 4ull * (uint64_t) (c->k_sat < 4000000u ? c->k_sat : 4000000u) + 64;
+        const uint32_t nbytes = (c->max_bits + 7) / 8;
+        for (uint64_t i = 0; i < n; i++) {
+            int r = 0;
+            if (s.state == 0) {
+                s.num_bits = 0;
+                memset(s.data, 0, nbytes < OOKD_MSG_BYTES ? nbytes : OOKD_MSG_BYTES);
+                r = idle_eval(c, &s, 0);
+            }
+            if (r == 0) {
+                (void) idle_eval(c, &s, 0);
+            }
+            s.prev_bit = 0;
+        }
+    }
+    *out = s;
+}

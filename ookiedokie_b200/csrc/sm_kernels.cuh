@@ -81,8 +81,19 @@ struct SmArgs {
     uint32_t first_chunk;     // chunk the walk starts at (1 when chunk 0 is a warm-up chunk being bypassed)
     uint32_t warm;            // chunk 0 is a warm-up chunk in front of the shard: it has no true entry
     SmCarry  *final_entry;    // warm: state at the shard's first output = exit of chunk 0's chosen pair
-    u64 *chunk_e;             // [n_chunks] index of the first edge at or after each chunk's start (sm_chunk_index_kernel)
+    u64 *chunk_e;             // [n_chunks] index of the first edge at or after each chunk's start (sm_anchor_kernel)
+    // Boundaries moved to anchors (sm_anchor_kernel): chunk c covers [bound_pos[c], bound_pos[c+1]).
+    i64 *bound_pos;           // [n_chunks]; null => the fixed buffer boundaries (Jacobi fallback)
+    i64 *seed_pos;            // [n_chunks] where the round-0 seed run of chunk c starts (>= bound_pos[c])
+    u64 *seed_e;              // [n_chunks] index of the first edge at or after seed_pos
+    uint8_t *seed_kind;       // [n_chunks] OOKD_SEED_*
+    SmCarry canon;            // state an idle machine is in (ookd_sm_idle_carry): the seed assumed at an anchor
 };
+
+#define OOKD_SEED_TRUE      0   /* the shard's true entry (chunk 0)                                             */
+#define OOKD_SEED_CANON     1   /* idle machine at the chunk's anchor; the chunk's boundary IS the anchor        */
+#define OOKD_SEED_ANCHOR    2   /* RESET at an anchor inside a chunk whose boundary stays fixed: source of exits */
+#define OOKD_SEED_RESET     3   /* no anchor: RESET at the chunk's first sample                                  */
 
 __device__ __forceinline__ i64 first_output_of_buffer(const SmArgs &a, u64 b)
 {
@@ -105,6 +116,10 @@ __device__ __forceinline__ i64 next_buffer_start(const SmArgs &a, i64 m, i64 lo)
     }
     return first_output_of_buffer(a, buffer_of_output(a, m) + 1);
 }
+
+// Bit 1 of SmCarry::prev: "device_process has given up on the buffer this position lies in" (ERROR before a span
+// boundary that is not a buffer boundary); the next span skips to the buffer's end before it evaluates anything.
+#define OOKD_CARRY_DROPPING 2u
 
 __device__ __forceinline__ bool carry_equal(const SmCarry &x, const SmCarry &y)
 {
@@ -299,6 +314,24 @@ __device__ __forceinline__ int sm_run_span(const SmArgs &a, const u64 n_edges, c
     u64 next_edge = (e < n_edges) ? a.edges[e] : INF;
     u64 after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;   // one-ahead prefetch
 
+    if (s.prev & OOKD_CARRY_DROPPING) {
+        // The previous span ended inside a buffer device_process had given up on (span boundaries sit on
+        // anchors, not on buffer boundaries): keep skipping to that buffer's end.
+        s.prev &= 1u;
+        i64 nb = next_buffer_start(a, pos, chunk_lo);
+        const bool more = nb > end;
+        if (more) nb = end;
+        if (next_edge < (u64) nb) {
+            const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb);
+            tb ^= (uint32_t) ((e2 - e) & 1);
+            e = e2;
+            next_edge = (e < n_edges) ? a.edges[e] : INF;
+            after_edge = (e + 1 < n_edges) ? a.edges[e + 1] : INF;
+        }
+        pos = nb;
+        if (more) s.prev |= OOKD_CARRY_DROPPING;
+    }
+
     while (pos < end) {
         const bool at_edge = (next_edge == (u64) pos);
         if (s.state == 0 || s.prev != tb || at_edge) {
@@ -321,7 +354,10 @@ __device__ __forceinline__ int sm_run_span(const SmArgs &a, const u64 n_edges, c
             } else if (r < 0) {
                 // device_process gives up on this buffer: resume at the next buffer's first output
                 i64 nb = next_buffer_start(a, pos - 1, chunk_lo);
-                if (nb > end) nb = end;
+                if (nb > end) {
+                    nb = end;
+                    s.prev |= OOKD_CARRY_DROPPING;           // the next span goes on skipping
+                }
                 if (nb > pos) {
                     if (next_edge < (u64) nb) {
                         const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb);
@@ -560,6 +596,23 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
     E.reset(e);
     uint32_t next_edge = E.at(e);                                       // NONE: no further edge in range
 
+    if (s.prev & OOKD_CARRY_DROPPING) {
+        // the previous span ended inside a buffer device_process had given up on: keep skipping to its end
+        s.prev &= 1u;
+        i64 nb64 = next_buffer_start(a, pos64, chunk_lo);
+        const bool more = nb64 > end64;
+        if (more) nb64 = end64;
+        const uint32_t nb = (uint32_t) (nb64 - chunk_lo);
+        if (next_edge < nb) {
+            const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb64);
+            tb ^= (uint32_t) ((e2 - e) & 1);
+            e = e2;
+            next_edge = E.at(e);
+        }
+        pos = nb;
+        if (more) s.prev |= OOKD_CARRY_DROPPING;
+    }
+
     while (pos < end) {
         const bool at_edge = (next_edge == pos);
         if (s.state == 0 || s.prev != tb) {
@@ -577,7 +630,10 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
             } else if (r < 0) {
                 // device_process gives up on this buffer: resume at the next buffer's first output
                 i64 nb64 = next_buffer_start(a, chunk_lo + (i64) pos - 1, chunk_lo);
-                if (nb64 > end64) nb64 = end64;
+                if (nb64 > end64) {
+                    nb64 = end64;
+                    s.prev |= OOKD_CARRY_DROPPING;
+                }
                 const uint32_t nb = (uint32_t) (nb64 - chunk_lo);
                 if (nb > pos) {
                     if (next_edge < nb) {
@@ -670,7 +726,10 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
             if (lane == 0) sm_emit(o, s, chunk_lo + (i64) pos - 1); else o.n_msgs++;
         } else if (r < 0) {
             i64 nb64 = next_buffer_start(a, chunk_lo + (i64) pos - 1, chunk_lo);
-            if (nb64 > end64) nb64 = end64;
+            if (nb64 > end64) {
+                nb64 = end64;
+                s.prev |= OOKD_CARRY_DROPPING;
+            }
             const uint32_t nb = (uint32_t) (nb64 - chunk_lo);
             if (nb > pos) {
                 if (next_edge < nb) {
@@ -699,28 +758,27 @@ __device__ __forceinline__ void load_table(SmTable &T, const SmTable *src_tab)
     __syncthreads();
 }
 
-__device__ __forceinline__ void chunk_bounds(const SmArgs &a, uint32_t c, i64 &start, i64 &end)
+__device__ __forceinline__ void chunk_bounds_fixed(const SmArgs &a, uint32_t c, i64 &start, i64 &end)
 {
     start = (c == 0) ? a.out_lo : first_output_of_buffer(a, a.first_buffer + (u64) c * a.chunk_buffers);
     end = first_output_of_buffer(a, a.first_buffer + (u64) (c + 1) * a.chunk_buffers);
     if (end > a.out_hi || c == a.n_chunks - 1) end = a.out_hi;
 }
 
-// e_start[c] for every chunk, once per decode: the rounds then start without a binary search.
-// edge count / decision in front of the shard: by value, or from the header the edge pass wrote
-#define OOKD_SM_EDGE_HDR(a)                                                                     \
-    const u64 n_edges = (a).hdr ? (a).hdr->n_edges : (a).n_edges;                               \
-    const uint32_t base_bit = (a).hdr ? (a).hdr->base_bit : (a).base_bit;
-
-__global__ void __launch_bounds__(128) sm_chunk_index_kernel(const SmArgs a)
+// Span of chunk c: between its boundary and the next chunk's (boundaries sit on anchors where sm_anchor_kernel
+// found one).  lo = the chunk's fixed start: a buffer boundary at or before the span, the origin of the
+// 32-bit offsets and of next_buffer_start().
+__device__ __forceinline__ void chunk_bounds(const SmArgs &a, uint32_t c, i64 &start, i64 &end, i64 &lo)
 {
-    OOKD_SM_EDGE_HDR(a)
-    (void) base_bit;
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_chunks) return;
-    i64 start, end;
-    chunk_bounds(a, c, start, end);
-    a.chunk_e[c] = edge_lower_bound(a.edges, n_edges, (u64) start);
+    i64 fixed_end;
+    chunk_bounds_fixed(a, c, lo, fixed_end);
+    if (a.bound_pos) {
+        start = a.bound_pos[c];
+        end = (c + 1 < a.n_chunks) ? a.bound_pos[c + 1] : a.out_hi;
+    } else {
+        start = lo;
+        end = fixed_end;
+    }
 }
 
 __device__ __forceinline__ void carry_reset(SmCarry &s, uint32_t prev)
@@ -733,6 +791,80 @@ __device__ __forceinline__ void carry_reset(SmCarry &s, uint32_t prev)
 // Table speculation: thread (c, j) = chunk c, pair slot j.
 // ---------------------------------------------------------------------------------------
 #define OOKD_TAB_INVALID 0xFFFFFFFFu      // entry.state of a seed that matches no real entry
+
+// edge count / decision in front of the shard: by value, or from the header the edge pass wrote
+#define OOKD_SM_EDGE_HDR(a)                                                                     \
+    const u64 n_edges = (a).hdr ? (a).hdr->n_edges : (a).n_edges;                               \
+    const uint32_t base_bit = (a).hdr ? (a).hdr->base_bit : (a).base_bit;
+
+// Anchors, once per decode.  One warp per chunk: the chunk's first "anchor" is the first rising edge from which
+// a freshly reset machine gets as far as appending a bit, i.e. a plausible message start (the 32 lanes probe 32
+// candidate edges at once).  The true run, whatever it did before, is normally idle when a message starts, so
+// the chunk's boundary is MOVED to its anchor and its table gets the pair "idle machine at the anchor -> ..."
+// as a real entry: when the previous chunk's run indeed arrives idle, the chain links up after round 0.
+// A chunk without an anchor keeps its fixed boundary and is seeded with RESET at its first sample (a guess
+// that usually lands mid-message; later rounds replace it).
+__global__ void __launch_bounds__(32) sm_anchor_kernel(const SmArgs a)
+{
+    OOKD_SM_EDGE_HDR(a)
+    __shared__ SmTable T;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t c = blockIdx.x;
+    if (c >= a.n_chunks) return;
+    load_table(T, a.tab);
+    i64 start, end;
+    chunk_bounds_fixed(a, c, start, end);
+    const u64 e = edge_lower_bound(a.edges, n_edges, (u64) start);
+    const uint32_t tb = base_bit ^ (uint32_t) (e & 1);       // true decision at start-1
+    bool have_anchor = false;
+    u64 anchor_e = 0;
+    if (!(c == 0 && !a.warm)) {
+        const u64 er0 = e + (tb == 1 ? 1 : 0);              // edge e falls when tb == 1; the next one rises
+        for (int batch = 0; batch < 3 && !have_anchor; batch++) {
+            const u64 er = er0 + 2 * (u64) (batch * 32 + lane);
+            const bool cand = er < n_edges && a.edges[er] < (u64) end;
+            bool alive = false;
+            if (cand) {
+                SmCarry p;
+                carry_reset(p, 0);
+                SpanOut po;
+                po.slots = nullptr; po.cap = 0; po.n_msgs = 0; po.overflow = nullptr;
+                alive = sm_run_span<true>(a, n_edges, T, p, (i64) a.edges[er], a.out_hi, er, 0, po, start) != 0;
+            }
+            const uint32_t m_alive = __ballot_sync(0xFFFFFFFFu, alive);
+            const uint32_t m_cand = __ballot_sync(0xFFFFFFFFu, cand);
+            if (m_alive) {
+                have_anchor = true;
+                anchor_e = er0 + 2 * (u64) (batch * 32 + (__ffs(m_alive) - 1));
+            }
+            if (m_cand != 0xFFFFFFFFu) break;                // ran out of rising edges in this chunk
+        }
+    }
+    if (lane != 0) return;
+    i64 bound = start, seed = start;
+    u64 bound_e = e, seed_e = e;
+    uint8_t kind;
+    if (c == 0 && !a.warm) {
+        kind = OOKD_SEED_TRUE;
+    } else if (have_anchor) {
+        seed = (i64) a.edges[anchor_e];
+        seed_e = anchor_e;
+        if (a.warm && c == 1) {
+            kind = OOKD_SEED_ANCHOR;                         // the shard's first output must stay a boundary
+        } else {
+            kind = OOKD_SEED_CANON;
+            bound = seed;
+            bound_e = seed_e;
+        }
+    } else {
+        kind = OOKD_SEED_RESET;
+    }
+    a.bound_pos[c] = bound;
+    a.chunk_e[c] = bound_e;
+    a.seed_pos[c] = seed;
+    a.seed_e[c] = seed_e;
+    a.seed_kind[c] = kind;
+}
 
 // One WARP per (chunk, slot); only lane 0 runs the machine.  The work is a chain of dependent
 // steps, so what matters is latency, not lanes: giving every run its own warp keeps runs from
@@ -747,15 +879,15 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
     const uint32_t gid = blockIdx.x;
     const uint32_t c = gid / KR, j = gid % KR;
     if (c >= a.n_chunks) return;
-    if (a.round >= 2 && a.walk_status[1]) return;            // an earlier walk of this burst already resolved the chain
+    if (a.round >= 1 && a.walk_status[1]) return;            // an earlier walk of this burst already resolved the chain
     if (a.round != 0) {
         // cheap rejection before anything is staged: most (chunk, slot) pairs have nothing new to run
         if (c == 0 || j >= a.cnt_in[c - 1]) return;
     }
     load_table(T, a.tab);
-    i64 start, end;
-    chunk_bounds(a, c, start, end);
-    const bool warp_ok = warp_sm_supported(a.tab) && (end - start) < (1ll << 31);
+    i64 start, end, lo;
+    chunk_bounds(a, c, start, end, lo);
+    const bool warp_ok = warp_sm_supported(a.tab) && (end - lo) < (1ll << 31);
     WarpSm W;
     if (warp_ok) warp_sm_load(W, &T, lane);
 
@@ -766,45 +898,19 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
     i64 pos = start;
     uint32_t slot;
     if (a.round == 0) {
-        // One speculative seed per chunk (chunk 0 of a shard with a known entry runs from that entry):
-        // RESET at the chunk's first "anchor" -- the first rising edge from which a freshly reset machine
-        // gets as far as appending a bit, i.e. a plausible message start -- or, when the chunk has none,
-        // RESET at its first sample.  A guess from the first sample usually lands mid-message, errors,
-        // and can stay out of step with the true run for many messages; the true run, whatever it did
-        // before, is normally idle when a message starts, so from the anchor on the two coincide.
-        // The 32 lanes probe 32 candidate edges at once; lane 0 then does the real run.
-        bool have_anchor = false;
-        u64 anchor_e = 0;
-        if (!(c == 0 && !a.warm)) {
-            const u64 er0 = e + (tb == 1 ? 1 : 0);          // edge e falls when tb == 1; the next one rises
-            for (int batch = 0; batch < 3 && !have_anchor; batch++) {
-                const u64 er = er0 + 2 * (u64) (batch * 32 + lane);
-                const bool cand = er < n_edges && a.edges[er] < (u64) end;
-                bool alive = false;
-                if (cand) {
-                    SmCarry p;
-                    carry_reset(p, 0);
-                    SpanOut po;
-                    po.slots = nullptr; po.cap = 0; po.n_msgs = 0; po.overflow = nullptr;
-                    alive = sm_run_span<true>(a, n_edges, T, p, (i64) a.edges[er], a.out_hi, er, 0, po, start) != 0;
-                }
-                const uint32_t m_alive = __ballot_sync(0xFFFFFFFFu, alive);
-                const uint32_t m_cand = __ballot_sync(0xFFFFFFFFu, cand);
-                if (m_alive) {
-                    have_anchor = true;
-                    anchor_e = er0 + 2 * (u64) (batch * 32 + (__ffs(m_alive) - 1));
-                }
-                if (m_cand != 0xFFFFFFFFu) break;            // ran out of rising edges in this chunk
-            }
-        }
+        // one speculative seed per chunk, prepared by sm_anchor_kernel
         if (!warp_ok && lane != 0) return;
-        if (c == 0 && !a.warm) {
+        const uint32_t kind = a.seed_kind[c];
+        pos = a.seed_pos[c];
+        e = a.seed_e[c];
+        tb = base_bit ^ (uint32_t) (e & 1);
+        if (kind == OOKD_SEED_TRUE) {
             s = a.entry0;
             entry = s;
-        } else if (have_anchor) {
-            pos = (i64) a.edges[anchor_e];
-            e = anchor_e;
-            tb = 0;
+        } else if (kind == OOKD_SEED_CANON) {
+            s = a.canon;
+            entry = s;
+        } else if (kind == OOKD_SEED_ANCHOR) {
             carry_reset(s, 0);
             entry = s;
             entry.state = OOKD_TAB_INVALID;                  // matches no real entry: it is only a source of exits
@@ -844,10 +950,10 @@ __global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
     o.n_msgs = 0;
     o.overflow = a.overflow;
     if (warp_ok) {
-        warp_sm_run_span(a, n_edges, W, s, pos, end, e, tb, o, start, lane);
+        warp_sm_run_span(a, n_edges, W, s, pos, end, e, tb, o, lo, lane);
         if (lane != 0) return;
     } else {
-        sm_run_span<false>(a, n_edges, T, s, pos, end, e, tb, o, start);
+        sm_run_span<false>(a, n_edges, T, s, pos, end, e, tb, o, lo);
     }
 
     a.tab_entry[(u64) c * K + slot] = entry;
@@ -871,8 +977,8 @@ __global__ void __launch_bounds__(32) sm_table_add_entry_kernel(const SmArgs a)
         if (carry_equal(s, a.tab_entry[(u64) c * K + i])) { *a.start_slot = i; return; }
     }
     if (n_here >= K) { atomicExch(a.overflow, 2u); return; }
-    i64 start, end;
-    chunk_bounds(a, c, start, end);
+    i64 start, end, lo;
+    chunk_bounds(a, c, start, end, lo);
     const u64 e = a.chunk_e[c];
     const uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);
     SpanOut o;
@@ -881,7 +987,7 @@ __global__ void __launch_bounds__(32) sm_table_add_entry_kernel(const SmArgs a)
     o.n_msgs = 0;
     o.overflow = a.overflow;
     const SmCarry entry = s;
-    sm_run_span<false>(a, a.n_edges, T, s, start, end, e, tb, o, start);
+    sm_run_span<false>(a, a.n_edges, T, s, start, end, e, tb, o, lo);
     a.tab_entry[(u64) c * K + n_here] = entry;
     a.tab_exit[(u64) c * K + n_here] = s;
     a.tab_nmsg[(u64) c * K + n_here] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
@@ -1015,7 +1121,7 @@ __global__ void __launch_bounds__(32) sm_round_kernel(const SmArgs a)
     if (c >= a.n_chunks) return;
 
     i64 start, end;
-    chunk_bounds(a, c, start, end);
+    chunk_bounds_fixed(a, c, start, end);
     const u64 e = edge_lower_bound(a.edges, a.n_edges, (u64) start);
     const uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);
 
