@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(EDGE_NT) edge_write_kernel(const EdgeArgs a)
 // A tile with more edges than its region holds (1 per 128 decisions) sets the overflow flag; the host then
 // uses the count / scan / write kernels above.
 // ---------------------------------------------------------------------------------------
-constexpr int EDGE1_ROWS = 8;                        // rows per warp; a row = 32 lanes x 2 words (512 B, coalesced)
+#ifndef OOKD_EDGE1_ROWS
+#define OOKD_EDGE1_ROWS 4
+#endif
+constexpr int EDGE1_ROWS = OOKD_EDGE1_ROWS;          // rows per warp; a row = 32 lanes x 2 words (512 B, coalesced)
 constexpr int EDGE1_WPW = EDGE1_ROWS * 64;           // words per warp (4 KiB of decisions)
 constexpr int EDGE1_WPB = (EDGE_NT / 32) * EDGE1_WPW;   // words per tile (32 KiB)
 constexpr int EDGE1_CAP = EDGE1_WPB * 64 / 128;      // edges a tile's region holds (2048)

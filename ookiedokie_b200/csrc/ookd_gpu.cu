@@ -752,7 +752,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
                 }
                 {
                     const u64 warps = (u64) nc * (rounds == 0 ? 1 : TAB_K);
-                    sm_table_round_kernel<<<(unsigned) warps, 32, 0, h->s_compute>>>(a);
+                    sm_table_round_kernel<<<(unsigned) ((warps + SM_ROUND_WARPS - 1) / SM_ROUND_WARPS), 32 * SM_ROUND_WARPS, 0, h->s_compute>>>(a);
                 }
                 h->launches++;
                 CU(h, cudaGetLastError());
@@ -892,7 +892,13 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     x.report_word = (i64) (((u64) (h->report_lo - h->bit_base)) >> 6);
     CU(h, cudaMemsetAsync((char *) h->scalars.p + 24, 0, 232, h->s_compute));      // [24, 256): keeps the refine counters
     {
-        const unsigned ctas = h->n_sm * 2;
+        static int per_sm = 0;
+        if (per_sm == 0) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edge_local_kernel, EDGE_NT, 0) != cudaSuccess || per_sm < 1) {
+                per_sm = 1;
+            }
+        }
+        const unsigned ctas = h->n_sm * (unsigned) per_sm;
         edge_local_kernel<<<eg < ctas ? eg : ctas, EDGE_NT, 0, h->s_compute>>>(x);
         scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>(x.e.block_counts, eg, (u64 *) h->scalars.p);
         edge_flatten_kernel<<<eg, 128, 0, h->s_compute>>>(x);
@@ -939,7 +945,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
             cur ^= 1;
         }
         const u64 warps = (u64) nc * (rounds == 0 ? 1 : TAB_K);
-        sm_table_round_kernel<<<(unsigned) warps, 32, 0, h->s_compute>>>(a);
+        sm_table_round_kernel<<<(unsigned) ((warps + SM_ROUND_WARPS - 1) / SM_ROUND_WARPS), 32 * SM_ROUND_WARPS, 0, h->s_compute>>>(a);
         h->launches++;
         CU(h, cudaGetLastError());
         rounds++;

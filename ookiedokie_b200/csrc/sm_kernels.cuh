@@ -869,22 +869,29 @@ __global__ void __launch_bounds__(32) sm_anchor_kernel(const SmArgs a)
 // One WARP per (chunk, slot); only lane 0 runs the machine.  The work is a chain of dependent
 // steps, so what matters is latency, not lanes: giving every run its own warp keeps runs from
 // serialising each other through divergence (8 runs sharing a warp cost ~8x the latency).
-__global__ void __launch_bounds__(32) sm_table_round_kernel(const SmArgs a)
+constexpr int SM_ROUND_WARPS = 8;                            // (chunk, slot) pairs per CTA
+
+__global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(const SmArgs a)
 {
     OOKD_SM_EDGE_HDR(a)
     __shared__ SmTable T;
+    __shared__ int s_any;
     const uint32_t K = a.tab_k;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t KR = (a.round == 0) ? 1u : K;             // warps (= CTAs) per chunk this round
-    const uint32_t gid = blockIdx.x;
+    const uint32_t KR = (a.round == 0) ? 1u : K;             // warps per chunk this round
+    const uint32_t gid = blockIdx.x * SM_ROUND_WARPS + (threadIdx.x >> 5);
     const uint32_t c = gid / KR, j = gid % KR;
-    if (c >= a.n_chunks) return;
     if (a.round >= 1 && a.walk_status[1]) return;            // an earlier walk of this burst already resolved the chain
-    if (a.round != 0) {
-        // cheap rejection before anything is staged: most (chunk, slot) pairs have nothing new to run
-        if (c == 0 || j >= a.cnt_in[c - 1]) return;
-    }
+    // cheap rejection before anything is staged: most (chunk, slot) pairs have nothing new to run
+    bool live = c < a.n_chunks;
+    if (live && a.round != 0) live = (c != 0) && j < a.cnt_in[c - 1];
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    if (live && lane == 0) s_any = 1;
+    __syncthreads();
+    if (!s_any) return;                                      // (CTA-uniform)
     load_table(T, a.tab);
+    if (!live) return;
     i64 start, end, lo;
     chunk_bounds(a, c, start, end, lo);
     const bool warp_ok = warp_sm_supported(a.tab) && (end - lo) < (1ll << 31);
@@ -1014,15 +1021,17 @@ __global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
     a.link[(u64) c * K + i] = l;
 }
 
-// One CTA resolves the chain from chunk 0 / slot 0.  Chasing 1 link per step would serialise
-// n_chunks shared-memory latencies, so links are first composed over segments of SEG chunks (one
-// thread per segment, all K start slots at once), the short chain over segments is walked by one
-// thread, and every thread then replays its own segment from its now-known entry slot.
+// One CTA resolves the chain from chunk first_chunk / slot *start_slot.  Chasing 1 link per step through global
+// memory would serialise n_chunks L2 latencies, so the link rows of a block of 4096 chunks are first staged in
+// shared memory (one coalesced pass), composed over segments of SEG chunks (one thread per segment, all K start
+// slots at once), the short chain over segments is walked by one thread, and every segment thread then replays
+// its own segment from its now-known entry slot.
 __global__ void __launch_bounds__(1024) sm_walk_kernel(const SmArgs a)
 {
-    constexpr uint32_t SEG = 32;
-    __shared__ uint8_t s_map[1024 * 8];                      // composed map of each segment
-    __shared__ uint8_t s_in[1024];                           // entry slot of each segment (0xFF = unreachable)
+    constexpr uint32_t SEG = 32, BLK = 4096, NSEG = BLK / SEG;
+    __shared__ uint2 s_link[BLK];                            // link rows of the block (8 slots x 1 byte)
+    __shared__ uint8_t s_map[NSEG * 8];                      // composed map of each segment
+    __shared__ uint8_t s_in[NSEG];                           // entry slot of each segment (0xFF = unreachable)
     __shared__ uint32_t s_carry, s_max;
     const uint32_t K = a.tab_k;                              // == 8 (one 8-byte link row per chunk)
     if (a.walk_status[1]) return;                            // resolved by an earlier walk of this burst
@@ -1030,18 +1039,22 @@ __global__ void __launch_bounds__(1024) sm_walk_kernel(const SmArgs a)
     __syncthreads();
     uint32_t done = 0;
 
-    for (uint32_t base = a.first_chunk; base < a.n_chunks; base += 1024 * SEG) {
-        const uint32_t n_here = min(1024u * SEG, a.n_chunks - base);
+    for (uint32_t base = a.first_chunk; base < a.n_chunks; base += BLK) {
+        const uint32_t n_here = min(BLK, a.n_chunks - base);
         const uint32_t n_seg = (n_here + SEG - 1) / SEG;
+        for (uint32_t i = threadIdx.x; i < n_here; i += blockDim.x) {
+            s_link[i] = *(const uint2 *) (a.link + (u64) (base + i) * 8);
+        }
+        __syncthreads();
         const uint32_t sg = threadIdx.x;
-        const uint32_t c_lo = base + sg * SEG, c_hi = min(c_lo + SEG, base + n_here);
-        // compose: m[k] = slot of chunk c_hi reached when chunk c_lo is entered in slot k
+        const uint32_t l_lo = sg * SEG, l_hi = min(l_lo + SEG, n_here);       // block-local chunk range of the segment
+        // compose: m[k] = slot of chunk l_hi reached when chunk l_lo is entered in slot k
         if (sg < n_seg) {
             uint32_t m[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) m[k] = (uint32_t) k;
-            for (uint32_t c = c_lo; c < c_hi; c++) {
-                const uint2 lw = *(const uint2 *) (a.link + (u64) c * 8);
+            for (uint32_t l = l_lo; l < l_hi; l++) {
+                const uint2 lw = s_link[l];
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const uint32_t cur = m[k];
@@ -1068,11 +1081,14 @@ __global__ void __launch_bounds__(1024) sm_walk_kernel(const SmArgs a)
         // replay the own segment to record the chosen slot of every chunk
         if (sg < n_seg && s_in[sg] != 0xFF) {
             uint32_t cur = s_in[sg], my_done = 0;
-            for (uint32_t c = c_lo; c < c_hi; c++) {
+            for (uint32_t l = l_lo; l < l_hi; l++) {
+                const uint32_t c = base + l;
                 a.chosen[c] = (uint8_t) cur;
                 my_done = c + 1;
                 if (c + 1 == a.n_chunks) break;
-                const uint32_t nx = a.link[(u64) c * 8 + cur];
+                const uint2 lw = s_link[l];
+                const uint32_t word = (cur < 4) ? lw.x : lw.y;
+                const uint32_t nx = (word >> (8 * (cur & 3))) & 0xFFu;
                 if (nx == 0xFF) break;
                 cur = nx;
             }
