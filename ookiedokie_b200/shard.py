@@ -15,6 +15,8 @@ The fixed point equals the sequential decode (each shard is a deterministic func
 `runner` is anything with decode(entry) / resolve(entry) -> (result, exit_carry_tuple), so the
 protocol itself is testable on CPU with gloo and a stand-in runner.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -63,6 +65,98 @@ _stitch_cache = {}
 _stitch_cap = {}
 
 
+class _ShmExchange:
+    """All-gather of small per-rank byte blocks through a shared-memory file (ranks of ONE host): the carry
+    records and message lists are a few hundred KB at most and every rank already has them in host memory,
+    so a host-mediated exchange beats staging them through the GPUs and a collective (~20 us against ~300 us
+    per step).  Slot layout per (parity, rank): u64 sequence number | u64 length | payload.  A rank publishes
+    step s by writing the payload and then the sequence number; readers spin on the sequence numbers.  Two
+    parities: nobody can be two steps ahead of a rank that is still reading, because publishing step s+1
+    happens after reading step s."""
+
+    HDR = 64
+
+    def __init__(self, rank, world, slot_bytes):
+        import mmap
+        import uuid
+        self.rank, self.world, self.slot = rank, world, self.HDR + slot_bytes
+        name = [f"/dev/shm/ookd_stitch_{os.getpid()}_{uuid.uuid4().hex}" if rank == 0 else None]
+        dist.broadcast_object_list(name, src=0)
+        self.path = name[0]
+        size = 2 * world * self.slot
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(size)
+        dist.barrier()
+        self.f = open(self.path, "r+b")
+        self.mm = mmap.mmap(self.f.fileno(), size)
+        self.buf = np.frombuffer(self.mm, dtype=np.uint8)
+        self.seq = 0
+        dist.barrier()
+        if rank == 0:
+            os.unlink(self.path)          # the mapping stays valid; nothing is left behind on exit
+
+    def _slot(self, parity, r):
+        o = (parity * self.world + r) * self.slot
+        return self.buf[o:o + self.slot]
+
+    def exchange(self, payload, timeout_s=120.0):
+        """payload: uint8 array (<= slot capacity).  -> list of uint8 arrays, one per rank (copies)."""
+        import time
+        self.seq += 1
+        par = self.seq & 1
+        mine = self._slot(par, self.rank)
+        n = payload.size
+        mine[self.HDR:self.HDR + n] = payload
+        mine[8:16].view(np.uint64)[0] = n
+        mine[0:8].view(np.uint64)[0] = self.seq          # published (x86 stores are not reordered)
+        out = []
+        t0 = None
+        for r in range(self.world):
+            sl = self._slot(par, r)
+            seq = sl[0:8].view(np.uint64)
+            spins = 0
+            while int(seq[0]) != self.seq:
+                spins += 1
+                if spins > 2000:
+                    if t0 is None:
+                        t0 = time.perf_counter()
+                    elif time.perf_counter() - t0 > timeout_s:
+                        raise RuntimeError(f"shared-memory stitch: rank {r} did not publish step {self.seq}")
+                    time.sleep(0)
+            ln = int(sl[8:16].view(np.uint64)[0])
+            out.append(sl[self.HDR:self.HDR + ln].copy())
+        return out
+
+
+_shm = {}
+SHM_SLOT_BYTES = 112 + 16384 * 56
+
+
+def _same_host(world):
+    names = [None] * world
+    import socket
+    dist.all_gather_object(names, socket.gethostname())
+    return all(n == names[0] for n in names)
+
+
+def _shm_exchange(rank, world):
+    """The shared-memory exchange of this process group, or None when the ranks span hosts / it cannot be set up."""
+    key = world
+    if key not in _shm:
+        ex = None
+        try:
+            ok = os.path.isdir("/dev/shm") and _same_host(world)
+            flags = [None] * world
+            dist.all_gather_object(flags, bool(ok))
+            if all(flags):
+                ex = _ShmExchange(rank, world, SHM_SLOT_BYTES)
+        except Exception:
+            ex = None
+        _shm[key] = ex
+    return _shm[key]
+
+
 def stitch_and_gather(runner, rank, world, msg_cap=None):
     """stitch() + gather_messages_raw() with ONE collective in the common case: every rank ships its
     carry record together with its (padded) message block; if the records are consistent the job is done.
@@ -76,6 +170,22 @@ def stitch_and_gather(runner, rank, world, msg_cap=None):
     dev = _dev()
     isz = MSG_DTYPE.itemsize
     rec = res["msgs_raw"]
+    ex = _shm_exchange(rank, world) if msg_cap is None else None
+    if ex is not None and REC_BYTES + len(rec) * isz <= SHM_SLOT_BYTES:
+        # ranks of one host: records and message lists go through shared memory, no device round trip
+        hdr = carry_to_bytes(exit_c) + carry_to_bytes(entry_used) + np.array([0, len(rec), 0, 0], dtype=np.uint32).tobytes()
+        payload = np.concatenate([np.frombuffer(hdr, dtype=np.uint8), rec.view(np.uint8).reshape(-1)])
+        parts = ex.exchange(payload)
+        ok = all(parts[r][48:96].tobytes() == parts[r - 1][:48].tobytes() for r in range(1, world))
+        if ok:
+            msgs = None
+            if rank == 0:
+                msgs = np.concatenate([p[REC_BYTES:] for p in parts]).view(MSG_DTYPE)     # (bytes first: concatenating
+                                                                                          # structured arrays is slow)
+            return res, exit_c, 1, msgs
+        res, exit_c, rounds = _stitch_rounds(runner, rank, world, res, exit_c, entry_used, dev)
+        msgs = gather_messages_raw(res["msgs_raw"], rank, world, res.get("_counts"))
+        return res, exit_c, rounds + 1, msgs
     cap = msg_cap if msg_cap is not None else _stitch_cap.get(world, 1024)
     key = (world, cap, dev.type, dev.index)
     sb = _stitch_cache.get(key)
@@ -102,8 +212,7 @@ def stitch_and_gather(runner, rank, world, msg_cap=None):
     if ok and max(counts) <= cap:
         msgs = None
         if rank == 0:
-            msgs = np.concatenate([g[r, REC_BYTES:REC_BYTES + counts[r] * isz].copy().view(MSG_DTYPE)
-                                   for r in range(world)])
+            msgs = np.concatenate([g[r, REC_BYTES:REC_BYTES + counts[r] * isz] for r in range(world)]).view(MSG_DTYPE)
         return res, exit_c, 1, msgs
     if not ok:
         # inconsistent entries: the round protocol re-runs the state-machine stage of the shards that guessed wrong

@@ -71,7 +71,7 @@ def main():
         # the single-collective form bench.py uses; twice, so that the adaptive block size is exercised, and once
         # with a block too small for the message lists (falls back to the separate gather)
         from ookiedokie_b200.binding import msgs_to_tuples
-        for cap in (None, None, 1):
+        for cap in (None, None, 1, 4096):
             res, exit_c, rounds, raw = S.stitch_and_gather(runner, rank, world, msg_cap=cap)
             msgs = msgs_to_tuples(raw, nbytes) if rank == 0 else None
             if rank == 0:
