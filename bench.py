@@ -254,6 +254,13 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--chunk-buffers", type=int, default=0)
+    ap.add_argument("--share", action="store_true", help="OOKD_FLAG_SHARE_SMS on the handles (three screening CTAs per SM)")
+    ap.add_argument("--pipeline", type=int, default=1,
+                    help="decodes in flight per GPU in the MAIN timed region (handles used round robin); the default 1 "
+                         "= one step at a time, which is what the roofline / ncu launch list describe")
+    ap.add_argument("--e2e-depth", type=int, default=1, help="decodes in flight in the end-to-end (host input) region")
+    ap.add_argument("--pipelined-depth", type=int, default=2,
+                    help="depth of the extra 'pipelined' measurement (consecutive windows overlapped); 0 = skip it")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -285,8 +292,13 @@ def main():
 
     fir = H.Fir(FILTER_NAME)
     dev = H.Device(DEVICE_NAME, FS // fir.total_decimation)
-    gpu = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
-                flags=args.flags, sm_chunk_buffers=args.chunk_buffers, sm_warmup=1 if world > 1 else 0)
+    depth = max(1, args.pipeline)
+    n_handles = max(depth, args.pipelined_depth, args.e2e_depth, 1)
+    flags = args.flags | (B.FLAG_SHARE_SMS if args.share else 0)
+    gpus = [B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
+                  flags=flags, sm_chunk_buffers=args.chunk_buffers, sm_warmup=1 if world > 1 else 0)
+            for _ in range(n_handles)]
+    gpu = gpus[0]
     n = args.samples
     halo = gpu.halo
     first = rank * n
@@ -301,36 +313,66 @@ def main():
             device_ptr=d_iq.data_ptr())
     torch.cuda.synchronize()
 
-    gpu.want_list = False           # keep messages as one structured array; no per-message Python work
+    for g in gpus:
+        g.want_list = False         # keep messages as one structured array; no per-message Python work
 
-    def one_step(iq_arg):
-        runner = S.GpuShardRunner(gpu, iq_arg, first, n, last)
-        res, exit_c, rounds, msgs = S.stitch_and_gather(runner, rank, world)
-        return res, msgs, runner
+    def run_steps(iq_arg, n_steps, depth=depth):
+        """n_steps decodes of the shard, `depth` in flight: step i+1 is enqueued (on the next handle) before step i
+        is waited for, as consecutive windows of a long capture are.  Every step is a complete decode incl. the
+        cross-rank stitch.  -> (last result, last messages, summed launches / fir / screen / kernel ms / syncs)."""
+        pending, acc = [], [0, 0.0, 0.0, 0.0, 0]
+        out = [None, None]
+
+        def finish(runner):
+            res, exit_c, rounds, msgs = S.stitch_and_gather(runner, rank, world)
+            acc[0] += runner.launches
+            acc[1] += runner.fir_ms
+            acc[2] += runner.screen_ms
+            acc[3] += runner.kernel_ms
+            acc[4] += runner.host_syncs
+            out[0], out[1] = res, msgs
+
+        for i in range(n_steps):
+            runner = S.GpuShardRunner(gpus[i % depth], iq_arg, first, n, last)
+            runner.begin()
+            pending.append(runner)
+            if len(pending) == depth:
+                finish(pending.pop(0))
+        while pending:
+            finish(pending.pop(0))
+        return out[0], out[1], acc
 
     dev_arg = (d_iq.data_ptr(), halo_avail + n)
     sampler = ClockSampler(local_rank)
     sampler.start()                 # started before the warm-up so that it is sampling when the timed region begins
-    for _ in range(args.warmup):
-        one_step(dev_arg)
+    run_steps(dev_arg, max(args.warmup, depth))
     barrier()
     t0 = time.perf_counter()
-    launches = 0
-    fir_ms = 0.0
-    screen_ms = 0.0
-    kernel_ms = 0.0
-    host_syncs = 0
-    for _ in range(args.steps):
-        res, msgs, runner = one_step(dev_arg)
-        launches += runner.launches
-        fir_ms += runner.fir_ms
-        screen_ms += runner.screen_ms
-        kernel_ms += runner.kernel_ms
-        host_syncs += runner.host_syncs
+    res, msgs, (launches, fir_ms, screen_ms, kernel_ms, host_syncs) = run_steps(dev_arg, args.steps)
     barrier()
     t1 = time.perf_counter()
     dt = t1 - t0
     clocks = sampler.stop(t0, t1)
+
+    # ---- extra: the same steps with consecutive decodes overlapped (two handles), as the windows of a long capture
+    #      are processed; every step is still a complete decode + stitch inside the timed region ----
+    pipelined = None
+    if args.pipelined_depth > 1:
+        pd = args.pipelined_depth
+        run_steps(dev_arg, max(args.warmup, pd), depth=pd)
+        barrier()
+        tp0 = time.perf_counter()
+        res_p, msgs_p, _ = run_steps(dev_arg, args.steps, depth=pd)
+        barrier()
+        dtp = time.perf_counter() - tp0
+        tpt = torch.tensor([dtp], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tpt, op=dist.ReduceOp.MAX)
+        dtp = float(tpt.item())
+        if rank == 0 and msgs is not None and msgs_p is not None:
+            assert np.array_equal(msgs_p, msgs), "pipelined decode differs from the one-at-a-time decode"
+        pipelined = {"depth": pd, "value": world * n / (dtp / args.steps) / 1e6, "unit": UNIT,
+                     "ms_per_step": 1e3 * dtp / args.steps, "steps": args.steps}
     t = torch.tensor([dt, fir_ms, kernel_ms, screen_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -352,11 +394,11 @@ def main():
         assert rc == 0
         import ctypes
         h_iq = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_int16)), shape=((halo_avail + n) * 2,))
-        one_step(h_iq)
+        ed = max(1, args.e2e_depth)
+        run_steps(h_iq, ed, depth=ed)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            res_e, msgs_e, _ = one_step(h_iq)
+        res_e, msgs_e, _ = run_steps(h_iq, args.e2e_steps, depth=ed)
         barrier()
         dte = time.perf_counter() - t0
         te = torch.tensor([dte], dtype=torch.float64, device="cuda")
@@ -365,7 +407,7 @@ def main():
         dte = float(te.item())
         d2h = len(res_e["msgs_raw"]) * 56 + 3 * 256 + 48
         e2e = {"value": world * n / (dte / args.e2e_steps) / 1e6, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps}
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "pipeline_depth": ed}
         if rank == 0 and msgs is not None and msgs_e is not None:
             assert np.array_equal(msgs_e, msgs), "host-input decode differs from device-input decode"
         cpu_prefix = h_iq[halo_avail * 2: (halo_avail + min(n, args.cpu_samples)) * 2].copy() if rank == 0 else None
@@ -403,10 +445,11 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(n), "samples_per_gpu": n, "device": DEVICE_NAME, "filter": FILTER_NAME,
                        "parallelism": f"time-shards x{world}" if world > 1 else "single shard",
+                       "pipeline_depth": depth,
                        "l2": "input shard (4 B/sample) larger than L2; no flush needed",
                        "messages_decoded": n_msgs, "messages_transmitted_upper_bound": n_tx_msgs,
                        "edges_last_rank": n_edges, "sm_rounds": sm_rounds},
-            "device_ms_per_step": kernel_ms_max / args.steps,
+            "step_latency_ms": kernel_ms_max / args.steps,      # CUDA-event span of one decode (overlaps its neighbours when pipelined)
             "fir_stage_ms_per_step": fir_ms_per_launch,
             "host_syncs_per_step": host_syncs / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -417,6 +460,8 @@ def main():
                          "kernel_ms_per_launch": screen_ms_per_launch},
             "clocks": clocks, "gpu_launches": launches,
         }
+        if pipelined:
+            line["pipelined"] = pipelined
         if e2e:
             line["e2e"] = e2e
         if cpu:

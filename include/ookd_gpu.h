@@ -170,6 +170,9 @@ struct ookd_gpu_config {
                                                 TMA-staged default                                */
 #define OOKD_FLAG_SYNC_TAIL      16u         /* edges / state machine with a host synchronisation between the
                                                 stages instead of the single-synchronisation default */
+#define OOKD_FLAG_SHARE_SMS      32u         /* pipelined use (several handles with a decode in flight on one
+                                                device): the persistent screening kernel takes three quarters of
+                                                each SM so that the other decode's tail kernels can run beside it */
 #define OOKD_FLAG_NO_SCREEN      2u          /* disable the reduced-precision screen (exact MACs
                                                 for every sample)                                */
 

@@ -23,6 +23,7 @@ FLAG_NO_SCREEN = 2
 FLAG_TILE_PER_CTA_SCREEN = 4
 FLAG_NO_TMA = 8
 FLAG_SYNC_TAIL = 16
+FLAG_SHARE_SMS = 32
 
 # every symbol include/ookd_gpu.h declares
 EXPORTS = [
@@ -372,6 +373,26 @@ class Gpu:
         self._check(lib().ookd_gpu_decode_shard(self.h, p, is_dev, first_sample, n_samples, int(last),
                                                 C.byref(en) if en is not None else None, C.byref(ex),
                                                 C.byref(res)), "ookd_gpu_decode_shard")
+        return self._result(res), ex.astuple()
+
+    def decode_begin(self, iq, first_sample, n_samples, last, entry=None):
+        """First half of decode_shard: enqueue every stage and return without waiting (see ookd_gpu_decode_begin)."""
+        if isinstance(iq, tuple):
+            p, is_dev, keep = C.c_void_p(int(iq[0])), 1, None
+        else:
+            keep = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+            p, is_dev = C.c_void_p(keep.ctypes.data), 0
+        self._keep = keep
+        en = SmCarry.fromtuple(entry) if entry is not None else None
+        self._check(lib().ookd_gpu_decode_begin(self.h, p, is_dev, first_sample, n_samples, int(last),
+                                                C.byref(en) if en is not None else None), "ookd_gpu_decode_begin")
+
+    def decode_end(self):
+        """Second half: wait, validate, fetch the results.  -> (result, exit carry tuple)."""
+        res = GpuResult()
+        ex = SmCarry()
+        self._check(lib().ookd_gpu_decode_end(self.h, C.byref(ex), C.byref(res)), "ookd_gpu_decode_end")
+        self._keep = None
         return self._result(res), ex.astuple()
 
     def resolve(self, entry):

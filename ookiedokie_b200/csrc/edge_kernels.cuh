@@ -282,31 +282,41 @@ __global__ void __launch_bounds__(128) edge_flatten_kernel(const Edge1Args x)
     }
 }
 
-// Single-CTA exclusive scan of n uint32 values in place; total to *total (64-bit).
-__global__ void __launch_bounds__(1024) scan_u32_kernel(uint32_t *v, uint32_t n, u64 *total)
+// Single-CTA exclusive scan of n uint32 values in place; total to *total (64-bit).  256 threads: small enough to
+// run next to another decode's persistent screening kernel (see OOKD_FLAG_SHARE_SMS).
+constexpr int SCAN_NT = 256;
+
+__global__ void __launch_bounds__(SCAN_NT) scan_u32_kernel(uint32_t *v, uint32_t n, u64 *total)
 {
-    __shared__ u64 s_part[1024];
-    const uint32_t per = (n + 1023) / 1024;
+    __shared__ u64 s_warp[SCAN_NT / 32];
+    const uint32_t per = (n + SCAN_NT - 1) / SCAN_NT;
     const uint32_t lo = threadIdx.x * per;
     const uint32_t hi = min(n, lo + per);
     u64 sum = 0;
     for (uint32_t i = lo; i < hi; i++) sum += v[i];
-    s_part[threadIdx.x] = sum;
-    __syncthreads();
-    // Hillis-Steele over 1024 partials
-    for (int d = 1; d < 1024; d <<= 1) {
-        u64 add = (threadIdx.x >= d) ? s_part[threadIdx.x - d] : 0;
-        __syncthreads();
-        s_part[threadIdx.x] += add;
-        __syncthreads();
+    // inclusive scan of the per-thread sums: warp shuffles, then the 8 warp totals
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t) d) inc += up;
     }
-    u64 run = s_part[threadIdx.x] - sum;            // exclusive prefix of this thread's segment
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    u64 base = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_NT / 32; w++) {
+        if (w < (int) warp) base += s_warp[w];
+        all += s_warp[w];
+    }
+    u64 run = base + inc - sum;                     // exclusive prefix of this thread's segment
     for (uint32_t i = lo; i < hi; i++) {
         const uint32_t x = v[i];
         v[i] = (uint32_t) run;                      // per-shard edge counts stay below 2^32
         run += x;
     }
-    if (threadIdx.x == 1023) *total = s_part[1023];
+    if (threadIdx.x == 0) *total = all;
 }
 
 }  // namespace ookd

@@ -268,6 +268,22 @@ encode_tiled_fn tensor_map_encoder()
     return fn;
 }
 
+// OOKD_FLAG_SHARE_SMS: the persistent screening kernels of different handles on one device must not overlap
+// EACH OTHER (two of them would fight over the same three quarters of every SM); what should overlap is one
+// decode's screening kernel with the other decode's tail.  A per-device event chains them: a screening launch
+// waits for the previous screening launch (of any handle of this process) on that device.
+cudaEvent_t *screen_token(int device)
+{
+    static cudaEvent_t tokens[64];
+    static bool made[64];
+    if (device < 0 || device >= 64) return nullptr;
+    if (!made[device]) {
+        if (cudaEventCreateWithFlags(&tokens[device], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        made[device] = true;
+    }
+    return &tokens[device];
+}
+
 TiledArgs tiled_args(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
 {
     TiledArgs a{};
@@ -332,9 +348,16 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
                 } else {
                     ta.fast_lo = ta.fast_hi = 0;
                 }
-                const u64 ctas = (u64) h->n_sm * OOKD_STMA_MINB;
+                // OOKD_FLAG_SHARE_SMS: three CTAs per SM instead of four, so that a quarter of every SM's registers
+                // and shared memory stays free for the latency-bound tail kernels of ANOTHER handle's decode
+                const bool share = (h->flags & OOKD_FLAG_SHARE_SMS) != 0;
+                const u64 ctas = (u64) h->n_sm * (share ? OOKD_STMA_MINB - 1 : OOKD_STMA_MINB);
+                static const bool use_token = getenv("OOKD_SCREEN_TOKEN") != nullptr;
+                cudaEvent_t *tok = (share && use_token) ? screen_token(h->device) : nullptr;
+                if (tok) CU(h, cudaStreamWaitEvent(h->s_compute, *tok, 0));
                 fir1_screen_tma_kernel<32><<<(unsigned) (stiles < ctas ? stiles : ctas), STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(
                     tmap, ta, sp);
+                if (tok) CU(h, cudaEventRecord(*tok, h->s_compute));
             } else if (h->persist) {
                 const u64 ctas = (u64) h->n_sm * OOKD_SCREEN_PERSIST_MINB;
                 fir1_screen_persist_kernel<32><<<(unsigned) (stiles < ctas ? stiles : ctas), 256, 0, h->s_compute>>>(sa, sp);
@@ -582,7 +605,7 @@ int run_state_machine_jacobi(ookd_gpu *h, const SmCarry &entry0, ookd_sm_carry *
         }
         CU(h, cudaMemcpyAsync(h->slot_off.p, h->slot_count.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice,
                               h->s_compute));
-        scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
+        scan_u32_kernel<<<1, SCAN_NT, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
         h->launches++;
         CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
         CU(h, cudaStreamSynchronize(h->s_compute));
@@ -625,7 +648,7 @@ int extract_edges(ookd_gpu *h, u64 n_bits, ookd_gpu_result *res)
     ea.block_counts = (uint32_t *) h->block_counts.p;
     h->stat_dense_tiles = 0;
     edge_count_kernel<<<eg, EDGE_NT, 0, h->s_compute>>>(ea);
-    scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>(ea.block_counts, eg, (u64 *) h->scalars.p);
+    scan_u32_kernel<<<1, SCAN_NT, 0, h->s_compute>>>(ea.block_counts, eg, (u64 *) h->scalars.p);
     h->launches += 2;
     CU(h, cudaGetLastError());
     // scalars[0] = total edges; also the first word of decisions (base_bit), the word holding the shard's
@@ -763,13 +786,13 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
                     // chunk-long latency
                     a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
                     sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
-                    sm_walk_kernel<<<1, 1024, 0, h->s_compute>>>(a);
+                    sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a);
                     h->launches += 2;
                 }
             }
             a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
             sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
-            sm_walk_kernel<<<1, 1024, 0, h->s_compute>>>(a);
+            sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a);
             h->launches += 2;
             CU(h, cudaGetLastError());
             CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
@@ -800,7 +823,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
     a.chosen = (uint8_t *) h->tab_chosen.p;
     a.msg_counts = (uint32_t *) h->slot_count.p;
     CU(h, cudaMemcpyAsync(h->slot_off.p, h->slot_count.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice, h->s_compute));
-    scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
+    scan_u32_kernel<<<1, SCAN_NT, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
     h->launches++;
     CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
     CU(h, cudaStreamSynchronize(h->s_compute));
@@ -900,7 +923,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
         }
         const unsigned ctas = h->n_sm * (unsigned) per_sm;
         edge_local_kernel<<<eg < ctas ? eg : ctas, EDGE_NT, 0, h->s_compute>>>(x);
-        scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>(x.e.block_counts, eg, (u64 *) h->scalars.p);
+        scan_u32_kernel<<<1, SCAN_NT, 0, h->s_compute>>>(x.e.block_counts, eg, (u64 *) h->scalars.p);
         edge_flatten_kernel<<<eg, 128, 0, h->s_compute>>>(x);
         h->launches += 3;
         CU(h, cudaGetLastError());
@@ -952,13 +975,13 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
         {
             a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
             sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
-            sm_walk_kernel<<<1, 1024, 0, h->s_compute>>>(a);
+            sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a);
             h->launches += 2;
         }
     }
     // ---- ordered gather of the chosen pairs' messages ----
     CU(h, cudaMemcpyAsync(h->slot_off.p, h->slot_count.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice, h->s_compute));
-    scan_u32_kernel<<<1, 1024, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
+    scan_u32_kernel<<<1, SCAN_NT, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
     sm_gather_table_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a, (const uint32_t *) h->slot_off.p,
                                                                        (SmMsg *) h->msgs_dev.p, msg_cap);
     h->launches += 2;

@@ -869,7 +869,7 @@ __global__ void __launch_bounds__(32) sm_anchor_kernel(const SmArgs a)
 // One WARP per (chunk, slot); only lane 0 runs the machine.  The work is a chain of dependent
 // steps, so what matters is latency, not lanes: giving every run its own warp keeps runs from
 // serialising each other through divergence (8 runs sharing a warp cost ~8x the latency).
-constexpr int SM_ROUND_WARPS = 8;                            // (chunk, slot) pairs per CTA
+constexpr int SM_ROUND_WARPS = 4;                            // (chunk, slot) pairs per CTA
 
 __global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(const SmArgs a)
 {
@@ -1026,7 +1026,9 @@ __global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
 // shared memory (one coalesced pass), composed over segments of SEG chunks (one thread per segment, all K start
 // slots at once), the short chain over segments is walked by one thread, and every segment thread then replays
 // its own segment from its now-known entry slot.
-__global__ void __launch_bounds__(1024) sm_walk_kernel(const SmArgs a)
+constexpr int SM_WALK_NT = 256;                             // small enough to run next to a persistent screening kernel
+
+__global__ void __launch_bounds__(SM_WALK_NT) sm_walk_kernel(const SmArgs a)
 {
     constexpr uint32_t SEG = 32, BLK = 4096, NSEG = BLK / SEG;
     __shared__ uint2 s_link[BLK];                            // link rows of the block (8 slots x 1 byte)

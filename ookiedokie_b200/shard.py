@@ -321,8 +321,17 @@ class GpuShardRunner:
         self.host_syncs += res.get("host_syncs", 0)
         self.kernel_ms += res["kernel_ms"]
 
+    def begin(self, entry=None):
+        """Enqueue the decode now; the next decode(entry) call only waits for it."""
+        self.gpu.decode_begin(self.iq, self.first, self.n, self.last, entry)
+        self._begun = True
+
     def decode(self, entry):
-        res, ex = self.gpu.decode_shard(self.iq, self.first, self.n, self.last, entry)
+        if getattr(self, "_begun", False):
+            self._begun = False
+            res, ex = self.gpu.decode_end()
+        else:
+            res, ex = self.gpu.decode_shard(self.iq, self.first, self.n, self.last, entry)
         self._acc(res)
         return res, ex
 
