@@ -857,6 +857,32 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
 // that did not fit or resolve (edge list / work list / message slots too small, chain not resolved after
 // three rounds) sets *done = false and the caller repeats the tail on the synchronous path, which handles
 // every such case.
+// Rounds enqueued blindly behind the edge pass.  Round 0 resolves the chain when every chunk is entered idle at its
+// anchor; each further round repairs one more consecutive chunk entered in another state.  A round that is not
+// needed costs ~9 us (three kernels that return at once), a missing one costs a synchronisation.
+constexpr uint32_t FAST_BURST_ROUNDS = 4;
+
+// arguments of the state-machine kernels on the single-synchronisation path (edge count / base bit from the
+// device-side header)
+SmArgs fast_sm_args(ookd_gpu *h, const SmCarry &entry0)
+{
+    SmArgs a = base_sm_args(h, entry0);
+    a.hdr = (const SmDevHdr *) ((char *) h->scalars.p + 256);
+    a.start_slot = (uint32_t *) ((char *) h->scalars.p + 48);
+    a.first_chunk = 0;
+    a.final_entry = (SmCarry *) h->final_entry.p;
+    a.tab_k = TAB_K;
+    a.tab_entry = (SmCarry *) h->tab_entry.p;
+    a.tab_exit = (SmCarry *) h->tab_exit.p;
+    a.tab_nmsg = (uint32_t *) h->tab_nmsg.p;
+    a.link = (uint8_t *) h->tab_link.p;
+    a.chosen = (uint8_t *) h->tab_chosen.p;
+    a.walk_status = (uint32_t *) ((char *) h->scalars.p + 40);
+    a.msg_counts = (uint32_t *) h->slot_count.p;
+    a.final_exit = (SmCarry *) ((char *) h->scalars.p + 192);
+    return a;
+}
+
 int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
 {
     int rc;
@@ -935,26 +961,13 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     h->entry_used = entry0;
     h->n_edges = 0;
     h->base_bit = 0;
-    SmArgs a = base_sm_args(h, entry0);
-    a.hdr = (const SmDevHdr *) ((char *) h->scalars.p + 256);
-    a.start_slot = (uint32_t *) ((char *) h->scalars.p + 48);
-    a.first_chunk = 0;
-    a.final_entry = (SmCarry *) h->final_entry.p;
-    a.tab_k = TAB_K;
-    a.tab_entry = (SmCarry *) h->tab_entry.p;
-    a.tab_exit = (SmCarry *) h->tab_exit.p;
-    a.tab_nmsg = (uint32_t *) h->tab_nmsg.p;
-    a.link = (uint8_t *) h->tab_link.p;
-    a.chosen = (uint8_t *) h->tab_chosen.p;
-    a.walk_status = (uint32_t *) ((char *) h->scalars.p + 40);
-    a.msg_counts = (uint32_t *) h->slot_count.p;
-    a.final_exit = (SmCarry *) ((char *) h->scalars.p + 192);
+    SmArgs a = fast_sm_args(h, entry0);
     sm_anchor_kernel<<<nc, 32, 0, h->s_compute>>>(a);
     h->launches++;
     CU(h, cudaMemsetAsync(h->tab_cnt[0].p, 0, sizeof(uint32_t) * nc, h->s_compute));
     int cur = 0;
     uint32_t rounds = 0;
-    for (uint32_t r = 0; r < 3; r++) {
+    for (uint32_t r = 0; r < FAST_BURST_ROUNDS; r++) {
         a.round = rounds;
         a.counter_idx = rounds & 31;
         if (rounds == 0) {
@@ -994,6 +1007,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
         CU(h, cudaMemcpyAsync((char *) h->h_scalars + 288, h->final_entry.p, sizeof(SmCarry), cudaMemcpyDeviceToHost, h->s_compute));
     }
     CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
+    h->pend.e0 = entry0;                                   // (count canonicalised above)
     h->pend.edge_cap = x.cap;
     h->pend.msg_cap = msg_cap;
     h->pend.n_copy = n_copy;
@@ -1007,8 +1021,8 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
     *done = false;
     const uint32_t nc = h->n_chunks;
     const u64 msg_cap = h->pend.msg_cap, n_copy = h->pend.n_copy;
-    const uint32_t rounds = h->pend.rounds;
-    const int cur = h->pend.cur;
+    uint32_t rounds = h->pend.rounds;
+    int cur = h->pend.cur;
     CU(h, cudaStreamSynchronize(h->s_compute));
     h->stat_syncs++;
 
@@ -1016,18 +1030,61 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
     const char *hs = (const char *) h->h_scalars;
     if (getenv("OOKD_DEBUG")) {
         const uint32_t *nr = (const uint32_t *) (hs + 64);
-        fprintf(stderr, "[ookd] fast tail: ran %u/%u/%u pairs in rounds 0/1/2, walks resolved %u, %u, %u of %u chunks, overflow %u\n",
-                nr[0], nr[1], nr[2], nr[16 + 0], nr[16 + 1], nr[16 + 2], nc, *(const uint32_t *) (hs + 32));
+        fprintf(stderr, "[ookd] fast tail: ran %u/%u/%u/%u pairs in rounds 0..3, walks resolved %u, %u, %u, %u of %u chunks, overflow %u\n",
+                nr[0], nr[1], nr[2], nr[3], nr[16 + 0], nr[16 + 1], nr[16 + 2], nr[16 + 3], nc, *(const uint32_t *) (hs + 32));
     }
     const u64 n_edges_total = *(const u64 *) hs;
-    const u64 n_msgs = *(const u64 *) (hs + 8);
+    u64 n_msgs = *(const u64 *) (hs + 8);
     const uint32_t refined = *(const uint32_t *) (hs + 16);
-    const uint32_t overflow = *(const uint32_t *) (hs + 32);
-    const uint32_t walk_complete = *(const uint32_t *) (hs + 44);
+    uint32_t overflow = *(const uint32_t *) (hs + 32);
+    uint32_t walk_complete = *(const uint32_t *) (hs + 44);
     h->stat_refined_blocks = refined;
     h->stat_dense_tiles = 0;
     if ((h->screen || h->path == FIR_SCREEN_DEC4) && refined > h->work_cap) return OOKD_OK;      // work list overflowed
     if (n_edges_total > h->pend.edge_cap || *(const uint32_t *) (hs + 28) != 0) return OOKD_OK;   // edge list / a tile region too small
+    // The chain did not resolve within the burst (several consecutive chunks entered in a state no table holds
+    // yet): keep the edges, anchors and tables and add rounds one at a time, each with its own link / walk /
+    // gather and one synchronisation, instead of starting over on the synchronous path.
+    while (overflow == 0 && walk_complete != 1 && rounds < 16) {
+        SmArgs a = fast_sm_args(h, h->pend.e0);
+        a.round = rounds;
+        a.counter_idx = rounds & 15;
+        CU(h, cudaMemcpyAsync(h->tab_cnt[cur ^ 1].p, h->tab_cnt[cur].p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice,
+                              h->s_compute));
+        a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
+        a.cnt_out = (uint32_t *) h->tab_cnt[cur ^ 1].p;
+        cur ^= 1;
+        const u64 warps = (u64) nc * TAB_K;
+        sm_table_round_kernel<<<(unsigned) ((warps + SM_ROUND_WARPS - 1) / SM_ROUND_WARPS), 32 * SM_ROUND_WARPS, 0, h->s_compute>>>(a);
+        rounds++;
+        a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
+        sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
+        sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a);
+        CU(h, cudaMemcpyAsync(h->slot_off.p, h->slot_count.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice, h->s_compute));
+        scan_u32_kernel<<<1, SCAN_NT, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
+        sm_gather_table_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a, (const uint32_t *) h->slot_off.p,
+                                                                           (SmMsg *) h->msgs_dev.p, msg_cap);
+        h->launches += 5;
+        CU(h, cudaGetLastError());
+        // keep [0, 8) of the host mirror (edge total) -- the device copy still holds it
+        CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 512, cudaMemcpyDeviceToHost, h->s_compute));
+        if (n_copy) {
+            CU(h, cudaMemcpyAsync(h->h_msgs_pin, h->msgs_dev.p, sizeof(SmMsg) * n_copy, cudaMemcpyDeviceToHost, h->s_compute));
+        }
+        if (h->warm) {
+            CU(h, cudaMemcpyAsync((char *) h->h_scalars + 288, h->final_entry.p, sizeof(SmCarry), cudaMemcpyDeviceToHost, h->s_compute));
+        }
+        CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
+        CU(h, cudaStreamSynchronize(h->s_compute));
+        h->stat_syncs++;
+        n_msgs = *(const u64 *) (hs + 8);
+        overflow = *(const uint32_t *) (hs + 32);
+        walk_complete = *(const uint32_t *) (hs + 44);
+        if (getenv("OOKD_DEBUG")) {
+            fprintf(stderr, "[ookd] fast tail: extra round %u, walk resolved %u of %u chunks, overflow %u\n", rounds - 1,
+                    *(const uint32_t *) (hs + 40), nc, overflow);
+        }
+    }
     if (overflow != 0 || walk_complete != 1 || n_msgs > msg_cap) {
         if (overflow == 1) h->slot_cap *= 4;
         return OOKD_OK;
