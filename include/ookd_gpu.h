@@ -249,8 +249,8 @@ int  ookd_gpu_decode_end(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd_g
 /* Batch of independent captures (each one a whole file: the loop of
  * ookiedokie_rx(), src/ookiedokie.c:238-290, run once per capture).  Capture i
  * is decoded by handles[caps[i].handle] -- handles may differ in device
- * description, filter and CUDA device -- with up to one capture in flight per
- * handle.  Messages of all captures are written to msgs_out in capture order;
+ * description, filter and CUDA device -- by one host thread per handle, each
+ * walking its handle's captures in order.  Messages of all captures are written to msgs_out in capture order;
  * capture i owns msgs_out[msg_first[i] .. msg_first[i+1]).  If msgs_cap is too
  * small OOKD_ERR_OVERFLOW is returned and msg_first[n_caps] holds the number
  * of messages.  results (nullable) receives per-capture statistics (its msgs

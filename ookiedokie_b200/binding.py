@@ -27,7 +27,7 @@ FLAG_SHARE_SMS = 32
 
 # every symbol include/ookd_gpu.h declares
 EXPORTS = [
-    "ookd_sm_compile", "ookd_sm_compiled_free", "ookd_power_threshold",
+    "ookd_sm_compile", "ookd_sm_compiled_free", "ookd_sm_idle_carry", "ookd_power_threshold",
     "ookd_gpu_device_count", "ookd_gpu_strerror", "ookd_gpu_last_error",
     "ookd_gpu_create", "ookd_gpu_destroy", "ookd_gpu_decode", "ookd_gpu_decode_shard",
     "ookd_gpu_decode_begin", "ookd_gpu_decode_end", "ookd_gpu_batch_decode",

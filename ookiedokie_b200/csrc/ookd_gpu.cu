@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "ookd_common.cuh"
@@ -254,17 +255,15 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 encode_tiled_fn tensor_map_encoder()
 {
-    static encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const encode_tiled_fn fn = []() -> encode_tiled_fn {          // (initialised once, thread safe)
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess) {
-            fn = (encode_tiled_fn) p;
+            return (encode_tiled_fn) p;
         }
-    }
+        return nullptr;
+    }();
     return fn;
 }
 
@@ -1529,44 +1528,45 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
 }
 
 // Independent captures: capture i is decoded whole (first sample 0, EOF padding) by
-// handles[caps[i].handle].  Up to one decode per handle is in flight: while the host waits for one handle's
-// single synchronisation the kernels of the others keep the device busy, so the latency-bound stages
-// (edge scan, state-machine rounds) of different captures overlap.
+// handles[caps[i].handle].  One host thread per handle walks that handle's captures in order (a decode of a small
+// capture is bound by the ~25 launches the host has to enqueue, so the enqueueing itself is what must run in
+// parallel); on the device the kernels of the different handles overlap, which hides the latency-bound stages
+// (edge scan, state-machine rounds) of one capture behind the streaming stages of the others.
 int ookd_gpu_batch_decode(ookd_gpu *const *handles, uint32_t n_handles, const struct ookd_capture *caps, uint32_t n_caps,
                           struct ookd_msg *msgs_out, uint64_t msgs_cap, uint64_t *msg_first, struct ookd_gpu_result *results)
 {
     if (!handles || !n_handles || (!caps && n_caps) || !msg_first) return OOKD_ERR_ARG;
-    std::vector<int64_t> in_flight(n_handles, -1);
+    for (uint32_t i = 0; i < n_caps; i++) {
+        if (caps[i].handle >= n_handles || !handles[caps[i].handle]) return OOKD_ERR_ARG;
+    }
     std::vector<u64> counts(n_caps, 0);
     std::vector<std::vector<ookd_msg>> held(n_caps);
-    auto finish = [&](uint32_t hi) -> int {
-        const int64_t ci = in_flight[hi];
-        if (ci < 0) return OOKD_OK;
-        in_flight[hi] = -1;
-        ookd_gpu_result r;
-        const int rc = ookd_gpu_decode_end(handles[hi], nullptr, &r);
-        if (rc) return rc;
-        counts[ci] = r.n_msgs;
-        held[ci].assign(r.msgs, r.msgs + r.n_msgs);          // the handle's list is reused by its next decode
-        if (results) {
-            results[ci] = r;
-            results[ci].msgs = nullptr;
+    std::vector<int> status(n_handles, OOKD_OK);
+    auto worker = [&](uint32_t hi) {
+        for (uint32_t i = 0; i < n_caps; i++) {
+            if (caps[i].handle != hi) continue;
+            ookd_gpu_result r;
+            int rc = ookd_gpu_decode_begin(handles[hi], caps[i].iq, caps[i].iq_is_device_ptr, 0, caps[i].n_samples, 1, nullptr);
+            if (!rc) rc = ookd_gpu_decode_end(handles[hi], nullptr, &r);
+            if (rc) {
+                status[hi] = rc;
+                return;
+            }
+            counts[i] = r.n_msgs;
+            held[i].assign(r.msgs, r.msgs + r.n_msgs);      // the handle's list is reused by its next decode
+            if (results) {
+                results[i] = r;
+                results[i].msgs = nullptr;
+            }
         }
-        return OOKD_OK;
     };
-    int rc = OOKD_OK;
-    for (uint32_t i = 0; i < n_caps && !rc; i++) {
-        const uint32_t hi = caps[i].handle;
-        if (hi >= n_handles || !handles[hi]) { rc = OOKD_ERR_ARG; break; }
-        if ((rc = finish(hi))) break;
-        rc = ookd_gpu_decode_begin(handles[hi], caps[i].iq, caps[i].iq_is_device_ptr, 0, caps[i].n_samples, 1, nullptr);
-        if (!rc) in_flight[hi] = i;
-    }
+    std::vector<std::thread> threads;
+    for (uint32_t hi = 1; hi < n_handles; hi++) threads.emplace_back(worker, hi);
+    worker(0);
+    for (auto &t : threads) t.join();
     for (uint32_t hi = 0; hi < n_handles; hi++) {
-        const int rc2 = finish(hi);
-        if (!rc) rc = rc2;
+        if (status[hi]) return status[hi];
     }
-    if (rc) return rc;
     u64 total = 0;
     for (uint32_t i = 0; i < n_caps; i++) {
         msg_first[i] = total;
