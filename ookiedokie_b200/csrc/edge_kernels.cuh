@@ -282,9 +282,9 @@ __global__ void __launch_bounds__(128) edge_flatten_kernel(const Edge1Args x)
     }
 }
 
-// Single-CTA exclusive scan of n uint32 values in place; total to *total (64-bit).  256 threads: small enough to
-// run next to another decode's persistent screening kernel (see OOKD_FLAG_SHARE_SMS).
-constexpr int SCAN_NT = 256;
+// Single-CTA exclusive scan of n uint32 values in place; total to *total (64-bit).
+
+constexpr int SCAN_NT = 1024;
 
 __global__ void __launch_bounds__(SCAN_NT) scan_u32_kernel(uint32_t *v, uint32_t n, u64 *total)
 {

@@ -302,8 +302,59 @@ ScreenArgs screen_args(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_va
     return sa;
 }
 
+// TMA-staged screening kernel (screen_tma.cuh) over `tiles` tiles of 4096 INPUT samples starting at tile
+// sa.tile_offset (tiles are numbered from h->bit_base in units of 4096 / dec outputs).
+int launch_screen_tma(ookd_gpu *h, const ScreenArgs &sa, const ScreenParams &sp, const uint32_t *d_in, i64 in_base,
+                      i64 in_valid_end, u64 tiles, int dec)
+{
+    // Tensor view: rows of 32 samples starting at row0 (the first input of a tile of this decode, at or after the
+    // first sample present); only tiles that lie wholly inside complete rows use the copy engine.
+    ScreenTmaArgs ta{};
+    ta.s = sa;
+    const i64 first_present = in_base > 0 ? in_base : 0;
+    i64 row0 = h->bit_base * dec;
+    if (row0 < first_present) row0 += (first_present - row0 + STMA_L - 1) / STMA_L * STMA_L;
+    const uintptr_t addr0 = (uintptr_t) (d_in + (row0 - in_base));
+    const i64 n_rows = (in_valid_end - row0) / 32;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    bool ok = (addr0 % 16 == 0) && n_rows >= STMA_L / 32 && n_rows < (1ll << 31) && tensor_map_encoder();
+    if (ok) {
+        const cuuint64_t gdim[2] = {32, (cuuint64_t) n_rows};
+        const cuuint64_t gstride[1] = {128};
+        const cuuint32_t box[2] = {32, STMA_L / 32};
+        const cuuint32_t estr[2] = {1, 1};
+        ok = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *) addr0, gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    ta.row0_sample = row0;
+    if (ok) {
+        ta.fast_lo = (uint32_t) ((row0 - h->bit_base * dec) / STMA_L);
+        ta.fast_hi = (uint32_t) ((row0 + n_rows * 32 - h->bit_base * dec) / STMA_L);
+    } else {
+        ta.fast_lo = ta.fast_hi = 0;
+    }
+    // OOKD_FLAG_SHARE_SMS: three CTAs per SM instead of four, so that a quarter of every SM's registers
+    // and shared memory stays free for the latency-bound tail kernels of ANOTHER handle's decode
+    const bool share = (h->flags & OOKD_FLAG_SHARE_SMS) != 0;
+    const u64 ctas = (u64) h->n_sm * (share ? OOKD_STMA_MINB - 1 : OOKD_STMA_MINB);
+    static const bool use_token = getenv("OOKD_SCREEN_TOKEN") != nullptr;
+    cudaEvent_t *tok = (share && use_token) ? screen_token(h->device) : nullptr;
+    if (tok) CU(h, cudaStreamWaitEvent(h->s_compute, *tok, 0));
+    const unsigned grid = (unsigned) (tiles < ctas ? tiles : ctas);
+    if (dec == 1) {
+        fir_screen_tma_kernel<1><<<grid, STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(tmap, ta, sp);
+    } else {
+        fir_screen_tma_kernel<4><<<grid, STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(tmap, ta, sp);
+    }
+    if (tok) CU(h, cudaEventRecord(*tok, h->s_compute));
+    return OOKD_OK;
+}
+
 int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end, i64 o_begin, i64 o_end)
 {
+    int rc;
     if (o_end <= o_begin) return OOKD_OK;
     if (h->path == FIR_TILED_1STAGE_32) {
         TapsParam<32> tp;
@@ -319,44 +370,7 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
             make_screen_params(h, sp);
             sa.n_tiles = (uint32_t) stiles;
             if (h->tma) {
-                // Tensor view: rows of 32 samples starting at row0 (a tile boundary of this decode at or after the
-                // first sample present); only tiles that lie wholly inside complete rows use the copy engine.
-                ScreenTmaArgs ta{};
-                ta.s = sa;
-                const i64 first_present = in_base > 0 ? in_base : 0;
-                i64 row0 = h->bit_base;
-                if (row0 < first_present) row0 += (first_present - row0 + SCREEN_L - 1) / SCREEN_L * SCREEN_L;
-                const uintptr_t addr0 = (uintptr_t) (d_in + (row0 - in_base));
-                const i64 n_rows = (in_valid_end - row0) / 32;
-                CUtensorMap tmap;
-                memset(&tmap, 0, sizeof(tmap));
-                bool ok = (addr0 % 16 == 0) && n_rows >= SCREEN_L / 32 && n_rows < (1ll << 31) && tensor_map_encoder();
-                if (ok) {
-                    const cuuint64_t gdim[2] = {32, (cuuint64_t) n_rows};
-                    const cuuint64_t gstride[1] = {128};
-                    const cuuint32_t box[2] = {32, SCREEN_L / 32};
-                    const cuuint32_t estr[2] = {1, 1};
-                    ok = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *) addr0, gdim, gstride, box, estr,
-                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-                }
-                ta.row0_sample = row0;
-                if (ok) {
-                    ta.fast_lo = (uint32_t) ((row0 - h->bit_base) / SCREEN_L);
-                    ta.fast_hi = (uint32_t) ((row0 + n_rows * 32 - h->bit_base) / SCREEN_L);
-                } else {
-                    ta.fast_lo = ta.fast_hi = 0;
-                }
-                // OOKD_FLAG_SHARE_SMS: three CTAs per SM instead of four, so that a quarter of every SM's registers
-                // and shared memory stays free for the latency-bound tail kernels of ANOTHER handle's decode
-                const bool share = (h->flags & OOKD_FLAG_SHARE_SMS) != 0;
-                const u64 ctas = (u64) h->n_sm * (share ? OOKD_STMA_MINB - 1 : OOKD_STMA_MINB);
-                static const bool use_token = getenv("OOKD_SCREEN_TOKEN") != nullptr;
-                cudaEvent_t *tok = (share && use_token) ? screen_token(h->device) : nullptr;
-                if (tok) CU(h, cudaStreamWaitEvent(h->s_compute, *tok, 0));
-                fir1_screen_tma_kernel<32><<<(unsigned) (stiles < ctas ? stiles : ctas), STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(
-                    tmap, ta, sp);
-                if (tok) CU(h, cudaEventRecord(*tok, h->s_compute));
+                if ((rc = launch_screen_tma(h, sa, sp, d_in, in_base, in_valid_end, stiles, 1))) return rc;
             } else if (h->persist) {
                 const u64 ctas = (u64) h->n_sm * OOKD_SCREEN_PERSIST_MINB;
                 fir1_screen_persist_kernel<32><<<(unsigned) (stiles < ctas ? stiles : ctas), 256, 0, h->s_compute>>>(sa, sp);
@@ -381,7 +395,11 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
         sa.n_tiles = (uint32_t) tiles;
         ScreenParams sp;
         make_screen_params_dec4(h, sp);
-        fir2_screen_kernel<<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, sp);
+        if (h->tma) {
+            if ((rc = launch_screen_tma(h, sa, sp, d_in, in_base, in_valid_end, tiles, 4))) return rc;
+        } else {
+            fir2_screen_kernel<<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, sp);
+        }
         h->launches++;
         CU(h, cudaGetLastError());
         return OOKD_OK;
@@ -1271,10 +1289,12 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     }
     h->n_sm = (unsigned) prop.multiProcessorCount;
     h->persist = (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) == 0;
-    h->tma = h->persist && !(h->flags & OOKD_FLAG_NO_TMA);
+    h->tma = h->persist && !(h->flags & OOKD_FLAG_NO_TMA);       // both screened shapes (one stage 32/1, dec4)
     if (h->tma) {
-        if (cudaFuncSetAttribute(fir1_screen_tma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, STMA_SMEM_BYTES) !=
-            cudaSuccess) {
+        if (cudaFuncSetAttribute(fir_screen_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, STMA_SMEM_BYTES) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(fir_screen_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, STMA_SMEM_BYTES) !=
+                cudaSuccess) {
             cudaGetLastError();
             h->tma = false;
         }

@@ -39,12 +39,14 @@ struct ScreenTmaArgs {
     uint32_t fast_lo, fast_hi;   // tiles [fast_lo, fast_hi) (numbered like s.tile_offset) can use the tensor copy
 };
 
-constexpr int STMA_NT = 256, STMA_SPT = 16, STMA_L = STMA_NT * STMA_SPT;   // 4096 samples per tile
+constexpr int STMA_NT = 256, STMA_SPT = 16, STMA_L = STMA_NT * STMA_SPT;   // 4096 input samples per tile
 constexpr int STMA_STAGES = 3;
 constexpr int STMA_BODY = STMA_L * 4;                           // 16 KiB per stage, 1024-byte aligned (128 B swizzle)
-constexpr int STMA_XY_ROWS = STMA_NT + 2;
-// bodies | history rows (128 B per stage) | (sum I, sum Q) rows | mbarriers, + 1 KiB alignment slack
-constexpr int STMA_SMEM_BYTES = 1024 + STMA_STAGES * STMA_BODY + STMA_STAGES * 128 + STMA_STAGES * STMA_XY_ROWS * 8 + 32;
+constexpr int STMA_HT_MAX = 5;                                  // history spans in front of a tile (2 for T=32/D=1, 5 for dec4)
+constexpr int STMA_HIST = 384;                                  // bytes of history rows per stage: rows -3..-1
+constexpr int STMA_XY_ROWS = STMA_NT + STMA_HT_MAX;
+// bodies | history rows | (sum I, sum Q) rows | mbarriers
+constexpr int STMA_SMEM_BYTES = STMA_STAGES * STMA_BODY + STMA_STAGES * STMA_HIST + STMA_STAGES * STMA_XY_ROWS * 8 + 32;
 static_assert(4 * (STMA_SMEM_BYTES + 1024) <= 228 * 1024, "four CTAs per SM");
 
 #ifndef OOKD_STMA_MINB
@@ -108,13 +110,19 @@ __device__ __forceinline__ int stma_chunk_off(int u, int v)
     return R * 128 + (((((u & 1) << 2) | v) ^ (R & 7)) << 4);
 }
 
-template <int T>
+// DEC = 1: one stage, 32 taps, decimation 1 (fs32_fs4, fs64_fs8): 16 outputs per thread, window = 2 spans back.
+// DEC = 4: two stages 16/2 + 32/2 (fs128_fs16_dec4): 4 outputs per thread, composite window of 78 inputs = 5 spans
+//          back (the proofs and the elements needed are those of fir2_screen_kernel, fir_kernels.cuh section 4).
+// Tiles, a.out_lo / out_hi / bit_base are in OUTPUT indices; a tile is 4096 INPUT samples = 4096 / DEC outputs.
+template <int DEC>
 __global__ void __launch_bounds__(STMA_NT, OOKD_STMA_MINB)
-fir1_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaArgs ta, const ScreenParams sp)
+fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaArgs ta, const ScreenParams sp)
 {
-    static_assert(T == 32, "window = exactly two 16-sample thread spans");
+    static_assert(DEC == 1 || DEC == 4, "shapes with a screening proof");
     constexpr int NT = STMA_NT, SPT = STMA_SPT, L = STMA_L, NS = STMA_STAGES;
-    extern __shared__ uint8_t smem_raw[];
+    constexpr int HT = (DEC == 1) ? 2 : 5;                     // history spans
+    constexpr int LOUT = L / DEC;                              // outputs per tile
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
 
     const ScreenArgs &sa = ta.s;
     const TiledArgs &a = sa.t;
@@ -123,9 +131,13 @@ fir1_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTma
     const uint32_t t_end = min(sa.tile_offset + sa.n_tiles, t_begin + per);
     if (t_begin >= t_end) return;
 
-    const uint32_t body0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t hist0 = body0 + NS * STMA_BODY + 128u;      // + 128: history rows are "row -1" of their stage
-    const uint32_t xy0 = body0 + NS * STMA_BODY + NS * 128u;
+    const uint32_t body0 = smem_u32(smem_raw);
+    // The 128-byte swizzle of the tensor copy assumes 1024-byte aligned bodies.  The dynamic shared-memory window
+    // starts on such a boundary; should it ever not, every tile takes the scalar-load path (the in-place rows use
+    // one address formula for writing and reading, so they stay consistent whatever the base).
+    const bool smem_aligned = (body0 & 1023u) == 0;
+    const uint32_t hist0 = body0 + NS * STMA_BODY + STMA_HIST;   // + STMA_HIST: history rows are rows -3..-1 of their stage
+    const uint32_t xy0 = body0 + NS * STMA_BODY + NS * STMA_HIST;
     const uint32_t bar0 = xy0 + NS * STMA_XY_ROWS * 8;
 
     const int u = (int) threadIdx.x;
@@ -136,10 +148,9 @@ fir1_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTma
     }
     __syncthreads();
 
-    auto tile_fast = [&](uint32_t tile) -> bool { return tile >= ta.fast_lo && tile < ta.fast_hi; };
-    auto tile_row = [&](uint32_t tile) -> int32_t {
-        return (int32_t) ((a.out_lo + (i64) tile * L - ta.row0_sample) >> 5);
-    };
+    auto tile_fast = [&](uint32_t tile) -> bool { return smem_aligned && tile >= ta.fast_lo && tile < ta.fast_hi; };
+    auto tile_in0 = [&](uint32_t tile) -> i64 { return (a.out_lo + (i64) tile * LOUT) * DEC; };   // first input of a tile
+    auto tile_row = [&](uint32_t tile) -> int32_t { return (int32_t) ((tile_in0(tile) - ta.row0_sample) >> 5); };
     auto issue = [&](uint32_t tile, int s) {
         const uint32_t bar = bar0 + 8 * s;
         mbar_expect_tx(bar, L * 4);
@@ -152,14 +163,16 @@ fir1_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTma
             w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
         }
     };
-    // store one span's statistics as the row of virtual thread uu (>= 0: body, < 0: history rows) of stage s
+    // base address of the row of virtual thread uu (>= 0: body, < 0: history rows) of stage s
+    auto row_base = [&](int s, int uu) -> uint32_t { return (uu >= 0) ? body0 + s * STMA_BODY : hist0 + s * STMA_HIST; };
+    // store one span's statistics as the row of virtual thread uu of stage s
     auto store_row = [&](int s, int uu, const uint32_t (&p)[16], int xs, int ys) {
-        const uint32_t rb = (uu >= 0) ? body0 + s * STMA_BODY : hist0 + s * 128u;
+        const uint32_t rb = row_base(s, uu);
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             sts128(rb + stma_chunk_off(uu, v), p[4 * v], p[4 * v + 1], p[4 * v + 2], p[4 * v + 3]);
         }
-        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(xy0 + (s * STMA_XY_ROWS + uu + 2) * 8), "r"(xs), "r"(ys)
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(xy0 + (s * STMA_XY_ROWS + uu + HT) * 8), "r"(xs), "r"(ys)
                      : "memory");
     };
 
@@ -168,30 +181,28 @@ fir1_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTma
         if (tile_fast(t_begin)) issue(t_begin, 0);
         if (t_begin + 1 < t_end && tile_fast(t_begin + 1)) issue(t_begin + 1, 1);
     }
-    if (u < 2) {
+    if (u < HT) {
         uint32_t w[16], p[16], gd;
         int xs, ys;
-        load_span_slow(a.out_lo + (i64) t_begin * L - 2 * SPT + (i64) u * SPT, w);
+        load_span_slow(tile_in0(t_begin) - HT * SPT + (i64) u * SPT, w);
         screen_span_stats(w, p, xs, ys, gd);
         if (gd >> 25) p[15] = 0xFFFFFFFFu;
-        store_row(0, u - 2, p, xs, ys);
+        store_row(0, u - HT, p, xs, ys);
     }
 
-    // own-row and neighbour-row offsets inside a stage body
-    int off_own[4], off_p2[4];
+    // own-row offsets inside a stage body
+    int off_own[4];
 #pragma unroll
-    for (int v = 0; v < 4; v++) {
-        off_own[v] = stma_chunk_off(u, v);
-        off_p2[v] = stma_chunk_off(u - 2, v);
-    }
-    const int off_tot1 = stma_chunk_off(u - 1, 3) + 12;
+    for (int v = 0; v < 4; v++) off_own[v] = stma_chunk_off(u, v);
+    // neighbour rows: offset of element e (0..15) of the row of virtual thread uu, relative to that row's base
+    auto elem_off = [&](int uu, int e) -> int { return stma_chunk_off(uu, e >> 2) + 4 * (e & 3); };
 
     int s = 0;                     // stage of the current tile = (tile - t_begin) % NS
     uint32_t phases = 0;           // bit s = parity the next wait on stage s uses
     for (uint32_t tile = t_begin; tile < t_end; tile++) {
         const uint32_t body = body0 + s * STMA_BODY;
-        const uint32_t hist = hist0 + s * 128u;
-        const i64 o0 = a.out_lo + (i64) tile * L;
+        const uint32_t hist = hist0 + s * STMA_HIST;
+        const i64 o0 = a.out_lo + (i64) tile * LOUT;
         uint32_t w[16];
         if (tile_fast(tile)) {
             mbar_wait(bar0 + 8 * s, (phases >> s) & 1u);
@@ -202,7 +213,7 @@ fir1_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTma
                 w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
             }
         } else {
-            load_span_slow(o0 + (i64) u * SPT, w);
+            load_span_slow(tile_in0(tile) + (i64) u * SPT, w);
         }
         uint32_t pre[SPT], guard;
         int sx, sy;
@@ -214,7 +225,7 @@ fir1_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTma
             for (int e = 0; e < 15; e++) p[e] = pre[e];
             p[15] = tot_own;
             store_row(s, u, p, sx, sy);
-            if (u >= NT - 2) {                                   // history rows of the next tile's stage
+            if (u >= NT - HT) {                                  // history rows of the next tile's stage
                 store_row(s == NS - 1 ? 0 : s + 1, u - NT, p, sx, sy);
             }
         }
@@ -223,77 +234,141 @@ fir1_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTma
         if (u == 0 && tile + 2 < t_end && tile_fast(tile + 2)) {
             issue(tile + 2, s == 0 ? NS - 1 : s - 1);            // (s + 2) % 3: the stage tile-1 has just left
         }
+        auto nb_base = [&](int k) -> uint32_t { return (u < k) ? hist : body; };     // base of the row of thread u - k
 
-        // ---- decisions for the 16 outputs of this thread (two groups of 8) ----
-        uint32_t p2[SPT];
+        if constexpr (DEC == 1) {
+            // ---- decisions for the 16 outputs of this thread (two groups of 8) ----
+            uint32_t p2[SPT];
 #pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const uint4 x = lds128((u < 2 ? hist : body) + off_p2[v]);
-            p2[4 * v] = x.x; p2[4 * v + 1] = x.y; p2[4 * v + 2] = x.z; p2[4 * v + 3] = x.w;
-        }
-        uint32_t tot1;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tot1) : "r"((u < 1 ? hist : body) + off_tot1));
-        const uint32_t tot2 = p2[SPT - 1];
-        uint32_t bits16 = 0;
-        bool undecided_lo = true, undecided_hi = true;
-        const i64 o = o0 + (i64) u * SPT;
-        if ((int) (tot_own | tot1 | tot2) >= 0) {
-            const uint32_t bsum = tot2 + tot1;
-            int dmax_lo = INT_MIN, dmax_hi = INT_MIN;
+            for (int v = 0; v < 4; v++) {
+                const uint4 x = lds128(nb_base(2) + stma_chunk_off(u - 2, v));
+                p2[4 * v] = x.x; p2[4 * v + 1] = x.y; p2[4 * v + 2] = x.z; p2[4 * v + 3] = x.w;
+            }
+            uint32_t tot1;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tot1) : "r"(nb_base(1) + elem_off(u - 1, 15)));
+            const uint32_t tot2 = p2[SPT - 1];
+            uint32_t bits16 = 0;
+            bool undecided_lo = true, undecided_hi = true;
+            const i64 o = o0 + (i64) u * SPT;
+            if ((int) (tot_own | tot1 | tot2) >= 0) {
+                const uint32_t bsum = tot2 + tot1;
+                int dmax_lo = INT_MIN, dmax_hi = INT_MIN;
 #pragma unroll
-            for (int j = 0; j < SPT; j++) {
-                const int d = (int) (pre[j] - p2[j]);          // all sums < 2^31: signed difference is exact
-                if (j < 8) dmax_lo = max(dmax_lo, d); else dmax_hi = max(dmax_hi, d);
+                for (int j = 0; j < SPT; j++) {
+                    const int d = (int) (pre[j] - p2[j]);          // all sums < 2^31: signed difference is exact
+                    if (j < 8) dmax_lo = max(dmax_lo, d); else dmax_hi = max(dmax_hi, d);
+                }
+                const bool off_lo = (uint32_t) ((int) bsum + dmax_lo) < sp.k0, off_hi = (uint32_t) ((int) bsum + dmax_hi) < sp.k0;
+                bool on = false;
+                if (!(off_lo && off_hi)) {
+                    int x1, y1, x2, y2;
+                    const uint32_t xy = xy0 + (s * STMA_XY_ROWS + u) * 8;     // rows u-2 (+0) and u-1 (+8)
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x2), "=r"(y2) : "r"(xy));
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x1), "=r"(y1) : "r"(xy + 8));
+                    const float X = (float) (sx + x1 + x2), Y = (float) (sy + y1 + y2);
+                    const float Q = (float) (bsum + pre[SPT - 1]);
+                    const float m2 = fmaf(X, X, Y * Y);
+                    const float mu = sqrt_approx(m2) * sp.inv_n;
+                    const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
+                    const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
+                    on = fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi;
+                }
+                if (on) {
+                    bits16 = 0xFFFFu;
+                    undecided_lo = undecided_hi = false;
+                } else {
+                    undecided_lo = !off_lo;
+                    undecided_hi = !off_hi;
+                }
             }
-            const bool off_lo = (uint32_t) ((int) bsum + dmax_lo) < sp.k0, off_hi = (uint32_t) ((int) bsum + dmax_hi) < sp.k0;
-            bool on = false;
-            if (!(off_lo && off_hi)) {
-                int x1, y1, x2, y2;
-                const uint32_t xy = xy0 + (s * STMA_XY_ROWS + u) * 8;     // rows u-2 (+0) and u-1 (+8)
-                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x2), "=r"(y2) : "r"(xy));
-                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(x1), "=r"(y1) : "r"(xy + 8));
-                const float X = (float) (sx + x1 + x2), Y = (float) (sy + y1 + y2);
-                const float Q = (float) (bsum + pre[SPT - 1]);
-                const float m2 = fmaf(X, X, Y * Y);
-                const float mu = sqrt_approx(m2) * sp.inv_n;
-                const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
-                const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
-                on = fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi;
+            const bool in_lo = o < a.out_hi, in_hi = o + 8 < a.out_hi;
+            if (in_lo) {
+                const i64 byte = (o - a.bit_base) >> 3;
+                if (in_hi) {
+                    *(uint16_t *) (a.out_bits + byte) = (uint16_t) bits16;
+                } else {
+                    a.out_bits[byte] = (uint8_t) bits16;
+                }
             }
-            if (on) {
-                bits16 = 0xFFFFu;
-                undecided_lo = undecided_hi = false;
-            } else {
-                undecided_lo = !off_lo;
-                undecided_hi = !off_hi;
+            const bool push_lo = undecided_lo && in_lo, push_hi = undecided_hi && in_hi;
+            const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, push_lo), m_hi = __ballot_sync(0xFFFFFFFFu, push_hi);
+            if (m_lo | m_hi) {
+                const uint32_t n_push = __popc(m_lo) + __popc(m_hi);
+                const int lane = u & 31;
+                uint32_t slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(sa.work_count, n_push);
+                slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+                const uint32_t below = (1u << lane) - 1;
+                const uint32_t grp0 = (uint32_t) ((o - a.bit_base) >> 3);
+                if (push_lo) {
+                    const uint32_t sl = slot0 + __popc(m_lo & below);
+                    if (sl < sa.work_cap) sa.work_list[sl] = grp0;
+                }
+                if (push_hi) {
+                    const uint32_t sl = slot0 + __popc(m_lo) + __popc(m_hi & below);
+                    if (sl < sa.work_cap) sa.work_list[sl] = grp0 + 1;
+                }
             }
-        }
-        const bool in_lo = o < a.out_hi, in_hi = o + 8 < a.out_hi;
-        if (in_lo) {
-            const i64 byte = (o - a.bit_base) >> 3;
-            if (in_hi) {
-                *(uint16_t *) (a.out_bits + byte) = (uint16_t) bits16;
-            } else {
-                a.out_bits[byte] = (uint8_t) bits16;
+        } else {
+            // ---- decisions for the 4 outputs of this thread; two threads share a byte / an 8-output group ----
+            auto ld = [&](int k, int e) -> uint32_t {
+                uint32_t v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(nb_base(k) + elem_off(u - k, e)));
+                return v;
+            };
+            const uint32_t t1 = ld(1, 15), t2 = ld(2, 15), t3 = ld(3, 15), t4 = ld(4, 15), t5 = ld(5, 15);
+            uint32_t bits4 = 0, und = 0xF;
+            if ((int) (tot_own | t1 | t2 | t3 | t4 | t5) >= 0) {
+                const uint32_t p4_1 = ld(4, 1), p5_5 = ld(5, 5), p5_9 = ld(5, 9), p5_13 = ld(5, 13);
+                const uint32_t mid3 = t3 + t2 + t1;               // spans u-3 .. u-1
+                const uint32_t mid4 = mid3 + t4;                  // spans u-4 .. u-1
+                // newest sample at element 3, 7, 11: window starts at element 6, 10, 14 of span u-5
+                const uint32_t e0 = (t5 - p5_5) + mid4 + pre[3];
+                const uint32_t e1 = (t5 - p5_9) + mid4 + pre[7];
+                const uint32_t e2 = (t5 - p5_13) + mid4 + pre[11];
+                // newest sample at element 15: window starts at element 2 of span u-4
+                const uint32_t e3 = (t4 - p4_1) + mid3 + pre[15];
+                und = (e0 < sp.k0 ? 0u : 1u) | (e1 < sp.k0 ? 0u : 2u) | (e2 < sp.k0 ? 0u : 4u) | (e3 < sp.k0 ? 0u : 8u);
+                if (und) {
+                    int X = sx, Y = sy;
+#pragma unroll
+                    for (int k = 1; k <= 5; k++) {
+                        int xk, yk;
+                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(xk), "=r"(yk)
+                                     : "r"(xy0 + (s * STMA_XY_ROWS + u - k + HT) * 8));
+                        X += xk;
+                        Y += yk;
+                    }
+                    const float Xf = (float) X, Yf = (float) Y;
+                    const float Q = (float) (t5 + mid4 + pre[15]);
+                    const float m2 = fmaf(Xf, Xf, Yf * Yf);
+                    const float mu = sqrt_approx(m2) * sp.inv_n;
+                    const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
+                    const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
+                    if (fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi) {
+                        bits4 = 0xF;
+                        und = 0;
+                    }
+                }
             }
-        }
-        const bool push_lo = undecided_lo && in_lo, push_hi = undecided_hi && in_hi;
-        const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, push_lo), m_hi = __ballot_sync(0xFFFFFFFFu, push_hi);
-        if (m_lo | m_hi) {
-            const uint32_t n_push = __popc(m_lo) + __popc(m_hi);
-            const int lane = u & 31;
-            uint32_t slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(sa.work_count, n_push);
-            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
-            const uint32_t below = (1u << lane) - 1;
-            const uint32_t grp0 = (uint32_t) ((o - a.bit_base) >> 3);
-            if (push_lo) {
-                const uint32_t sl = slot0 + __popc(m_lo & below);
-                if (sl < sa.work_cap) sa.work_list[sl] = grp0;
+            const uint32_t other_bits = __shfl_down_sync(0xFFFFFFFFu, bits4, 1);
+            const uint32_t other_und = __shfl_down_sync(0xFFFFFFFFu, und, 1);
+            const i64 o = o0 + (i64) u * 4;                       // first output of this thread
+            const bool in_range = ((u & 1) == 0) && o < a.out_hi;
+            const bool push = in_range && ((und | other_und) != 0);
+            if (in_range) {
+                a.out_bits[(o - a.bit_base) >> 3] = (uint8_t) (bits4 | (other_bits << 4));
             }
-            if (push_hi) {
-                const uint32_t sl = slot0 + __popc(m_lo) + __popc(m_hi & below);
-                if (sl < sa.work_cap) sa.work_list[sl] = grp0 + 1;
+            const uint32_t m_push = __ballot_sync(0xFFFFFFFFu, push);
+            if (m_push) {
+                const int lane = u & 31;
+                uint32_t slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(sa.work_count, (uint32_t) __popc(m_push));
+                slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+                if (push) {
+                    const uint32_t sl = slot0 + __popc(m_push & ((1u << lane) - 1));
+                    if (sl < sa.work_cap) sa.work_list[sl] = (uint32_t) ((o - a.bit_base) >> 3);
+                }
             }
         }
         s = (s == NS - 1) ? 0 : s + 1;

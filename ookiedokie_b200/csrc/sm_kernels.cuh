@@ -1026,7 +1026,7 @@ __global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
 // shared memory (one coalesced pass), composed over segments of SEG chunks (one thread per segment, all K start
 // slots at once), the short chain over segments is walked by one thread, and every segment thread then replays
 // its own segment from its now-known entry slot.
-constexpr int SM_WALK_NT = 256;                             // small enough to run next to a persistent screening kernel
+constexpr int SM_WALK_NT = 1024;
 
 __global__ void __launch_bounds__(SM_WALK_NT) sm_walk_kernel(const SmArgs a)
 {
