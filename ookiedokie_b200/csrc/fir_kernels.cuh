@@ -876,4 +876,73 @@ __global__ void __launch_bounds__(256) fir2_refine_kernel(const ScreenArgs sa, c
     }
 }
 
+// Same job, one THREAD per undecided group of 8 outputs m0..m0+7.  The 46 stage-1 outputs s[2 m0 + 15] .. s[2 m0 - 30]
+// the group needs are computed ONCE each (newest first, from a 16-sample register window that slides down by two
+// inputs per step) and fed to every output y[m] they belong to: walking u downwards visits the taps of each y[m] in
+// the reference's order j = 0, 1, ... (src/fir.c:313-318), so all sums stay bit-exact; 4.4x fewer MACs than the
+// lane-per-output form.
+__global__ void __launch_bounds__(128) fir2_refine_group_kernel(const ScreenArgs sa, const Taps2Param taps)
+{
+    const TiledArgs &a = sa.t;
+    const uint32_t n_groups = min(*sa.work_count, sa.work_cap);
+    for (uint32_t qi = blockIdx.x * blockDim.x + threadIdx.x; qi < n_groups; qi += gridDim.x * blockDim.x) {
+        const uint32_t grp = sa.work_list[qi];
+        const i64 m0 = a.bit_base + (i64) grp * 8;             // first output of the group
+        const i64 u_top = 2 * m0 + 15;                         // newest stage-1 output needed (by y[m0+7], j = 0)
+        const i64 g_top = 2 * u_top + 1;                       // newest input: 4 m0 + 31
+        const i64 g_bot = 2 * (u_top - 45) + 1 - 15;           // oldest input: 4 m0 - 74
+        const bool inside = g_bot >= a.in_base && g_bot >= 0 && g_top < a.in_valid_end;
+        auto sample = [&](i64 g) -> float2 {
+            if (inside) return sc16q11_to_float2(__ldg(a.in + (g - a.in_base)));
+            return sc16q11_to_float2((g >= 0 && g >= a.in_base && g < a.in_valid_end) ? __ldg(a.in + (g - a.in_base)) : 0u);
+        };
+        float2 w[16];                                          // w[k] = x[2u+1-k] for the current u
+#pragma unroll
+        for (int k = 0; k < 16; k++) w[k] = sample(g_top - k);
+        float re[8], im[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            re[q] = 0.0f;
+            im[q] = 0.0f;
+        }
+#pragma unroll
+        for (int d = 0; d < 46; d++) {                         // u = u_top - d
+            float sr = 0.0f, si = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                sr = mac_exact(sr, taps.t1[i], w[i].x);
+                si = mac_exact(si, taps.t1[i], w[i].y);
+            }
+            // stage-1 outputs with a negative index are the zeros fir_reset leaves in the delay line (+0.0 exactly;
+            // a sum of products of zero inputs could be -0.0, which the reference never sees there)
+            if (u_top - d < 0) {
+                sr = 0.0f;
+                si = 0.0f;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                constexpr int dummy = 0;
+                (void) dummy;
+                const int j = 2 * q + 1 - (15 - d);            // tap of y[m0+q] this s[u] multiplies: j = 2(m0+q)+1-u
+                if (j >= 0 && j < 32) {
+                    re[q] = mac_exact(re[q], taps.t2[j], sr);
+                    im[q] = mac_exact(im[q], taps.t2[j], si);
+                }
+            }
+            if (d < 45) {
+#pragma unroll
+                for (int k = 0; k < 14; k++) w[k] = w[k + 2];
+                w[14] = sample(g_top - (2 * d + 16));
+                w[15] = sample(g_top - (2 * d + 17));
+            }
+        }
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            bits |= (power_exact(re[q], im[q]) >= a.pstar ? 1u : 0u) << q;
+        }
+        a.out_bits[grp] = (uint8_t) bits;
+    }
+}
+
 }  // namespace ookd

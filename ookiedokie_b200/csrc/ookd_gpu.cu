@@ -417,7 +417,11 @@ int launch_fir_refine(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_val
         tp.d_t1 = h->stages[0].d_taps;
         tp.d_t2 = h->stages[1].d_taps;
         ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
-        fir2_refine_kernel<<<8 * h->n_sm, 256, 0, h->s_compute>>>(sa, tp);
+        if (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) {
+            fir2_refine_kernel<<<8 * h->n_sm, 256, 0, h->s_compute>>>(sa, tp);           // lane-per-output form
+        } else {
+            fir2_refine_group_kernel<<<16 * h->n_sm, 128, 0, h->s_compute>>>(sa, tp);
+        }
         h->launches++;
         CU(h, cudaGetLastError());
         return OOKD_OK;
