@@ -455,7 +455,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
                          "peak_source": peak_src,
-                         "kernel": "fir1_screen_tma_kernel<32> (SC16Q11 -> window energies -> threshold decisions), "
+                         "kernel": "fir_screen_tma_kernel<1> (SC16Q11 -> window energies -> threshold decisions), "
                                    "4 B/sample algorithmic, one launch per step",
                          "kernel_ms_per_launch": screen_ms_per_launch},
             "clocks": clocks, "gpu_launches": launches,
