@@ -148,6 +148,7 @@ def lib():
         L.ookd_sm_compile.restype = C.c_int
         L.ookd_sm_compile.argtypes = [C.POINTER(SmDesc), C.POINTER(SmCompiled)]
         L.ookd_sm_compiled_free.argtypes = [C.POINTER(SmCompiled)]
+        L.ookd_sm_idle_carry.argtypes = [C.POINTER(SmCompiled), C.POINTER(SmCarry)]
         L.ookd_power_threshold.restype = C.c_float
         L.ookd_power_threshold.argtypes = [C.c_float]
         L.ookd_gpu_device_count.restype = C.c_int
@@ -265,6 +266,20 @@ def sm_compile(states, num_bits, sample_rate):
                          for i in range(out.num_triggers)])
     lib().ookd_sm_compiled_free(C.byref(out))
     return res
+
+
+def sm_idle_carry(states, num_bits, sample_rate):
+    """Host-only: the state the compiled machine settles in on a constant-0 input from RESET (the stitcher's
+    speculative seed).  -> carry tuple (state, k, num_bits, prev_bit, data32)."""
+    d, keep = make_sm_desc(states, num_bits, sample_rate)
+    out = SmCompiled()
+    rc = lib().ookd_sm_compile(C.byref(d), C.byref(out))
+    if rc != 0:
+        raise OokdError(f"ookd_sm_compile: {lib().ookd_gpu_strerror(rc).decode()}")
+    c = SmCarry()
+    lib().ookd_sm_idle_carry(C.byref(out), C.byref(c))
+    lib().ookd_sm_compiled_free(C.byref(out))
+    return c.astuple()
 
 
 def power_threshold(thr):

@@ -226,3 +226,45 @@ def test_batch_of_independent_captures_matches_oracle():
     msgs2, _ = B.batch_decode(gpus, [((t.data_ptr(), t.numel() // 2), captures[i][1]) for i, t in enumerate(d_caps)])
     for i in range(4):
         assert np.array_equal(msgs2[i], msgs[i])
+
+
+@pytest.mark.parametrize("devname,filt", [("p3l-nexa2012", "fs32_fs4"), ("unknown-remote1", "fs128_fs16_dec4")])
+def test_every_code_path_gives_the_same_decode(devname, filt):
+    """Flags select alternative kernels / host paths (TMA vs register-prefetch vs tile-per-CTA screening, exact
+    kernel, synchronous tail, shared SMs, generic FIR): edges and messages must be identical, and equal to the oracle."""
+    dev = O.load_device(devname)
+    fields = util.nexa_fields if "nexa" in devname else util.remote_fields
+    iq, sent, _ = util.capture(dev, 12, sigma=0.02, amplitude=0.6, phase=1.1, seed=4242, fields=fields,
+                               glitches=((9000, 100),))
+    stages = O.load_filter(filt)
+    ref = O.rx(iq, stages, dev, samples_per_buffer=8192, want_bits=True)
+    for flags in (0, B.FLAG_SYNC_TAIL, B.FLAG_NO_TMA, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_SHARE_SMS,
+                  B.FLAG_FORCE_GENERIC, B.FLAG_NO_TMA | B.FLAG_SYNC_TAIL):
+        for chunk_buffers in (0, 5):
+            g = B.Gpu(filter_stages=stages, sm=util.sm_spec(dev, stages), threshold=0.1, samples_per_buffer=8192, flags=flags,
+                      sm_chunk_buffers=chunk_buffers)
+            got = g.decode(iq)
+            fb, edges = g.edges()
+            assert fb == ref["first_bit"] and np.array_equal(edges, ref["edges"]), (flags, chunk_buffers)
+            assert got["msgs"] == ref["msgs"], (flags, chunk_buffers)
+            g.close()
+    assert len(ref["msgs"]) >= 8
+
+
+def test_two_decodes_in_flight():
+    """ookd_gpu_decode_begin on two handles, then ookd_gpu_decode_end on both (and the other way round)."""
+    dev = O.load_device("p3l-nexa2012")
+    stages = O.load_filter("fs32_fs4")
+    caps = [util.capture(dev, 4 + i, sigma=0.02, phase=0.5 * i, seed=900 + i, fields=util.nexa_fields)[0] for i in range(2)]
+    want = [O.rx(c, stages, dev, samples_per_buffer=8192)["msgs"] for c in caps]
+    gpus = [B.Gpu(filter_stages=stages, sm=util.sm_spec(dev, stages), threshold=0.1, samples_per_buffer=8192) for _ in range(2)]
+    for order in ((0, 1), (1, 0)):
+        for i in range(2):
+            gpus[i].decode_begin(caps[i], 0, len(caps[i]), True)
+        with pytest.raises(B.OokdError):
+            gpus[0].decode_begin(caps[0], 0, len(caps[0]), True)       # one decode per handle
+        for i in order:
+            res, _ = gpus[i].decode_end()
+            assert res["msgs"] == want[i]
+    with pytest.raises(B.OokdError):
+        gpus[0].decode_end()                                           # nothing in flight

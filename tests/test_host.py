@@ -117,6 +117,25 @@ def test_sm_compile_windows_replay_the_double_accumulation(name, rate):
     assert c["k_sat"] == max(finite) + 1
 
 
+@pytest.mark.parametrize("name,rate", [("p3l-nexa2012", 3000000), ("unknown-remote1", 750000), ("p3l-nexa2012", 750000)])
+def test_idle_carry_is_where_the_reference_machine_settles(name, rate):
+    """ookd_sm_idle_carry (the stitcher's speculative seed at an anchor) against the oracle's per-sample state
+    machine fed with zeros: same state, no bits, prev 0, and the count saturated for that state."""
+    dev = O.load_device(name)
+    c = B.sm_compile(dev["states"], dev["num_bits"], rate)
+    state, k, nbits, prev, data = B.sm_idle_carry(dev["states"], dev["num_bits"], rate)
+    sm = O.Sm(dev, rate)
+    zeros = np.zeros(4 * c["k_sat"] + 64, dtype=np.uint8)
+    done = 0
+    while done < len(zeros):
+        r, n = sm.process(zeros[done:])
+        done += n
+    o_state, o_k, o_nbits, o_prev, o_data = sm.get_state()
+    assert (state, nbits, prev) == (o_state, o_nbits, o_prev) == (state, 0, 0)
+    assert k == c["states"][state]["ksat"]                   # the oracle counts in microseconds; ours saturates
+    assert bytes(data) == bytes(o_data)
+
+
 def test_sm_compile_survey_probe_values():
     # SURVEY.md 7-4: at 3 MHz the 500 us window opens at k = 1276 (not 1275), a 1500 us timeout fires at 4501
     dev = O.load_device("p3l-nexa2012")
