@@ -876,6 +876,107 @@ __global__ void __launch_bounds__(256) fir2_refine_kernel(const ScreenArgs sa, c
     }
 }
 
+// Tiled EXACT kernel for the two-stage shape (every output computed with the reference's in-order MACs): the path
+// for captures where the screen cannot decide anything (low SNR) and for OOKD_FLAG_NO_SCREEN.
+// CTA = 288 threads, tile = 512 final outputs = 2048 inputs.
+//   stage inputs  : [4 m0 - 80, 4 m0 + 2048) converted once into shared memory (float2, one pad slot per 8 samples:
+//                   thread stride 9 float2 => conflict-free 64-bit loads)
+//   phase 1       : thread t < 264 computes the stage-1 outputs s[2 m0 - 30 + 4t .. + 3] from a 22-sample register
+//                   window (16 taps, decimation 2) and stores them (one pad slot per 4: thread stride 5 float2)
+//   phase 2       : thread t < 256 computes y[m0 + 2t], y[m0 + 2t + 1] from a 34-value window of s (32 taps, decimation 2)
+// ~77 instructions per input sample against the 64 the arithmetic itself needs.
+constexpr int F2X_NT = 288, F2X_M = 512, F2X_IN = 4 * F2X_M + 80, F2X_NS = 2 * F2X_M + 30;
+
+__global__ void __launch_bounds__(F2X_NT, 2) fir2_exact_tiled_kernel(const TiledArgs a, const Taps2Param taps)
+{
+    __shared__ float2 s_x[F2X_IN + F2X_IN / 8 + 8];        // (+8: the last phase-1 thread reads a few slots past its valid window)
+    __shared__ float2 s_s[(F2X_NS + 3) / 4 * 5 + 1];
+    const int t = (int) threadIdx.x;
+    const i64 m0 = a.out_lo + (i64) blockIdx.x * F2X_M;       // first output of the tile (a.out_lo % 8 == a.bit_base % 8)
+    const i64 g0 = 4 * m0 - 80;                               // first staged input
+
+    // ---- stage inputs: 4 samples (16 B) per thread per step ----
+    const bool aligned = (((g0 - a.in_base) & 3) == 0) && ((((uintptr_t) a.in) & 15) == 0);
+    for (int q = t; q < F2X_IN / 4; q += F2X_NT) {
+        const i64 g = g0 + 4 * q;
+        uint32_t w[4];
+        if (aligned && g >= a.in_base && g >= 0 && g + 4 <= a.in_valid_end) {
+            const uint4 v = __ldg((const uint4 *) (a.in + (g - a.in_base)));
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const i64 ge = g + e;
+                w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int x = 4 * q + e;
+            s_x[x + (x >> 3)] = sc16q11_to_float2(w[e]);
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 1: stage-1 outputs v = 4t .. 4t+3 (u = 2 m0 - 30 + v); s[u] = sum_i t1[i] x[2u+1-i], local x = 2v + 21 - i ----
+    if (4 * t < F2X_NS) {
+        float2 win[22];                                       // local x 8t + 6 .. 8t + 27
+#pragma unroll
+        for (int q = 0; q < 22; q++) {
+            const int x = 8 * t + 6 + q;
+            win[q] = s_x[x + (x >> 3)];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            float sr = 0.0f, si = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                sr = mac_exact(sr, taps.t1[i], win[2 * c + 15 - i].x);       // local 2v+21-i = 8t + 6 + (2c + 15 - i)
+                si = mac_exact(si, taps.t1[i], win[2 * c + 15 - i].y);
+            }
+            const int v = 4 * t + c;
+            if (2 * m0 - 30 + v < 0) {                        // stage-1 outputs before the capture: the zeros of fir_reset
+                sr = 0.0f;
+                si = 0.0f;
+            }
+            if (v < F2X_NS) s_s[5 * t + c] = make_float2(sr, si);           // v + (v >> 2) == 5t + c
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: y[m0 + 2t + q] = sum_j t2[j] s[2m+1-j], local v = 4t + 2q + 31 - j ----
+    uint32_t bits2 = 0;
+    if (t < F2X_M / 2) {
+        float2 sw[34];                                        // local v 4t .. 4t + 33
+#pragma unroll
+        for (int q = 0; q < 34; q++) {
+            const int v = 4 * t + q;
+            sw[q] = s_s[v + (v >> 2)];
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            float re = 0.0f, im = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                re = mac_exact(re, taps.t2[j], sw[2 * q + 31 - j].x);
+                im = mac_exact(im, taps.t2[j], sw[2 * q + 31 - j].y);
+            }
+            bits2 |= (power_exact(re, im) >= a.pstar ? 1u : 0u) << q;
+        }
+    }
+    // four threads share a byte of decisions (warps 0..7 are complete; warp 8 has no outputs)
+    if (t < F2X_M / 2) {
+        const uint32_t b1 = __shfl_down_sync(0xFFFFFFFFu, bits2, 1);
+        const uint32_t b2 = __shfl_down_sync(0xFFFFFFFFu, bits2, 2);
+        const uint32_t b3 = __shfl_down_sync(0xFFFFFFFFu, bits2, 3);
+        const i64 o = m0 + 2 * t;
+        if ((t & 3) == 0 && o < a.out_hi) {
+            // outputs past out_hi inside the last byte are masked by the consumers
+            a.out_bits[(o - a.bit_base) >> 3] = (uint8_t) (bits2 | (b1 << 2) | (b2 << 4) | (b3 << 6));
+        }
+    }
+}
+
 // Same job, one THREAD per undecided group of 8 outputs m0..m0+7.  The 46 stage-1 outputs s[2 m0 + 15] .. s[2 m0 - 30]
 // the group needs are computed ONCE each (newest first, from a 16-sample register window that slides down by two
 // inputs per step) and fed to every output y[m] they belong to: walking u downwards visits the taps of each y[m] in

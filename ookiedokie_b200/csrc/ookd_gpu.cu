@@ -58,6 +58,7 @@ struct ookd_gpu {
     bool screen = false;
     bool persist = false;
     bool tma = false;                 // TMA-staged screening kernel (screen_tma.cuh)
+    bool screen2 = false;             // dec4 shape: screen + refine (else the exact tiled two-stage kernel)
     unsigned n_sm = 148;
 
     bool have_sm = false;
@@ -386,6 +387,20 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
         CU(h, cudaGetLastError());
         return OOKD_OK;
     }
+    if (h->path == FIR_SCREEN_DEC4 && !h->screen2) {
+        Taps2Param tp;
+        memcpy(tp.t1, h->stages[0].taps.data(), sizeof(tp.t1));
+        memcpy(tp.t2, h->stages[1].taps.data(), sizeof(tp.t2));
+        tp.d_t1 = h->stages[0].d_taps;
+        tp.d_t2 = h->stages[1].d_taps;
+        TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
+        a.out_lo = o_begin; a.out_hi = o_end;
+        const u64 tiles = (u64) (o_end - o_begin + F2X_M - 1) / F2X_M;
+        fir2_exact_tiled_kernel<<<(unsigned) tiles, F2X_NT, 0, h->s_compute>>>(a, tp);
+        h->launches++;
+        CU(h, cudaGetLastError());
+        return OOKD_OK;
+    }
     if (h->path == FIR_SCREEN_DEC4) {
         constexpr int L2 = 1024;                                        // outputs per tile of fir2_screen_kernel
         const u64 tiles = (u64) (o_end - o_begin + L2 - 1) / L2;
@@ -410,6 +425,7 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
 // Second pass of the screened path: exact recomputation of the groups the screen left undecided.
 int launch_fir_refine(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
 {
+    if (h->path == FIR_SCREEN_DEC4 && !h->screen2) return OOKD_OK;
     if (h->path == FIR_SCREEN_DEC4 && h->out_hi > h->bit_base) {
         Taps2Param tp;
         memcpy(tp.t1, h->stages[0].taps.data(), sizeof(tp.t1));
@@ -447,9 +463,8 @@ int run_generic_chain(ookd_gpu *h, const void *d_in, bool in_is_i16, i64 in_base
 int launch_fir_exact_all(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
 {
     if (h->path == FIR_SCREEN_DEC4) {
-        h->path = FIR_GENERIC;                                          // stop screening on this handle
-        return run_generic_chain(h, d_in, true, in_base, in_valid_end, h->bit_base, h->out_hi, nullptr,
-                                 (uint32_t *) h->bits.p, h->bit_base);
+        h->screen2 = false;                                             // stop screening on this handle
+        return launch_fir(h, d_in, in_base, in_valid_end, h->bit_base, h->out_hi);
     }
     TapsParam<32> tp;
     memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
@@ -1061,7 +1076,7 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
     uint32_t walk_complete = *(const uint32_t *) (hs + 44);
     h->stat_refined_blocks = refined;
     h->stat_dense_tiles = 0;
-    if ((h->screen || h->path == FIR_SCREEN_DEC4) && refined > h->work_cap) return OOKD_OK;      // work list overflowed
+    if ((h->screen || h->screen2) && refined > h->work_cap) return OOKD_OK;      // work list overflowed
     if (n_edges_total > h->pend.edge_cap || *(const uint32_t *) (hs + 28) != 0) return OOKD_OK;   // edge list / a tile region too small
     // The chain did not resolve within the burst (several consecutive chunks entered in a state no table holds
     // yet): keep the edges, anchors and tables and add rounds one at a time, each with its own link / walk /
@@ -1287,9 +1302,10 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
         }
     }
     const bool pstar_ok = h->pstar > 0.0f && h->pstar < 3.0e38f;
-    if (!(h->flags & (OOKD_FLAG_FORCE_GENERIC | OOKD_FLAG_NO_SCREEN)) && pstar_ok && h->stages.size() == 2 &&
+    if (!(h->flags & OOKD_FLAG_FORCE_GENERIC) && h->stages.size() == 2 &&
         h->stages[0].T == 16 && h->stages[0].D == 2 && h->stages[1].T == 32 && h->stages[1].D == 2) {
         h->path = FIR_SCREEN_DEC4;
+        h->screen2 = !(h->flags & OOKD_FLAG_NO_SCREEN) && pstar_ok;
     }
     h->n_sm = (unsigned) prop.multiProcessorCount;
     h->persist = (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) == 0;
@@ -1390,7 +1406,7 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     if ((rc = ensure(h, h->bits, (n_bits / 8 + 64 + 8) & ~7ull))) return rc;
 
     CU(h, cudaEventRecord(h->ev_t0, h->s_compute));
-    if (h->screen || h->path == FIR_SCREEN_DEC4) {
+    if (h->screen || h->screen2) {
         // work list for undecided 8-output groups: room for 1/8 of all groups (beyond that the capture is
         // mostly "near the threshold" and screening is pointless)
         const u64 groups = n_bits / 8 + 1;
@@ -1503,7 +1519,7 @@ int ookd_gpu_decode_end(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd_gp
         // everything fit and resolved behind a single synchronisation
     } else if (n_bits > 0) {
         if ((rc = extract_edges(h, n_bits, res))) return rc;
-        if ((h->screen || h->path == FIR_SCREEN_DEC4) && h->stat_refined_blocks > h->work_cap) {
+        if ((h->screen || h->screen2) && h->stat_refined_blocks > h->work_cap) {
             // too many undecided groups for the work list: redo the decisions exactly, extract the edges again,
             // and stop screening on this handle (the capture is not in the regime where it pays)
             h->stat_dense_tiles = 1;
