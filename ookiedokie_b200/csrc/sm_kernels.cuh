@@ -455,11 +455,15 @@ __device__ __forceinline__ int warp_sm_apply(const WarpSm &W, SmCarry &s, uint32
     if (action == OOKD_ACT_APPEND_0 || action == OOKD_ACT_APPEND_1) {
         if (s.num_bits <= W.max_bits && s.num_bits < 256) {
             const u64 m = 1ull << (s.num_bits & 63);
-            const uint32_t w = s.num_bits >> 6;
             const u64 set = (action == OOKD_ACT_APPEND_1) ? m : 0ull;
+            if (s.num_bits < 64) {                              // (uniform) the common case: one word
+                s.data[0] = (s.data[0] & ~m) | set;
+            } else {
+                const uint32_t w = s.num_bits >> 6;
 #pragma unroll
-            for (uint32_t i = 0; i < 4; i++) {
-                if (i == w) s.data[i] = (s.data[i] & ~m) | set;
+                for (uint32_t i = 1; i < 4; i++) {
+                    if (i == w) s.data[i] = (s.data[i] & ~m) | set;
+                }
             }
         }
         s.num_bits++;
@@ -660,8 +664,7 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
         const uint32_t k = s.k;
         const uint32_t b = tb ^ 1u;                                     // value of the edge sample
         const bool in_state = (W.t_state == s.state);
-        const u64 ke64 = (u64) k + g;
-        const uint32_t k_e = (ke64 < (u64) W.s_ksat) ? (uint32_t) ke64 : W.s_ksat;      // count at the edge sample
+        const uint32_t k_e = min(k + g, W.s_ksat);                      // count at the edge sample (k, g < 2^31)
         const bool mc = s.num_bits >= W.max_bits;
         const bool is_to = W.t_cond == OOKD_COND_TIMEOUT, is_mc = W.t_cond == OOKD_COND_MSG_COMPLETE;
         const bool is_quiet = W.t_cond == OOKD_COND_ALWAYS || is_to || is_mc;
@@ -677,7 +680,19 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
                             (is_to && W.s_ktimeout != OOKD_K_INF && k_e >= W.s_ktimeout) || (is_mc && mc);
         const bool e_ok = in_state && have_edge && k_e >= W.t_kmin && k_e <= W.t_kmax && cond_e;
         const uint32_t tau = (tau_q < g) ? tau_q : (e_ok ? g : OOKD_K_INF);
-        const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, tau);
+        // earliest offset, ties to the lowest lane (= list order): ONE reduction over (tau << 5 | lane); offsets
+        // beyond 2^27 - 2 samples (never in practice) take the two-step form
+        uint32_t m;
+        int f;
+        if (g < (1u << 27) - 1) {
+            const uint32_t key = (tau == OOKD_K_INF) ? 0xFFFFFFFFu : ((tau << 5) | lane);
+            const uint32_t best = __reduce_min_sync(0xFFFFFFFFu, key);
+            m = (best == 0xFFFFFFFFu) ? OOKD_K_INF : (best >> 5);
+            f = (int) (best & 31u);
+        } else {
+            m = __reduce_min_sync(0xFFFFFFFFu, tau);
+            f = (m == OOKD_K_INF) ? 0 : __ffs(__ballot_sync(0xFFFFFFFFu, tau == m)) - 1;
+        }
         if (m == OOKD_K_INF) {
             // nothing fires up to and including the edge sample
             const uint32_t ksat = __shfl_sync(0xFFFFFFFFu, W.ksat_by_state, (int) s.state);
@@ -693,8 +708,11 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
             }
             continue;
         }
-        const int f = __ffs(__ballot_sync(0xFFFFFFFFu, tau == m)) - 1;
-        const uint32_t pack = __shfl_sync(0xFFFFFFFFu, W.t_pack, f);
+        // the winner's (action, next state), and in bit 31 whether its state-duration check passes on the edge sample
+        const bool is_edge = (W.t_cond == OOKD_COND_PULSE_START || W.t_cond == OOKD_COND_PULSE_END);
+        const uint32_t dur_ok = (!is_edge || (k_e >= W.s_dmin && k_e <= W.s_dmax)) ? 0x80000000u : 0u;
+        const uint32_t packd = __shfl_sync(0xFFFFFFFFu, W.t_pack | dur_ok, f);
+        const uint32_t pack = packd & 0x7FFFFFFFu;
         if (m < g) {
             // a trigger that needs no edge fires inside the quiet stretch
             pos += m;
@@ -707,10 +725,8 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
             continue;
         }
         // fires on the edge sample, with count k_e
-        const bool is_edge = (W.t_cond == OOKD_COND_PULSE_START || W.t_cond == OOKD_COND_PULSE_END);
-        const uint32_t dur = __ballot_sync(0xFFFFFFFFu, !is_edge || (k_e >= W.s_dmin && k_e <= W.s_dmax));
         int r;
-        if ((dur >> f) & 1u) {
+        if (packd >> 31) {
             r = warp_sm_apply(W, s, pack);
         } else {
             r = -1;
