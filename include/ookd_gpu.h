@@ -161,6 +161,10 @@ struct ookd_gpu_config {
                                                 chunk of history (ookd_gpu_halo() grows accordingly) and
                                                 derive a provisional entry from it, so that multi-GPU time
                                                 shards normally need no second pass (see result.entry_used) */
+    uint32_t sm_burst_rounds;                /* state-machine rounds enqueued blindly behind the edge pass; 0 => default
+                                                (4).  A round that turns out not to be needed costs ~9 us, a missing
+                                                one a host synchronisation: raise it where the slowest of many shards
+                                                sets the pace (multi-GPU)                                            */
 };
 
 #define OOKD_FLAG_FORCE_GENERIC  1u          /* always use the shape-agnostic FIR kernels       */

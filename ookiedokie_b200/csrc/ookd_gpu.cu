@@ -54,6 +54,7 @@ struct ookd_gpu {
     float threshold = 0.1f, pstar = 0.0f;
     uint32_t spb = 8192;
     uint32_t chunk_buffers = 64;
+    uint32_t burst_rounds = 4;
     uint32_t flags = 0;
     bool screen = false;
     bool persist = false;
@@ -1003,7 +1004,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     CU(h, cudaMemsetAsync(h->tab_cnt[0].p, 0, sizeof(uint32_t) * nc, h->s_compute));
     int cur = 0;
     uint32_t rounds = 0;
-    for (uint32_t r = 0; r < FAST_BURST_ROUNDS; r++) {
+    for (uint32_t r = 0; r < h->burst_rounds; r++) {
         a.round = rounds;
         a.counter_idx = rounds & 31;
         if (rounds == 0) {
@@ -1066,8 +1067,9 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
     const char *hs = (const char *) h->h_scalars;
     if (getenv("OOKD_DEBUG")) {
         const uint32_t *nr = (const uint32_t *) (hs + 64);
-        fprintf(stderr, "[ookd] fast tail: ran %u/%u/%u/%u pairs in rounds 0..3, walks resolved %u, %u, %u, %u of %u chunks, overflow %u\n",
-                nr[0], nr[1], nr[2], nr[3], nr[16 + 0], nr[16 + 1], nr[16 + 2], nr[16 + 3], nc, *(const uint32_t *) (hs + 32));
+        fprintf(stderr, "[ookd] fast tail: ran %u/%u/%u/%u/%u/%u pairs in rounds 0..5, walks resolved %u, %u, %u, %u, %u, %u of %u chunks, overflow %u\n",
+                nr[0], nr[1], nr[2], nr[3], nr[4], nr[5], nr[16 + 0], nr[16 + 1], nr[16 + 2], nr[16 + 3], nr[16 + 4], nr[16 + 5], nc,
+                *(const uint32_t *) (hs + 32));
     }
     const u64 n_edges_total = *(const u64 *) hs;
     u64 n_msgs = *(const u64 *) (hs + 8);
@@ -1232,6 +1234,7 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     h->flags = cfg->flags;
     h->chunk_buffers = cfg->sm_chunk_buffers ? cfg->sm_chunk_buffers : 64;
     h->warmup = cfg->sm_warmup != 0;
+    h->burst_rounds = cfg->sm_burst_rounds ? (cfg->sm_burst_rounds < 16 ? cfg->sm_burst_rounds : 16) : FAST_BURST_ROUNDS;
 
 #define CREATE_FAIL(code)                                                                        \
     do { ookd_gpu_destroy(h); return (code); } while (0)
