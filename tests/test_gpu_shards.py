@@ -94,3 +94,52 @@ def test_warmup_history_gives_the_true_entry(devname, filt, spb):
     # an explicit (corrected) entry after a warm decode bypasses the warm-up chunk
     res_t, ex_t = g.resolve(prev_exit if False else res["entry_used"])
     assert res_t["msgs"] == res["msgs"] and ex_t == ex
+
+
+def test_shard_count_invariance_at_scale():
+    """BASELINE configs[3] in miniature, as a size-independent property: a 2^31-sample (8 GiB) continuous capture
+    synthesised on the device decodes to the same message list as ONE shard and as 2, 4 and 8 time shards
+    (FIR halo + warm-up history, no entry state given: each shard finds its own footing and its entry must equal
+    the predecessor's exit), and the edge lists concatenate to the single-shard list."""
+    import torch
+    from ookiedokie_b200 import host as H
+    free, _ = torch.cuda.mem_get_info()
+    if free < 24 << 30:
+        pytest.skip("needs ~20 GiB of device memory")
+    n = 1 << 31
+    fir = H.Fir("fs32_fs4")
+    dev = H.Device("p3l-nexa2012", util.FS)
+    msgs = [dev.message({"Channel": str(1 + i % 3), "Temperature (C)": f"{-20.0 + 0.1 * ((i * 37) % 900):.1f}"})
+            for i in range(n // 380000 + 8)]
+    tog, total = dev.toggles(msgs, 12000)
+    assert total >= n
+    d_iq = torch.empty((n * 2,), dtype=torch.int16, device="cuda")
+    B.synth(n, np.ascontiguousarray(tog), 1488, 1253, O.noise_scale_for_sigma(0.02), 0xBEEF, device_id=0,
+            device_ptr=d_iq.data_ptr())
+    torch.cuda.synchronize()
+    g1 = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=0.1, samples_per_buffer=8192)
+    g1.want_list = False
+    whole, _ = g1.decode_shard((d_iq.data_ptr(), n), 0, n, True, None)
+    _, whole_edges = g1.edges()
+    whole_edges = whole_edges.copy()
+    whole_msgs = whole["msgs_raw"].copy()
+    assert len(whole_msgs) > 4000
+    g1.close()
+    gw = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=0.1, samples_per_buffer=8192, sm_warmup=1)
+    gw.want_list = False
+    halo = gw.halo
+    for shards in (2, 4, 8):
+        per = n // shards
+        got_msgs, got_edges, prev_exit = [], [], None
+        for r in range(shards):
+            first = r * per
+            h = min(halo, first)
+            ptr = d_iq.data_ptr() + (first - h) * 4
+            res, ex = gw.decode_shard((ptr, h + per), first, per, r == shards - 1, None)
+            if r > 0:
+                assert tuple(res["entry_used"]) == tuple(prev_exit), (shards, r)
+            got_msgs.append(res["msgs_raw"].copy())
+            got_edges.append(gw.edges()[1].copy())
+            prev_exit = ex
+        assert np.array_equal(np.concatenate(got_msgs), whole_msgs), shards
+        assert np.array_equal(np.concatenate(got_edges), whole_edges), shards
