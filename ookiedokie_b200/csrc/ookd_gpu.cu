@@ -304,6 +304,10 @@ ScreenArgs screen_args(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_va
     return sa;
 }
 
+#ifndef OOKD_STMA_L2_PROMOTION
+#define OOKD_STMA_L2_PROMOTION CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+#endif
+
 // TMA-staged screening kernel (screen_tma.cuh) over `tiles` tiles of 4096 INPUT samples starting at tile
 // sa.tile_offset (tiles are numbered from h->bit_base in units of 4096 / dec outputs).
 int launch_screen_tma(ookd_gpu *h, const ScreenArgs &sa, const ScreenParams &sp, const uint32_t *d_in, i64 in_base,
@@ -328,7 +332,7 @@ int launch_screen_tma(ookd_gpu *h, const ScreenArgs &sa, const ScreenParams &sp,
         const cuuint32_t estr[2] = {1, 1};
         ok = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void *) addr0, gdim, gstride, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                                  OOKD_STMA_L2_PROMOTION, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     }
     ta.row0_sample = row0;
     if (ok) {

@@ -49,6 +49,9 @@ constexpr int STMA_XY_ROWS = STMA_NT + STMA_HT_MAX;
 constexpr int STMA_SMEM_BYTES = STMA_STAGES * STMA_BODY + STMA_STAGES * STMA_HIST + STMA_STAGES * STMA_XY_ROWS * 8 + 32;
 static_assert(4 * (STMA_SMEM_BYTES + 1024) <= 228 * 1024, "four CTAs per SM");
 
+#ifndef OOKD_STMA_L2_HINT
+#define OOKD_STMA_L2_HINT 0x12F0000000000000ull     /* evict-first (0x1000000000000000 = normal, 0x14F0000000000000 = evict-last) */
+#endif
 #ifndef OOKD_STMA_MINB
 #define OOKD_STMA_MINB 4
 #endif
@@ -87,7 +90,7 @@ __device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap *m
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst), "l"((uint64_t) map), "r"(bar), "r"(0), "r"(row),
-        "l"(0x12F0000000000000ull)
+        "l"(OOKD_STMA_L2_HINT)
         : "memory");
 }
 
