@@ -333,6 +333,30 @@ def main():
             acc[4] += runner.host_syncs
             out[0], out[1] = res, msgs
 
+        if depth == 1 and world > 1 and len(gpus) > 1:
+            # One decode at a time on the GPU, but the cross-rank stitch of step i (host only: shared-memory exchange,
+            # waiting for the slowest rank) runs while the GPU already works on step i+1 -- the next window is enqueued
+            # on the other handle AFTER this one has completed, so device work never overlaps.
+            def finish_decoded(runner, decoded):
+                res, exit_c, rounds, msgs = S.stitch_and_gather(runner, rank, world, decoded=decoded)
+                acc[0] += runner.launches
+                acc[1] += runner.fir_ms
+                acc[2] += runner.screen_ms
+                acc[3] += runner.kernel_ms
+                acc[4] += runner.host_syncs
+                out[0], out[1] = res, msgs
+
+            cur = S.GpuShardRunner(gpus[0], iq_arg, first, n, last)
+            cur.begin()
+            for i in range(n_steps):
+                decoded = cur.decode(None)                    # waits for step i
+                nxt = None
+                if i + 1 < n_steps:
+                    nxt = S.GpuShardRunner(gpus[(i + 1) % 2], iq_arg, first, n, last)
+                    nxt.begin()
+                finish_decoded(cur, decoded)
+                cur = nxt
+            return out[0], out[1], acc
         for i in range(n_steps):
             runner = S.GpuShardRunner(gpus[i % depth], iq_arg, first, n, last)
             runner.begin()
@@ -447,6 +471,8 @@ def main():
             "config": {"workload": workload_name(n), "samples_per_gpu": n, "device": DEVICE_NAME, "filter": FILTER_NAME,
                        "parallelism": f"time-shards x{world}" if world > 1 else "single shard",
                        "pipeline_depth": depth,
+                       "stitch": ("host-side exchange of step i overlaps the decode of step i+1" if world > 1 and depth == 1
+                                  else "n/a" if world == 1 else "inside each step"),
                        "l2": "input shard (4 B/sample) larger than L2; no flush needed",
                        "messages_decoded": n_msgs, "messages_transmitted_upper_bound": n_tx_msgs,
                        "edges_last_rank": n_edges, "sm_rounds": sm_rounds},

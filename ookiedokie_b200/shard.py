@@ -157,13 +157,15 @@ def _shm_exchange(rank, world):
     return _shm[key]
 
 
-def stitch_and_gather(runner, rank, world, msg_cap=None):
+def stitch_and_gather(runner, rank, world, msg_cap=None, decoded=None):
     """stitch() + gather_messages_raw() with ONE collective in the common case: every rank ships its
     carry record together with its (padded) message block; if the records are consistent the job is done.
     The block is sized from the largest per-rank message count of the previous call (every rank saw the same
     counts, so every rank picks the same size).  Returns (result, exit, rounds, messages on rank 0 | None)."""
     from .binding import MSG_DTYPE
-    res, exit_c = runner.decode(None)
+    # decoded = (result, exit) of runner.decode(None) when the caller has already waited for the decode (so that it
+    # could enqueue the next window before the cross-rank exchange of this one)
+    res, exit_c = decoded if decoded is not None else runner.decode(None)
     if world == 1:
         return res, exit_c, 1, res["msgs_raw"]
     entry_used = tuple(res["entry_used"])
