@@ -967,21 +967,53 @@ __global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(con
     }
     if (lane == 0) atomicAdd(&a.n_ran[a.counter_idx], 1u);
 
-    SpanOut o;
-    o.slots = a.slots + ((u64) c * K + slot) * a.slot_cap;
-    o.cap = a.slot_cap;
-    o.n_msgs = 0;
-    o.overflow = a.overflow;
-    if (warp_ok) {
-        warp_sm_run_span(a, n_edges, W, s, pos, end, e, tb, o, lo, lane);
-        if (lane != 0) return;
-    } else {
-        sm_run_span<false>(a, n_edges, T, s, pos, end, e, tb, o, lo);
+    // Run the chunk; in a repair round (>= 1) keep going: if the exit is not yet an entry of the NEXT chunk either,
+    // the same warp adds that pair too and runs on.  A cascade of consecutive chunks entered in a state no table
+    // holds (e.g. a string of messages lost to dropped buffers) is then repaired in ONE round -- its cost is the
+    // chain itself -- instead of one round, link and walk per chunk.
+    uint32_t cc = c;
+    for (int hop = 0;; hop++) {
+        SpanOut o;
+        o.slots = a.slots + ((u64) cc * K + slot) * a.slot_cap;
+        o.cap = a.slot_cap;
+        o.n_msgs = 0;
+        o.overflow = a.overflow;
+        if (warp_ok) {
+            warp_sm_run_span(a, n_edges, W, s, pos, end, e, tb, o, lo, lane);
+        } else {
+            sm_run_span<false>(a, n_edges, T, s, pos, end, e, tb, o, lo);
+        }
+        if (lane == 0) {
+            a.tab_entry[(u64) cc * K + slot] = entry;
+            a.tab_exit[(u64) cc * K + slot] = s;
+            a.tab_nmsg[(u64) cc * K + slot] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
+        }
+        if (a.round == 0 || !warp_ok || hop >= 16 || cc + 1 >= a.n_chunks) return;
+        // (all lanes hold the same carry; memory reads below are uniform)
+        const uint32_t nn = cc + 1;
+        const uint32_t n_next = a.cnt_in[nn];                // entries that were complete before this round
+        bool known = false;
+        for (uint32_t i = 0; i < n_next; i++) {
+            if (carry_equal(s, a.tab_entry[(u64) nn * K + i])) { known = true; break; }
+        }
+        if (known) return;
+        uint32_t nslot = 0;
+        if (lane == 0) nslot = atomicAdd(&a.cnt_out[nn], 1u);
+        nslot = __shfl_sync(0xFFFFFFFFu, nslot, 0);
+        if (nslot >= K) {
+            if (lane == 0) atomicExch(a.overflow, 2u);      // table full: host falls back
+            return;
+        }
+        if (lane == 0) atomicAdd(&a.n_ran[a.counter_idx], 1u);
+        cc = nn;
+        slot = nslot;
+        entry = s;
+        chunk_bounds(a, cc, start, end, lo);
+        if ((end - lo) >= (1ll << 31)) return;               // (cannot happen when the first chunk passed the check)
+        pos = start;
+        e = a.chunk_e[cc];
+        tb = base_bit ^ (uint32_t) (e & 1);
     }
-
-    a.tab_entry[(u64) c * K + slot] = entry;
-    a.tab_exit[(u64) c * K + slot] = s;
-    a.tab_nmsg[(u64) c * K + slot] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
 }
 
 // Resolve: a corrected entry for chunk 0 (the shard's true entry state arrived from the previous
