@@ -1,8 +1,10 @@
 // ookd_gpu.cu -- C ABI of the sm_100a receive path (include/ookd_gpu.h).
 //
 // One handle = one CUDA device + two streams (copy, compute) + grow-only workspaces.
-// A decode is:  [H2D pieces ->] FIR/threshold kernel(s) -> edge count / scan / write ->
-// state-machine rounds -> message gather -> D2H of the (tiny) message list.
+// A decode is:  [H2D pieces ->] screening kernel -> exact refine of the undecided groups -> edge extraction ->
+// anchors -> state-machine rounds with link / walk -> message gather -> D2H of the (tiny) message list,
+// all enqueued behind one another with ONE host synchronisation at the end (decode_tail_fast_*); whatever
+// does not fit or resolve is repeated on the synchronous path (extract_edges / run_state_machine).
 // There is no CPU fallback anywhere in this file: without a usable device every compute
 // entry point returns OOKD_ERR_CUDA.
 #include <cstdarg>

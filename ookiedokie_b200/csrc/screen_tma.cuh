@@ -1,4 +1,5 @@
-// screen_tma.cuh -- production form of the one-stage (T = 32, decimation 1) screening kernel.
+// screen_tma.cuh -- production form of the screening kernels: fir_screen_tma_kernel<1> for the one-stage shape
+// (T = 32, decimation 1) and <4> for the two-stage 16/2 + 32/2 shape (fs128_fs16_dec4).
 //
 // Same decisions as fir1_screen_kernel / fir1_screen_persist_kernel (fir_kernels.cuh, section 3: the
 // Cauchy-Schwarz "off" proof on exact integer window energies, the mean/scatter "on" proof, everything
@@ -18,10 +19,10 @@
 // 4 LDS.128 (prefix row of thread u-2) + one word of thread u-1, decisions.  After the barrier thread 0
 // re-arms the stage freed by the previous tile and issues the copy of tile i+2.
 //
-// The two prefix rows in front of a tile (threads u-2, u-1 for u = 0, 1) live in a 128-byte "row -1" per
-// stage (virtual threads -2, -1, same address formula); the last two threads of tile i write theirs into
-// the history row of stage (i+1) % 3 as well, which nobody reads before the barrier of tile i+1 and
-// nobody rewrites before tile i+3.
+// The prefix rows in front of a tile (threads u-k for u < k; k <= 2 for <1>, k <= 5 for <4>) live in "rows -3..-1"
+// per stage (virtual threads -5..-1, same address formula); the last threads of tile i write theirs into the
+// history rows of stage (i+1) % 3 as well, which nobody reads before the barrier of tile i+1 and nobody
+// rewrites before tile i+3.
 //
 // Tiles the tensor copy cannot serve (capture start/end, input not 16-byte aligned) take guarded
 // scalar loads into the same registers; everything after that is identical.

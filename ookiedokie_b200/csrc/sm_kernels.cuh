@@ -10,19 +10,21 @@
 // twice, :526-538) and the first sample after a dropped buffer tail (prev_bit is stale there,
 // :549-552) take the single-sample path, which mirrors handle_rx_triggers one to one.
 //
-// Parallel form.  The output stream is cut into chunks of whole buffers.  The machine's state at a
-// chunk boundary depends on everything before it, so each chunk keeps a small TABLE of
-// (entry state -> exit state, messages) pairs, one thread per pair:
-//   round 0   one speculative seed per chunk: RESET at the chunk's first "anchor" (first rising edge
-//             from which a fresh machine appends a bit, i.e. a plausible message start; the 32 lanes
-//             of the warp probe 32 candidate edges at once), or RESET at the chunk's first sample when
-//             it has none; chunk 0 runs from the true entry;
-//   round r   every exit in chunk c-1's table that is not yet an entry of chunk c's table is run;
-//   link/walk exits are matched to the next chunk's entries and one thread walks the chain from
-//             chunk 0's true entry.  If the walk reaches the last chunk the decode is resolved:
-//             the chosen pairs ARE the sequential run, because each pair is the deterministic
+// Parallel form.  The output stream is cut into chunks of whole buffers, and each chunk's boundary is then MOVED to
+// the chunk's first "anchor" (first rising edge from which a fresh machine appends a bit, i.e. a plausible message
+// start; sm_anchor_kernel, 32 lanes probe 32 candidate edges at once).  The machine's state at a boundary depends
+// on everything before it, so each chunk keeps a small TABLE of (entry state -> exit state, messages) pairs, one
+// warp per pair (lane j owns trigger j: warp_sm_*):
+//   round 0   one speculative seed per chunk: the idle machine (ookd_sm_idle_carry) at the anchor, as a real
+//             entry -- the truth is normally idle when a message starts -- or RESET at the chunk's first sample
+//             when it has no anchor; chunk 0 runs from the true entry;
+//   round r   every exit in chunk c-1's table that is not yet an entry of chunk c's table is run, and the warp
+//             runs on into the following chunks while its exit is still unknown there (cascades);
+//   link/walk exits are matched to the next chunk's entries and the chain is walked from chunk 0's true entry
+//             (links composed over segments in parallel).  If the walk reaches the last chunk the decode is
+//             resolved: the chosen pairs ARE the sequential run, because each pair is the deterministic
 //             function of its entry.  Otherwise another round adds the missing entries.
-// A Jacobi relaxation over single exits (sm_round_kernel: re-run exactly the chunks whose entry
+// A Jacobi relaxation over single exits (sm_round_kernel, fixed boundaries: re-run exactly the chunks whose entry
 // changed until nothing changes) is kept as the always-terminating fallback.
 //
 // Counts k saturate per state at ksat = 1 + (largest finite bound any predicate of that state
