@@ -297,7 +297,7 @@ def main():
     flags = args.flags | (B.FLAG_SHARE_SMS if args.share else 0)
     gpus = [B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
                   flags=flags, sm_chunk_buffers=args.chunk_buffers, sm_warmup=1 if world > 1 else 0,
-                  sm_burst_rounds=(4 if world > 1 else 0))   # the slowest shard sets the pace: one more blind round
+                  sm_burst_rounds=(3 if world > 1 else 0))   # the slowest shard sets the pace: one more blind round
             for _ in range(n_handles)]
     gpu = gpus[0]
     n = args.samples

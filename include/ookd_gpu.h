@@ -162,7 +162,7 @@ struct ookd_gpu_config {
                                                 derive a provisional entry from it, so that multi-GPU time
                                                 shards normally need no second pass (see result.entry_used) */
     uint32_t sm_burst_rounds;                /* state-machine rounds enqueued blindly behind the edge pass; 0 => default
-                                                (3).  A round that turns out not to be needed costs ~9 us, a missing
+                                                (2: the seed round and one repair round, which chases cascades).  A round that turns out not to be needed costs ~9 us, a missing
                                                 one a host synchronisation: raise it where the slowest of many shards
                                                 sets the pace (multi-GPU)                                            */
 };

@@ -56,7 +56,7 @@ struct ookd_gpu {
     float threshold = 0.1f, pstar = 0.0f;
     uint32_t spb = 8192;
     uint32_t chunk_buffers = 64;
-    uint32_t burst_rounds = 3;
+    uint32_t burst_rounds = 2;
     uint32_t flags = 0;
     bool screen = false;
     bool persist = false;
@@ -901,9 +901,9 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
 // three rounds) sets *done = false and the caller repeats the tail on the synchronous path, which handles
 // every such case.
 // Rounds enqueued blindly behind the edge pass.  Round 0 resolves the chain when every chunk is entered idle at its
-// anchor; each further round repairs one more consecutive chunk entered in another state.  A round that is not
-// needed costs ~9 us (three kernels that return at once), a missing one costs a synchronisation.
-constexpr uint32_t FAST_BURST_ROUNDS = 3;
+// anchor; round 1 repairs the chunks entered in another state and runs on through cascades of them.  A round that
+// is not needed costs ~9 us (three kernels that return at once), a missing one costs a synchronisation.
+constexpr uint32_t FAST_BURST_ROUNDS = 2;
 
 // arguments of the state-machine kernels on the single-synchronisation path (edge count / base bit from the
 // device-side header)
