@@ -797,7 +797,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
             CU(h, cudaGetLastError());
             rounds = 1;
         } else {
-            CU(h, cudaMemsetAsync(h->tab_cnt[0].p, 0, sizeof(uint32_t) * nc, h->s_compute));
+            fill_u32_kernel<<<(nc + 255) / 256, 256, 0, h->s_compute>>>((uint32_t *) h->tab_cnt[0].p, nc, 1u);     // slot 0 = the seed
         }
         for (;;) {
             // round 0 (seeds) and round 1 (predecessors' exits) back to back, later rounds one at a time;
@@ -1007,7 +1007,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     SmArgs a = fast_sm_args(h, entry0);
     sm_anchor_kernel<<<nc, 32, 0, h->s_compute>>>(a);
     h->launches++;
-    CU(h, cudaMemsetAsync(h->tab_cnt[0].p, 0, sizeof(uint32_t) * nc, h->s_compute));
+    fill_u32_kernel<<<(nc + 255) / 256, 256, 0, h->s_compute>>>((uint32_t *) h->tab_cnt[0].p, nc, 1u);     // slot 0 = the seed
     int cur = 0;
     uint32_t rounds = 0;
     for (uint32_t r = 0; r < h->burst_rounds; r++) {

@@ -815,6 +815,12 @@ __device__ __forceinline__ void carry_reset(SmCarry &s, uint32_t prev)
     const u64 n_edges = (a).hdr ? (a).hdr->n_edges : (a).n_edges;                               \
     const uint32_t base_bit = (a).hdr ? (a).hdr->base_bit : (a).base_bit;
 
+__global__ void fill_u32_kernel(uint32_t *p, uint32_t n, uint32_t v)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 // Anchors, once per decode.  One warp per chunk: the chunk's first "anchor" is the first rising edge from which
 // a freshly reset machine gets as far as appending a bit, i.e. a plausible message start (the 32 lanes probe 32
 // candidate edges at once).  The true run, whatever it did before, is normally idle when a message starts, so
@@ -943,8 +949,7 @@ __global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(con
             carry_reset(s, tb);
             entry = s;
         }
-        slot = 0;
-        if (lane == 0) a.cnt_out[c] = 1;
+        slot = 0;                                            // (every chunk's count starts at 1: the seed's slot)
     } else {
         if (!warp_ok && lane != 0) return;
         if (c == 0) return;
@@ -969,7 +974,7 @@ __global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(con
     }
     if (lane == 0) atomicAdd(&a.n_ran[a.counter_idx], 1u);
 
-    // Run the chunk; in a repair round (>= 1) keep going: if the exit is not yet an entry of the NEXT chunk either,
+    // Run the chunk, and keep going: if the exit is not an entry of the NEXT chunk (round 0: not that chunk's seed),
     // the same warp adds that pair too and runs on.  A cascade of consecutive chunks entered in a state no table
     // holds (e.g. a string of messages lost to dropped buffers) is then repaired in ONE round -- its cost is the
     // chain itself -- instead of one round, link and walk per chunk.
@@ -990,13 +995,25 @@ __global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(con
             a.tab_exit[(u64) cc * K + slot] = s;
             a.tab_nmsg[(u64) cc * K + slot] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
         }
-        if (a.round == 0 || !warp_ok || hop >= 16 || cc + 1 >= a.n_chunks) return;
+        if (!warp_ok || hop >= 16 || cc + 1 >= a.n_chunks) return;
         // (all lanes hold the same carry; memory reads below are uniform)
         const uint32_t nn = cc + 1;
-        const uint32_t n_next = a.cnt_in[nn];                // entries that were complete before this round
         bool known = false;
-        for (uint32_t i = 0; i < n_next; i++) {
-            if (carry_equal(s, a.tab_entry[(u64) nn * K + i])) { known = true; break; }
+        if (a.round == 0) {
+            // the only entry chunk nn has (or is getting right now, from its own warp) is its seed
+            const uint32_t kind = a.seed_kind[nn];
+            if (kind == OOKD_SEED_CANON) {
+                known = carry_equal(s, a.canon);
+            } else if (kind == OOKD_SEED_RESET) {
+                SmCarry r;
+                carry_reset(r, base_bit ^ (uint32_t) (a.seed_e[nn] & 1));
+                known = carry_equal(s, r);
+            }                                                // OOKD_SEED_ANCHOR: its entry matches nothing
+        } else {
+            const uint32_t n_next = a.cnt_in[nn];            // entries that were complete before this round
+            for (uint32_t i = 0; i < n_next; i++) {
+                if (carry_equal(s, a.tab_entry[(u64) nn * K + i])) { known = true; break; }
+            }
         }
         if (known) return;
         uint32_t nslot = 0;
