@@ -168,8 +168,9 @@ struct ookd_gpu_config {
 };
 
 #define OOKD_FLAG_FORCE_GENERIC  1u          /* always use the shape-agnostic FIR kernels       */
-#define OOKD_FLAG_TILE_PER_CTA_SCREEN 4u     /* one-tile-per-CTA form of the screening kernel instead of the
-                                                persistent, register-prefetching default                        */
+#define OOKD_FLAG_TILE_PER_CTA_SCREEN 4u     /* earliest forms, kept for cross-checking: one-tile-per-CTA screening
+                                                kernel and lane-per-output refine kernels instead of the persistent
+                                                TMA-staged screen and the group-per-thread refine                  */
 #define OOKD_FLAG_NO_TMA         8u          /* persistent screening kernel with register prefetch instead of the
                                                 TMA-staged default                                */
 #define OOKD_FLAG_SYNC_TAIL      16u         /* edges / state machine with a host synchronisation between the
@@ -177,8 +178,8 @@ struct ookd_gpu_config {
 #define OOKD_FLAG_SHARE_SMS      32u         /* pipelined use (several handles with a decode in flight on one
                                                 device): the persistent screening kernel takes three quarters of
                                                 each SM so that the other decode's tail kernels can run beside it */
-#define OOKD_FLAG_NO_SCREEN      2u          /* disable the reduced-precision screen (exact MACs
-                                                for every sample)                                */
+#define OOKD_FLAG_NO_SCREEN      2u          /* no screening: the exact tiled kernels compute every output with the
+                                                reference's in-order MACs (same decisions, fp32-issue bound)        */
 
 struct ookd_gpu_result {
     uint64_t n_in;                           /* input samples consumed incl. EOF zero padding   */
