@@ -178,6 +178,8 @@ struct ookd_gpu_config {
 #define OOKD_FLAG_SHARE_SMS      32u         /* pipelined use (several handles with a decode in flight on one
                                                 device): the persistent screening kernel takes three quarters of
                                                 each SM so that the other decode's tail kernels can run beside it */
+#define OOKD_FLAG_NO_GRAPH       64u         /* enqueue the decode tail (edges, state machine, gather, read-back)
+                                                operation by operation instead of replaying its CUDA graph      */
 #define OOKD_FLAG_NO_SCREEN      2u          /* no screening: the exact tiled kernels compute every output with the
                                                 reference's in-order MACs (same decisions, fp32-issue bound)        */
 

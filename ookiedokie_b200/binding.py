@@ -24,6 +24,7 @@ FLAG_TILE_PER_CTA_SCREEN = 4
 FLAG_NO_TMA = 8
 FLAG_SYNC_TAIL = 16
 FLAG_SHARE_SMS = 32
+FLAG_NO_GRAPH = 64
 
 # every symbol include/ookd_gpu.h declares
 EXPORTS = [

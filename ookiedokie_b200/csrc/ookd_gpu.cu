@@ -102,6 +102,13 @@ struct ookd_gpu {
     uint32_t stat_refined_blocks = 0, stat_dense_tiles = 0;
     uint32_t work_cap = 0;
 
+    // the single-synchronisation tail as a CUDA graph: captured once per geometry, replayed with one launch
+    cudaGraphExec_t tail_graph = nullptr;
+    std::vector<u64> tail_key;
+    uint32_t tail_rounds = 0, tail_launches = 0;
+    int tail_cur = 0;
+    bool tail_graph_off = false;
+
     // a decode between ookd_gpu_decode_begin and ookd_gpu_decode_end
     struct Pending {
         bool active = false, fast = false;
@@ -957,10 +964,12 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     if ((rc = ensure(h, h->slots, sizeof(SmMsg) * (size_t) nc * TAB_K * h->slot_cap))) return rc;
     const u64 msg_cap = (u64) nc * h->slot_cap;                       // at most slot_cap messages per chunk are kept
     if ((rc = ensure(h, h->msgs_dev, sizeof(SmMsg) * msg_cap))) return rc;
-    u64 n_copy = h->last_n_msgs + h->last_n_msgs / 4 + 1024;         // messages copied back speculatively
+    u64 n_copy = 1024;                                               // messages copied back speculatively:
+    while (n_copy < h->last_n_msgs + h->last_n_msgs / 4 + 512) n_copy *= 2;   // a power of two (stable graph key)
     if (n_copy > msg_cap) n_copy = msg_cap;
     if (h->h_msgs_pin_cap < n_copy) {
         if (h->h_msgs_pin) cudaFreeHost(h->h_msgs_pin);
+    if (h->tail_graph) cudaGraphExecDestroy(h->tail_graph);
         h->h_msgs_pin = nullptr;
         h->h_msgs_pin_cap = 0;
         CU(h, cudaHostAlloc((void **) &h->h_msgs_pin, sizeof(SmMsg) * n_copy, cudaHostAllocDefault));
@@ -982,15 +991,29 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     x.cap = h->edges.cap / sizeof(u64);
     x.hdr = (u64 *) ((char *) h->scalars.p + 256);
     x.report_word = (i64) (((u64) (h->report_lo - h->bit_base)) >> 6);
+    // ---- state machine arguments ----
+    h->tables_valid = false;
+    h->first_chunk = 0;
+    h->entry_used = entry0;
+    h->n_edges = 0;
+    h->base_bit = 0;
+    SmArgs a = fast_sm_args(h, entry0);
+    int cur = 0;
+    uint32_t rounds = 0;
+
+    static const int edge_ctas_per_sm = []() {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, edge_local_kernel, EDGE_NT, 0) != cudaSuccess || n < 1) n = 1;
+        return n;
+    }();
+
+    // everything below is one fixed sequence of stream operations for a given geometry and set of buffers
+    auto enqueue_ops = [&]() -> int {
+    cur = 0;
+    rounds = 0;
     CU(h, cudaMemsetAsync((char *) h->scalars.p + 24, 0, 232, h->s_compute));      // [24, 256): keeps the refine counters
     {
-        static int per_sm = 0;
-        if (per_sm == 0) {
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, edge_local_kernel, EDGE_NT, 0) != cudaSuccess || per_sm < 1) {
-                per_sm = 1;
-            }
-        }
-        const unsigned ctas = h->n_sm * (unsigned) per_sm;
+        const unsigned ctas = h->n_sm * (unsigned) edge_ctas_per_sm;
         edge_local_kernel<<<eg < ctas ? eg : ctas, EDGE_NT, 0, h->s_compute>>>(x);
         scan_u32_kernel<<<1, SCAN_NT, 0, h->s_compute>>>(x.e.block_counts, eg, (u64 *) h->scalars.p);
         edge_flatten_kernel<<<eg, 128, 0, h->s_compute>>>(x);
@@ -999,17 +1022,9 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     }
 
     // ---- state machine burst ----
-    h->tables_valid = false;
-    h->first_chunk = 0;
-    h->entry_used = entry0;
-    h->n_edges = 0;
-    h->base_bit = 0;
-    SmArgs a = fast_sm_args(h, entry0);
     sm_anchor_kernel<<<nc, 32, 0, h->s_compute>>>(a);
     h->launches++;
     fill_u32_kernel<<<(nc + 255) / 256, 256, 0, h->s_compute>>>((uint32_t *) h->tab_cnt[0].p, nc, 1u);     // slot 0 = the seed
-    int cur = 0;
-    uint32_t rounds = 0;
     for (uint32_t r = 0; r < h->burst_rounds; r++) {
         a.round = rounds;
         a.counter_idx = rounds & 31;
@@ -1048,6 +1063,64 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     }
     if (h->warm) {
         CU(h, cudaMemcpyAsync((char *) h->h_scalars + 288, h->final_entry.p, sizeof(SmCarry), cudaMemcpyDeviceToHost, h->s_compute));
+    }
+    return OOKD_OK;
+    };
+
+    // ---- replay the captured graph when nothing it depends on has changed; capture it otherwise ----
+    bool launched = false;
+    if (!h->tail_graph_off && !(h->flags & OOKD_FLAG_NO_GRAPH)) {
+        std::vector<u64> key;
+        auto add = [&](u64 v) { key.push_back(v); };
+        add(n_bits); add(nc); add(eg); add(h->burst_rounds); add(msg_cap); add(n_copy); add((u64) h->bit_base); add(h->pre);
+        add((u64) h->report_lo); add((u64) h->out_lo); add((u64) h->out_hi); add(h->first_buffer); add(h->spb);
+        add(h->total_dec); add(h->chunk_buffers); add(h->warm ? 1 : 0); add(h->slot_cap); add(x.cap); add(h->n_sm);
+        add(entry0.state); add(entry0.k); add(entry0.num_bits); add(entry0.prev);
+        for (int i = 0; i < 4; i++) add(entry0.data[i]);
+        const void *ptrs[] = {h->bits.p, h->edges.p, h->block_counts.p, h->edge_tmp.p, h->scalars.p, h->h_scalars, h->h_msgs_pin,
+                              h->msgs_dev.p, h->slots.p, h->slot_count.p, h->slot_off.p, h->tab_entry.p, h->tab_exit.p,
+                              h->tab_nmsg.p, h->tab_cnt[0].p, h->tab_cnt[1].p, h->tab_link.p, h->tab_chosen.p, h->final_entry.p,
+                              h->chunk_e.p, h->bound_pos.p, h->seed_pos.p, h->seed_e.p, h->seed_kind.p, h->d_tab};
+        for (const void *q : ptrs) add((u64) (uintptr_t) q);
+        if (h->tail_graph && key == h->tail_key) {
+            CU(h, cudaGraphLaunch(h->tail_graph, h->s_compute));
+            cur = h->tail_cur;
+            rounds = h->tail_rounds;
+            h->launches += h->tail_launches;
+            launched = true;
+        } else {
+            if (h->tail_graph) {
+                cudaGraphExecDestroy(h->tail_graph);
+                h->tail_graph = nullptr;
+            }
+            const uint32_t launches_before = h->launches;
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(h->s_compute, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int orc = enqueue_ops();
+                const cudaError_t ec = cudaStreamEndCapture(h->s_compute, &graph);
+                ok = (orc == OOKD_OK) && ec == cudaSuccess && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&h->tail_graph, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (ok) {
+                h->tail_key = key;
+                h->tail_cur = cur;
+                h->tail_rounds = rounds;
+                h->tail_launches = h->launches - launches_before;
+                CU(h, cudaGraphLaunch(h->tail_graph, h->s_compute));
+                launched = true;
+            } else {
+                // graphs unavailable for this sequence: plain enqueueing from now on
+                cudaGetLastError();
+                h->tail_graph = nullptr;
+                h->tail_graph_off = true;
+                h->launches = launches_before;
+            }
+        }
+    }
+    if (!launched) {
+        if ((rc = enqueue_ops())) return rc;
     }
     CU(h, cudaEventRecord(h->ev_t1, h->s_compute));
     h->pend.e0 = entry0;                                   // (count canonicalised above)

@@ -241,7 +241,7 @@ def test_every_code_path_gives_the_same_decode(devname, filt):
     stages = O.load_filter(filt)
     ref = O.rx(iq, stages, dev, samples_per_buffer=8192, want_bits=True)
     for flags in (0, B.FLAG_SYNC_TAIL, B.FLAG_NO_TMA, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_SHARE_SMS,
-                  B.FLAG_FORCE_GENERIC, B.FLAG_NO_TMA | B.FLAG_SYNC_TAIL):
+                  B.FLAG_FORCE_GENERIC, B.FLAG_NO_TMA | B.FLAG_SYNC_TAIL, B.FLAG_NO_GRAPH):
         for chunk_buffers in (0, 5):
             g = B.Gpu(filter_stages=stages, sm=util.sm_spec(dev, stages), threshold=0.1, samples_per_buffer=8192, flags=flags,
                       sm_chunk_buffers=chunk_buffers)
@@ -270,3 +270,19 @@ def test_two_decodes_in_flight():
             assert res["msgs"] == want[i]
     with pytest.raises(B.OokdError):
         gpus[0].decode_end()                                           # nothing in flight
+
+
+def test_graph_replay_across_different_captures_of_one_shape():
+    """The decode tail is captured into a CUDA graph once per geometry and replayed: same-length captures with
+    different contents (and a different length in between, which re-captures) must each decode like the oracle."""
+    dev = O.load_device("p3l-nexa2012")
+    stages = O.load_filter("fs32_fs4")
+    g = B.Gpu(filter_stages=stages, sm=util.sm_spec(dev, stages), threshold=0.1, samples_per_buffer=8192)
+    base = [util.capture(dev, 5, sigma=0.02, phase=0.2 * i, seed=300 + i, fields=util.nexa_fields)[0] for i in range(4)]
+    n = min(len(c) for c in base)
+    caps = [c[:n] for c in base] + [base[0][: n - 50000]] + [c[:n] for c in base[:2]]
+    for c in caps:
+        want = O.rx(c, stages, dev, samples_per_buffer=8192)
+        got = g.decode(c)
+        assert got["msgs"] == want["msgs"]
+        assert np.array_equal(g.edges()[1], want["edges"])

@@ -25,7 +25,7 @@ for i in range(n_caps):
     B.synth(n, np.ascontiguousarray(tog), 1488, 1253, int(round(sigma * 2048 / ih4 * (1 << 24))), 1000 + i, device_ptr=d.data_ptr())
     bufs.append(d)
 torch.cuda.synchronize()
-for per in (4, 8, 16):
+for per in (2, 4, 8):
     gpus = []
     for kind in range(2):
         for _ in range(per):
