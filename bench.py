@@ -40,7 +40,7 @@ UNIT = "Msamples/s"
 
 def workload_name(samples):
     return (f"{DEVICE_NAME} + {FILTER_NAME}, {samples * 4 / 2**30:.3g} GiB synthetic SC16Q11 capture per GPU "
-            f"(amp {AMP}, sigma {SIGMA}, thr {THR}, spb {SPB}, fs {FS})")
+            f"(amp {AMP}, near-Gaussian noise sigma {SIGMA} [Irwin-Hall 12, tails to 6 sigma], thr {THR}, spb {SPB}, fs {FS})")
 
 
 def message_params(i):
@@ -65,9 +65,13 @@ def on_level():
     return int(round(AMP * 2048.0 * math.cos(PHASE))), int(round(AMP * 2048.0 * math.sin(PHASE)))
 
 
-def noise_scale():
-    ih4_std = (4.0 * (65536.0 ** 2 - 1.0) / 12.0) ** 0.5       # std of the sum of four 16-bit uniforms
-    return int(round(SIGMA * 2048.0 / ih4_std * (1 << 24)))
+NOISE_TERMS = 12        # noise = centred sum of twelve 16-bit uniforms (Irwin-Hall 12): Gaussian to within a few per cent
+                        # out to 4 sigma, tails to +-6 sigma; integer-only, so the CPU and GPU generators agree byte for byte
+
+
+def noise_scale(sigma=SIGMA):
+    std = (NOISE_TERMS * (65536.0 ** 2 - 1.0) / 12.0) ** 0.5       # std of the sum of NOISE_TERMS 16-bit uniforms
+    return int(round(sigma * 2048.0 / std * (1 << 24)))
 
 
 class ClockSampler(threading.Thread):
@@ -179,8 +183,10 @@ def reference_binary():
     return p if os.path.exists(p) else None
 
 
-def run_reference_cpu(iq_prefix, repeats=1):
-    """Times the unmodified reference binary on a capture prefix.  -> (Msamples/s, n_rows)."""
+def run_reference_cpu(iq_prefix, repeats=1, want_parity=False, device=DEVICE_NAME, filt=FILTER_NAME):
+    """Times the unmodified reference binary on a capture prefix.  -> (Msamples/s, n_rows[, csv rows, first_bit, edges]).
+    The parity outputs (csv rows without the wall-clock column, --rx-rec-dig transitions) come from a second, untimed
+    run so that the timed one is the plain decode."""
     ref = reference_binary()
     tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else None
     with tempfile.TemporaryDirectory(dir=tmpdir) as td:
@@ -189,17 +195,27 @@ def run_reference_cpu(iq_prefix, repeats=1):
         n = iq_prefix.size // 2
         best, rows = None, 0
         env = dict(os.environ, OOKD_DATA_DIR=os.path.join(ROOT, "ookiedokie_b200", "data") + "/")
-        dev_path = os.path.join(ROOT, "ookiedokie_b200", "data", "devices", DEVICE_NAME + ".json")
-        filt_path = os.path.join(ROOT, "ookiedokie_b200", "data", "filters", FILTER_NAME + ".json")
+        dev_path = os.path.join(ROOT, "ookiedokie_b200", "data", "devices", device + ".json")
+        filt_path = os.path.join(ROOT, "ookiedokie_b200", "data", "filters", filt + ".json")
+        cmd = [ref, "--rx", "bladerf_file", "-A", cap, "-d", dev_path, "-F", filt_path, "--rx-fmt", "csv",
+               "--samples-per-buffer", str(SPB), "-T", str(THR), "-s", str(FS)]
         for _ in range(repeats):
             t0 = time.perf_counter()
-            out = subprocess.run([ref, "--rx", "bladerf_file", "-A", cap, "-d", dev_path, "-F", filt_path, "--rx-fmt",
-                                  "csv", "--samples-per-buffer", str(SPB), "-T", str(THR), "-s", str(FS)],
-                                 capture_output=True, text=True, env=env, check=True)
+            out = subprocess.run(cmd, capture_output=True, text=True, env=env, check=True)
             dt = time.perf_counter() - t0
             rows = max(len(out.stdout.strip().splitlines()) - 1, 0)
             best = dt if best is None else min(best, dt)
-    return n / best / 1e6, rows
+        if not want_parity:
+            return n / best / 1e6, rows
+        dig = os.path.join(td, "dig.csv")
+        out = subprocess.run(cmd + ["-B", dig], capture_output=True, text=True, env=env, check=True)
+        lines = out.stdout.strip().splitlines()
+        has_ts = "nexa" in device                       # ts_mode unix-frac: first column is the wall clock
+        csv_rows = [l.split(",")[1:] if has_ts else l.split(",") for l in lines[1:]]
+        dl = open(dig).read().strip().splitlines()
+        first_bit = int(dl[0].split(",")[1])
+        edges = [int(dl[k].split(",")[0]) for k in range(2, len(dl), 2)]
+    return n / best / 1e6, rows, csv_rows, first_bit, edges
 
 
 def impl_reference(args, rank, world):
@@ -220,7 +236,7 @@ def impl_reference(args, rank, world):
     msgs = [O.message_bytes(dev, message_params(i)) for i in range(n_msgs)]
     tog, _ = O.toggles_from_messages(dev, msgs, FS, LEAD)
     i_on, q_on = on_level()
-    iq = O.synth(n, tog, i_on, q_on, noise_scale(), SEED)
+    iq = O.synth(n, tog, i_on, q_on, noise_scale(), SEED, noise_terms=NOISE_TERMS)
     for _ in range(args.warmup):
         run_reference_cpu(iq)
     vals = []
@@ -240,6 +256,136 @@ def impl_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def pin_to_gpu_numa(local_rank):
+    """Run this rank (and therefore allocate its pinned staging memory) on the CPUs local to its GPU.
+    -> description for the bench line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = open(base + "/local_cpulist").read().strip()
+        if node < 0 or not cpus:
+            return {"numa_node": node, "pinned": False}
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"numa_node": node, "pinned": bool(ids), "cpus": cpus}
+    except Exception as e:                                   # sysfs layout differs / containers without it
+        return {"pinned": False, "why": str(e)[:80]}
+
+
+FP32_ISSUE_PER_S = 148 * 128 * 1.965e9                       # fp32 lanes x clock (MEASURED_PEAKS.json sm_max_mhz)
+
+
+def measure_c3(local_rank, peak):
+    """BASELINE configs[2]: unknown-remote1 through fs128_fs16_dec4 on a low-SNR capture (amp 0.30, near-Gaussian noise
+    sigma 0.10): nothing can be screened, the exact two-stage kernel computes every output (fp32-issue bound)."""
+    import numpy as np
+    import torch
+    from ookiedokie_b200 import binding as B
+    from ookiedokie_b200 import host as H
+    n = 1 << 28
+    fir = H.Fir("fs128_fs16_dec4")
+    dev = H.Device("unknown-remote1", FS // fir.total_decimation)
+    tx = H.Device("unknown-remote1", FS)
+    buttons = ["Power", "Pause", "P1"]
+    msgs = [tx.message({"ID": hex(i % 256), "Button": buttons[i % 3]}) for i in range(n // 200000 + 8)]
+    tog, total = tx.toggles(msgs, LEAD)
+    import math
+    i_on, q_on = int(round(0.30 * 2048 * math.cos(0.4))), int(round(0.30 * 2048 * math.sin(0.4)))
+    d = torch.empty((n * 2,), dtype=torch.int16, device="cuda")
+    B.synth(n, np.ascontiguousarray(tog), i_on, q_on, noise_scale(0.10), 7, device_id=local_rank, device_ptr=d.data_ptr(),
+            noise_terms=NOISE_TERMS)
+    torch.cuda.synchronize()
+    g = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank)
+    g.want_list = False
+    first = g.decode((d.data_ptr(), n))                      # (the screen's verdict: work list overflow -> exact kernels)
+    g.decode((d.data_ptr(), n))
+    steps = 5
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fir_ms = 0.0
+    for _ in range(steps):
+        r = g.decode((d.data_ptr(), n))
+        fir_ms += r["fir_ms"]
+    dt = (time.perf_counter() - t0) / steps
+    out = {"workload": "unknown-remote1 + fs128_fs16_dec4, 2^28 samples, amp 0.30, near-Gaussian sigma 0.10, thr 0.1",
+           "ms_per_step": 1e3 * dt, "value": n / dt / 1e6, "unit": UNIT,
+           "messages_transmitted": int(n // 210900), "messages_decoded": int(len(r["msgs_raw"])),
+           "edges": r["n_edges"], "sm_rounds": r["sm_rounds"],
+           "screened": bool(r["refined_tiles"] == 0 and first["refined_tiles"] == 0),
+           "fir_kernel_ms": fir_ms / steps,
+           "hbm_frac_job": 4.0 * n / dt / 1e9 / peak,
+           "fp32_issue_frac_fir": (64.0 * n / (fir_ms / steps * 1e-3)) / FP32_ISSUE_PER_S if fir_ms > 0 else None,
+           "note": "64 exact fp32 mul/add per input sample for this filter shape (32 with FMA screening)"}
+    g.close()
+    del d
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_c5(rank, world, local_rank, peak, n_caps_total=256, log2n=24):
+    """BASELINE configs[4] (scaled to what one default run can synthesise): independent captures, devices alternating
+    p3l-nexa2012 / unknown-remote1, authored fs64_fs8 filter, sigma in {0, 0.02, 0.05}, seeds = index; capture i is
+    decoded by rank i mod world (no exchange at all)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ookiedokie_b200 import binding as B
+    from ookiedokie_b200 import host as H
+    n = 1 << log2n
+    fir = H.Fir("fs64_fs8")
+    names = ["p3l-nexa2012", "unknown-remote1"]
+    devs = [H.Device(nm, FS // fir.total_decimation) for nm in names]
+    mine = [i for i in range(n_caps_total) if i % world == rank]
+    bufs = []
+    for i in mine:
+        kind = i % 2
+        msgs = [devs[kind].message({}) for _ in range(n // (180000 if kind else 400000) + 2)]
+        tog, total = devs[kind].toggles(msgs, LEAD)
+        sigma = [0.0, 0.02, 0.05][i % 3]
+        d = torch.empty(n * 2, dtype=torch.int16, device="cuda")
+        B.synth(n, np.ascontiguousarray(tog), 1488, 1253, noise_scale(sigma) if sigma else 0, 1000 + i, device_id=local_rank,
+                device_ptr=d.data_ptr(), noise_terms=NOISE_TERMS)
+        bufs.append(d)
+    torch.cuda.synchronize()
+    per = 4                                                  # handles per device description: captures in flight
+    gpus = [B.Gpu(filter_stages=fir.stages, sm=devs[kind].sm_spec(), threshold=THR, samples_per_buffer=SPB,
+                  device_id=local_rank) for kind in range(2) for _ in range(per)]
+    caps = [((bufs[j].data_ptr(), n), (i % 2) * per + (j // 2) % per) for j, i in enumerate(mine)]
+    B.batch_decode(gpus, caps[:2 * per])                     # warm-up (workspace allocation)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    msgs, stats = B.batch_decode(gpus, caps)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt, float(sum(len(m) for m in msgs))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dt, n_msgs = float(tmax[0].item()), int(t[1].item())
+    else:
+        n_msgs = int(t[1].item())
+    for g in gpus:
+        g.close()
+    del bufs
+    torch.cuda.empty_cache()
+    return {"workload": f"{n_caps_total} independent captures x 2^{log2n} samples, p3l-nexa2012 / unknown-remote1 alternating, "
+                        f"fs64_fs8, sigma in {{0, 0.02, 0.05}}, capture i on rank i mod {world}",
+            "captures": n_caps_total, "ms_total": 1e3 * dt, "captures_per_s": n_caps_total / dt,
+            "value": n_caps_total * n / dt / 1e6, "unit": UNIT, "messages_decoded": n_msgs,
+            "hbm_frac_job": 4.0 * n_caps_total * n / dt / 1e9 / (peak * world),
+            "handles_per_gpu": 2 * per, "launches_per_capture": float(np.mean([s["gpu_launches"] for s in stats]))}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,6 +398,7 @@ def main():
     ap.add_argument("--ref-samples", type=int, default=1 << 25, help="prefix per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra configs block (C3 low SNR, C5 batch)")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--chunk-buffers", type=int, default=0)
     ap.add_argument("--share", action="store_true", help="OOKD_FLAG_SHARE_SMS on the handles (three screening CTAs per SM)")
@@ -271,6 +418,7 @@ def main():
         impl_reference(args, rank, world)
         return
 
+    import ctypes as C
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -281,6 +429,7 @@ def main():
     if not torch.cuda.is_available() or B.device_count() == 0:
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the receive path")
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -293,11 +442,10 @@ def main():
     fir = H.Fir(FILTER_NAME)
     dev = H.Device(DEVICE_NAME, FS // fir.total_decimation)
     depth = max(1, args.pipeline)
-    n_handles = max(depth, args.pipelined_depth, args.e2e_depth, 1)
+    n_handles = max(depth, args.pipelined_depth, args.e2e_depth, 2 if world > 1 else 1)
     flags = args.flags | (B.FLAG_SHARE_SMS if args.share else 0)
     gpus = [B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
-                  flags=flags, sm_chunk_buffers=args.chunk_buffers, sm_warmup=1 if world > 1 else 0,
-                  sm_burst_rounds=(3 if world > 1 else 0))   # the slowest shard sets the pace: one more blind round
+                  flags=flags, sm_chunk_buffers=args.chunk_buffers, sm_warmup=1 if world > 1 else 0)
             for _ in range(n_handles)]
     gpu = gpus[0]
     n = args.samples
@@ -311,21 +459,68 @@ def main():
     # ---- shard resident in HBM (synthesised on the device; identical bytes to the CPU recipe) ----
     d_iq = torch.empty(((halo_avail + n) * 2,), dtype=torch.int16, device="cuda")
     B.synth(halo_avail + n, tog, i_on, q_on, noise_scale(), SEED, first_sample=first - halo_avail, device_id=local_rank,
-            device_ptr=d_iq.data_ptr())
+            device_ptr=d_iq.data_ptr(), noise_terms=NOISE_TERMS)
     torch.cuda.synchronize()
 
     for g in gpus:
         g.want_list = False         # keep messages as one structured array; no per-message Python work
 
-    def run_steps(iq_arg, n_steps, depth=depth):
-        """n_steps decodes of the shard, `depth` in flight: step i+1 is enqueued (on the next handle) before step i
-        is waited for, as consecutive windows of a long capture are.  Every step is a complete decode incl. the
-        cross-rank stitch.  -> (last result, last messages, summed launches / fir / screen / kernel ms / syncs)."""
-        pending, acc = [], [0, 0.0, 0.0, 0.0, 0]
+    L = B.lib()
+
+    def run_steps_single(iq_ptr, is_dev, n_steps, depth=1):
+        """world == 1: n_steps decodes through the C ABI, `depth` in flight (decode_begin on the next handle before
+        decode_end of this one).  The messages are in host memory (result.msgs) when a call returns; only the LAST
+        step's list is converted to numpy.  -> (last result dict, summed launches / fir / screen / kernel ms / syncs)."""
+        acc = [0, 0.0, 0.0, 0.0, 0]
+        res, ex = B.GpuResult(), B.SmCarry()
+        p = C.c_void_p(iq_ptr)
+        last_gpu = gpus[0]
+
+        def account():
+            acc[0] += res.gpu_launches
+            acc[1] += res.fir_ms
+            acc[2] += res.screen_ms
+            acc[3] += res.kernel_ms
+            acc[4] += res.host_syncs
+
+        if depth <= 1:
+            h = gpus[0].h
+            for _ in range(n_steps):
+                rc = L.ookd_gpu_decode_shard(h, p, is_dev, first, n, int(last), None, C.byref(ex), C.byref(res))
+                if rc:
+                    raise SystemExit(f"decode failed: {L.ookd_gpu_last_error(h).decode()}")
+                account()
+        else:
+            pend = []
+            for i in range(n_steps):
+                g = gpus[i % depth]
+                rc = L.ookd_gpu_decode_begin(g.h, p, is_dev, first, n, int(last), None)
+                if rc:
+                    raise SystemExit(f"decode_begin failed: {L.ookd_gpu_last_error(g.h).decode()}")
+                pend.append(g)
+                if len(pend) == depth:
+                    g0 = pend.pop(0)
+                    if L.ookd_gpu_decode_end(g0.h, C.byref(ex), C.byref(res)):
+                        raise SystemExit(f"decode_end failed: {L.ookd_gpu_last_error(g0.h).decode()}")
+                    account()
+                    last_gpu = g0
+            while pend:
+                g0 = pend.pop(0)
+                if L.ookd_gpu_decode_end(g0.h, C.byref(ex), C.byref(res)):
+                    raise SystemExit(f"decode_end failed: {L.ookd_gpu_last_error(g0.h).decode()}")
+                account()
+                last_gpu = g0
+        out = last_gpu._result(res)
+        return out, out["msgs_raw"], acc
+
+    def run_steps_multi(iq_arg, n_steps, depth=1):
+        """world > 1: every step is a complete decode incl. the cross-rank stitch (ookiedokie_b200/shard.py)."""
+        st = S.PipelinedStitcher(rank, world)
+        acc = [0, 0.0, 0.0, 0.0, 0]
         out = [None, None]
 
-        def finish(runner):
-            res, exit_c, rounds, msgs = S.stitch_and_gather(runner, rank, world)
+        def finish(runner, decoded, confirm_now=False):
+            res, exit_c, rounds, msgs = st.finish(runner, decoded, confirm_now)
             acc[0] += runner.launches
             acc[1] += runner.fir_ms
             acc[2] += runner.screen_ms
@@ -333,47 +528,51 @@ def main():
             acc[4] += runner.host_syncs
             out[0], out[1] = res, msgs
 
-        if depth == 1 and world > 1 and len(gpus) > 1:
-            # One decode at a time on the GPU, but the cross-rank stitch of step i (host only: shared-memory exchange,
-            # waiting for the slowest rank) runs while the GPU already works on step i+1 -- the next window is enqueued
-            # on the other handle AFTER this one has completed, so device work never overlaps.
-            def finish_decoded(runner, decoded):
-                res, exit_c, rounds, msgs = S.stitch_and_gather(runner, rank, world, decoded=decoded)
-                acc[0] += runner.launches
-                acc[1] += runner.fir_ms
-                acc[2] += runner.screen_ms
-                acc[3] += runner.kernel_ms
-                acc[4] += runner.host_syncs
-                out[0], out[1] = res, msgs
-
+        if depth <= 1:
+            # One decode at a time on the GPU; the cross-rank exchange of step i (host only) is published without
+            # waiting for the other ranks and checked while the GPU already works on step i+1 (two handles: the tables
+            # of step i stay intact until its stitch is confirmed).
             cur = S.GpuShardRunner(gpus[0], iq_arg, first, n, last)
             cur.begin()
             for i in range(n_steps):
                 decoded = cur.decode(None)                    # waits for step i
+                st.confirm_pending()                          # step i-1: its handle is the one step i+1 goes to
                 nxt = None
                 if i + 1 < n_steps:
                     nxt = S.GpuShardRunner(gpus[(i + 1) % 2], iq_arg, first, n, last)
                     nxt.begin()
-                finish_decoded(cur, decoded)
+                finish(cur, decoded)
                 cur = nxt
-            return out[0], out[1], acc
-        for i in range(n_steps):
-            runner = S.GpuShardRunner(gpus[i % depth], iq_arg, first, n, last)
-            runner.begin()
-            pending.append(runner)
-            if len(pending) == depth:
-                finish(pending.pop(0))
-        while pending:
-            finish(pending.pop(0))
+        else:
+            pending = []
+            for i in range(n_steps):
+                runner = S.GpuShardRunner(gpus[i % depth], iq_arg, first, n, last)
+                runner.begin()
+                pending.append(runner)
+                if len(pending) == depth:
+                    r0 = pending.pop(0)
+                    finish(r0, r0.decode(None), True)         # (its handle takes the next step at once)
+            while pending:
+                r0 = pending.pop(0)
+                finish(r0, r0.decode(None), True)
+        st.drain()
+        out[1] = st.last_messages if rank == 0 else None
         return out[0], out[1], acc
+
+    def run_steps(iq_arg, n_steps, depth=1):
+        if world == 1:
+            if isinstance(iq_arg, tuple):
+                return run_steps_single(iq_arg[0], 1, n_steps, depth)
+            return run_steps_single(iq_arg.ctypes.data, 0, n_steps, depth)
+        return run_steps_multi(iq_arg, n_steps, depth)
 
     dev_arg = (d_iq.data_ptr(), halo_avail + n)
     sampler = ClockSampler(local_rank)
     sampler.start()                 # started before the warm-up so that it is sampling when the timed region begins
-    run_steps(dev_arg, max(args.warmup, depth))
+    run_steps(dev_arg, max(args.warmup, depth), depth)
     barrier()
     t0 = time.perf_counter()
-    res, msgs, (launches, fir_ms, screen_ms, kernel_ms, host_syncs) = run_steps(dev_arg, args.steps)
+    res, msgs, (launches, fir_ms, screen_ms, kernel_ms, host_syncs) = run_steps(dev_arg, args.steps, depth)
     barrier()
     t1 = time.perf_counter()
     dt = t1 - t0
@@ -407,18 +606,29 @@ def main():
     n_msgs = len(msgs) if msgs is not None else 0
     n_edges = res["n_edges"]
     sm_rounds = res["sm_rounds"]
+    refined_groups = res["refined_blocks"]
 
     # ---- end to end: shard in pinned host memory, H2D inside the timed region ----
     e2e = None
     if not args.no_e2e:
         nbytes = (halo_avail + n) * 4
-        hptr = B.lib().ookd_gpu_host_alloc(nbytes)
+        hptr = L.ookd_gpu_host_alloc(nbytes)
         if not hptr:
             raise SystemExit("pinned host allocation failed")
-        rc = B.lib().ookd_gpu_memcpy_d2h(local_rank, hptr, d_iq.data_ptr(), nbytes)
+        rc = L.ookd_gpu_memcpy_d2h(local_rank, hptr, d_iq.data_ptr(), nbytes)
         assert rc == 0
-        import ctypes
-        h_iq = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_int16)), shape=((halo_avail + n) * 2,))
+        h_iq = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_int16)), shape=((halo_avail + n) * 2,))
+        # ceiling: the plain pinned-host -> device copy of the same bytes, all ranks at once, same run
+        barrier()
+        tc0 = time.perf_counter()
+        for _ in range(2):
+            assert L.ookd_gpu_memcpy_h2d(local_rank, d_iq.data_ptr(), hptr, nbytes) == 0
+        torch.cuda.synchronize()
+        tcopy = (time.perf_counter() - tc0) / 2
+        tct = torch.tensor([tcopy], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tct, op=dist.ReduceOp.MAX)
+        tcopy = float(tct.item())
         ed = max(1, args.e2e_depth)
         run_steps(h_iq, ed, depth=ed)
         barrier()
@@ -431,39 +641,84 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dte = float(te.item())
         d2h = len(res_e["msgs_raw"]) * 56 + 3 * 256 + 48
-        e2e = {"value": world * n / (dte / args.e2e_steps) / 1e6, "unit": UNIT, "h2d_bytes_per_step": nbytes,
-               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "pipeline_depth": ed}
+        e2e_value = world * n / (dte / args.e2e_steps) / 1e6
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "pipeline_depth": ed,
+               "h2d_gbs": world * nbytes / (dte / args.e2e_steps) / 1e9,
+               "h2d_ceiling_gbs": world * nbytes / tcopy / 1e9,
+               "frac_of_h2d_ceiling": (dte / args.e2e_steps) and tcopy / (dte / args.e2e_steps),
+               "pinned_memory": numa}
         if rank == 0 and msgs is not None and msgs_e is not None:
             assert np.array_equal(msgs_e, msgs), "host-input decode differs from device-input decode"
         cpu_prefix = h_iq[halo_avail * 2: (halo_avail + min(n, args.cpu_samples)) * 2].copy() if rank == 0 else None
-        B.lib().ookd_gpu_host_free(hptr)
+        L.ookd_gpu_host_free(hptr)
     else:
         cpu_prefix = d_iq[halo_avail * 2: (halo_avail + min(n, args.cpu_samples)) * 2].cpu().numpy() if rank == 0 else None
 
-    # ---- CPU baseline (rank 0, N = 1 only): the unmodified reference binary on a bounded prefix ----
+    # ---- CPU baseline + parity AT BENCHMARK SCALE (rank 0, N = 1 only): the unmodified reference binary on a bounded
+    #      prefix; its csv rows and --rx-rec-dig transitions are compared with a GPU decode of exactly that prefix ----
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         nc = cpu_prefix.size // 2
         if reference_binary() is not None:
-            v, rows = run_reference_cpu(cpu_prefix)
-            n_gpu_rows = int((msgs["out_sample"] + 1 <= (nc // SPB) * SPB).sum()) if msgs is not None else 0
+            v, rows, ref_rows, ref_fb, ref_edges = run_reference_cpu(cpu_prefix, want_parity=True)
+            pg = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
+                       flags=flags)
+            got = pg.decode((d_iq.data_ptr(), nc))
+            fb, edges = pg.edges()
+            gpu_rows, cur_buf = [], None
+            for out_sample, buf, nbits, data in got["msgs"]:
+                vals = [val for key, val in dev.format(data) if key != "Decode Timestamp"]
+                if buf != cur_buf:
+                    gpu_rows.append([])
+                    cur_buf = buf
+                gpu_rows[-1].extend(vals)
+            assert fb == ref_fb, "first threshold decision differs from the reference binary's"
+            assert len(edges) == len(ref_edges) and np.array_equal(edges, np.array(ref_edges, dtype=np.uint64)), \
+                "threshold transitions differ from the reference binary's --rx-rec-dig output"
+            assert gpu_rows == ref_rows, "decoded messages differ from the reference binary's csv output"
+            parity = {"against": "unmodified reference binary (csv rows + --rx-rec-dig transitions)", "n": nc,
+                      "msgs": len(ref_rows), "edges": len(ref_edges), "equal": True}
+            pg.close()
             cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "reference", "host_cores_available": os.cpu_count(),
-                   "sample": f"first {nc} samples ({nc * 4 / 2**20:.0f} MiB) of the same capture; "
-                             f"{rows} messages (GPU decoded {n_gpu_rows} in the same span)"}
+                   "sample": f"first {nc} samples ({nc * 4 / 2**20:.0f} MiB) of the same capture; {rows} messages"}
         else:
             from oracle import oracle as O
             odev = O.load_device(DEVICE_NAME)
             t0 = time.perf_counter()
             r = O.rx(cpu_prefix, O.load_filter(FILTER_NAME), odev, threshold_=THR, samples_per_buffer=SPB, samplerate=FS)
             v = nc / (time.perf_counter() - t0) / 1e6
+            pg = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
+                       flags=flags)
+            got = pg.decode((d_iq.data_ptr(), nc))
+            fb, edges = pg.edges()
+            assert fb == r["first_bit"] and np.array_equal(edges, r["edges"]), "edges differ from the oracle's"
+            assert got["msgs"] == r["msgs"], "decoded messages differ from the oracle's"
+            parity = {"against": "oracle port", "n": nc, "msgs": len(r["msgs"]), "edges": len(r["edges"]), "equal": True}
+            pg.close()
             cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "host_cores_available": os.cpu_count(),
                    "sample": f"first {nc} samples of the same capture; {len(r['msgs'])} messages"}
 
+    # ---- the other BASELINE configs, outside the headline timed region ----
+    peak, peak_src = measured_peak()
+    configs = None
+    if not args.no_configs:
+        del d_iq
+        torch.cuda.empty_cache()
+        configs = {}
+        try:
+            if world == 1:
+                configs["c3_lowsnr_remote1_dec4"] = measure_c3(local_rank, peak)
+            configs["c5_batch_mixed_fs64_fs8"] = measure_c5(rank, world, local_rank, peak)
+        except Exception as e:                               # the headline line must survive a failure here
+            configs["error"] = f"{type(e).__name__}: {str(e)[:200]}"
+
     if rank == 0:
-        peak, peak_src = measured_peak()
         fir_ms_per_launch = fir_ms_max / args.steps
         screen_ms_per_launch = screen_ms_max / args.steps
         achieved = 4.0 * n / (screen_ms_per_launch * 1e-3) / 1e9 if screen_ms_per_launch > 0 else None
+        job_gbs = 4.0 * n / (ms_per_step * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -471,11 +726,11 @@ def main():
             "config": {"workload": workload_name(n), "samples_per_gpu": n, "device": DEVICE_NAME, "filter": FILTER_NAME,
                        "parallelism": f"time-shards x{world}" if world > 1 else "single shard",
                        "pipeline_depth": depth,
-                       "stitch": ("host-side exchange of step i overlaps the decode of step i+1" if world > 1 and depth == 1
-                                  else "n/a" if world == 1 else "inside each step"),
+                       "stitch": (S.stitch_description() if world > 1 else "n/a"),
                        "l2": "input shard (4 B/sample) larger than L2; no flush needed",
                        "messages_decoded": n_msgs, "messages_transmitted_upper_bound": n_tx_msgs,
-                       "edges_last_rank": n_edges, "sm_rounds": sm_rounds},
+                       "edges_last_rank": n_edges, "sm_rounds": sm_rounds,
+                       "refined_fraction": refined_groups / (n / fir.total_decimation / 8.0)},
             "step_latency_ms": kernel_ms_max / args.steps,      # CUDA-event span of one decode (overlaps its neighbours when pipelined)
             "fir_stage_ms_per_step": fir_ms_per_launch,
             "host_syncs_per_step": host_syncs / args.steps,
@@ -484,7 +739,8 @@ def main():
                          "peak_source": peak_src,
                          "kernel": "fir_screen_tma_kernel<1> (SC16Q11 -> window energies -> threshold decisions), "
                                    "4 B/sample algorithmic, one launch per step",
-                         "kernel_ms_per_launch": screen_ms_per_launch},
+                         "kernel_ms_per_launch": screen_ms_per_launch,
+                         "job_gbs": job_gbs / world, "job_frac": job_gbs / world / peak},
             "clocks": clocks, "gpu_launches": launches,
         }
         if pipelined:
@@ -493,6 +749,10 @@ def main():
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if parity:
+            line["parity_checked"] = parity
+        if configs:
+            line["configs"] = configs
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

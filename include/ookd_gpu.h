@@ -180,6 +180,9 @@ struct ookd_gpu_config {
                                                 each SM so that the other decode's tail kernels can run beside it */
 #define OOKD_FLAG_NO_GRAPH       64u         /* enqueue the decode tail (edges, state machine, gather, read-back)
                                                 operation by operation instead of replaying its CUDA graph      */
+#define OOKD_FLAG_UNFUSED_SM    128u          /* state-machine stage as separate kernels (anchors, rounds, link, walk,
+                                                scan, gather) with blindly enqueued repair rounds instead of the one
+                                                cooperative kernel that iterates on the device until the chain resolves */
 #define OOKD_FLAG_NO_SCREEN      2u          /* no screening: the exact tiled kernels compute every output with the
                                                 reference's in-order MACs (same decisions, fp32-issue bound)        */
 
@@ -272,6 +275,32 @@ int  ookd_gpu_batch_decode(ookd_gpu *const *handles, uint32_t n_handles,
                            const struct ookd_capture *caps, uint32_t n_caps,
                            struct ookd_msg *msgs_out, uint64_t msgs_cap, uint64_t *msg_first,
                            struct ookd_gpu_result *results);
+/* ---- one window over several GPUs of this process (`gpu_ids, n_gpus`; 8(e)-2 time shards) ----
+ * The window [first_sample, first_sample + n_samples) is cut into n_gpus consecutive shards (whole multiples of
+ * lcm(samples_per_buffer, decimation)); shard g is decoded by GPU gpu_ids[g] on its own host thread
+ * (ookd_gpu_decode_shard with FIR halo and one chunk of state-machine warm-up history), then the shards are stitched
+ * on the host: a shard entered in another state than its predecessor was left in re-runs only its state-machine stage
+ * (ookd_gpu_resolve).  No collective and no peer copy: one 48-byte carry per boundary and the message lists cross GPUs.
+ * The result is what ookiedokie_rx()'s loop (src/ookiedokie.c:238-290) prints for the window.
+ * iq: host memory pointing at sample first_sample - min(ookd_gpu_multi_halo(), first_sample) (pinned recommended), or,
+ * with iq_is_device_ptrs != 0, an array of n_gpus device pointers (const int16_t *const *), pointer g on GPU
+ * gpu_ids[g] pointing at shard g's first sample (ookd_gpu_multi_shard_range) minus min(halo, that sample). */
+typedef struct ookd_gpu_multi ookd_gpu_multi;
+int  ookd_gpu_multi_create(ookd_gpu_multi **m, const struct ookd_gpu_config *cfg /* device_id ignored */,
+                           const int32_t *gpu_ids, uint32_t n_gpus);
+void ookd_gpu_multi_destroy(ookd_gpu_multi *m);
+uint32_t ookd_gpu_multi_halo(const ookd_gpu_multi *m);
+uint32_t ookd_gpu_multi_n_gpus(const ookd_gpu_multi *m);
+ookd_gpu *ookd_gpu_multi_handle(ookd_gpu_multi *m, uint32_t g);          /* per-GPU handle (e.g. for ookd_gpu_filtered_sc16q11) */
+uint32_t ookd_gpu_multi_shards_used(const ookd_gpu_multi *m);            /* shards of the last decode (<= n_gpus)               */
+const char *ookd_gpu_multi_last_error(const ookd_gpu_multi *m);
+int  ookd_gpu_multi_shard_range(const ookd_gpu_multi *m, uint64_t first_sample, uint64_t n_samples, uint32_t g,
+                                uint64_t *shard_first, uint64_t *shard_n);
+int  ookd_gpu_multi_decode(ookd_gpu_multi *m, const void *iq, int iq_is_device_ptrs, uint64_t first_sample,
+                           uint64_t n_samples, int last, const struct ookd_sm_carry *entry,
+                           struct ookd_sm_carry *exit_, struct ookd_gpu_result *res);
+int  ookd_gpu_multi_edges(ookd_gpu_multi *m, const uint64_t **edges, uint64_t *n_edges, uint32_t *first_bit);
+
 uint32_t ookd_gpu_halo(const ookd_gpu *h);               /* input samples of FIR history  */
 uint32_t ookd_gpu_total_decimation(const ookd_gpu *h);
 void ookd_gpu_initial_carry(const ookd_gpu *h, struct ookd_sm_carry *c);  /* RESET, k=0 */
@@ -291,6 +320,12 @@ int  ookd_gpu_bits(ookd_gpu *h, uint8_t *bits_out, uint64_t max_out, uint64_t *n
 int  ookd_gpu_filtered(ookd_gpu *h, const int16_t *iq, uint64_t n_samples, int iq_is_device_ptr,
                        float *out_iq_host, uint64_t max_out, uint64_t *n_out);
 
+/* Filtered + decimated samples of the shard the LAST decode covered, re-quantised to SC16Q11 the way the reference's
+ * post-filter recorder does -- (int16_t) (x * 2048.0f), complexf_to_sc16q11 (src/complexf.h:87-96) via
+ * sdr_bladerf_file_tx (src/sdr/bladeRF_file.c:128-155): what --rx-rec writes (src/ookiedokie.c:265-270).  Interleaved
+ * int16 I,Q.  Uses the decode's input again: device input must still be valid, host input is the handle's staged copy. */
+int  ookd_gpu_filtered_sc16q11(ookd_gpu *h, int16_t *out_host, uint64_t max_out, uint64_t *n_out);
+
 /* Same arithmetic on caller-supplied complex float input (what fir_test feeds
  * fir_filter_and_decimate, src/test/fir_test.c:246-275). */
 int  ookd_gpu_filter_cf(ookd_gpu *h, const float *in_iq_host, uint64_t n_samples,
@@ -304,6 +339,13 @@ int  ookd_gpu_synth(int32_t device_id, int16_t *dst, int dst_is_device_ptr,
                     uint64_t first_sample, uint64_t n_samples,
                     const uint64_t *toggles_host, uint64_t n_toggles,
                     int32_t i_on, int32_t q_on, int32_t noise_scale, uint64_t seed);
+
+/* Same with a choice of noise law: noise_terms = 4 (ookd_gpu_synth: sum of four uniforms, bounded at +-3.46 sigma)
+ * or 12 (Irwin-Hall of twelve uniforms: Gaussian to within a few per cent out to 4 sigma, tails to +-6 sigma). */
+int  ookd_gpu_synth_ex(int32_t device_id, int16_t *dst, int dst_is_device_ptr,
+                       uint64_t first_sample, uint64_t n_samples,
+                       const uint64_t *toggles_host, uint64_t n_toggles,
+                       int32_t i_on, int32_t q_on, int32_t noise_scale, uint64_t seed, uint32_t noise_terms);
 
 /* Pinned host memory for captures handed to ookd_gpu_decode. */
 void *ookd_gpu_host_alloc(size_t bytes);

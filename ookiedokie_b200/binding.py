@@ -25,6 +25,7 @@ FLAG_NO_TMA = 8
 FLAG_SYNC_TAIL = 16
 FLAG_SHARE_SMS = 32
 FLAG_NO_GRAPH = 64
+FLAG_UNFUSED_SM = 128
 
 # every symbol include/ookd_gpu.h declares
 EXPORTS = [
@@ -33,9 +34,12 @@ EXPORTS = [
     "ookd_gpu_create", "ookd_gpu_destroy", "ookd_gpu_decode", "ookd_gpu_decode_shard",
     "ookd_gpu_decode_begin", "ookd_gpu_decode_end", "ookd_gpu_batch_decode",
     "ookd_gpu_resolve", "ookd_gpu_halo", "ookd_gpu_total_decimation", "ookd_gpu_initial_carry",
-    "ookd_gpu_edges", "ookd_gpu_bits", "ookd_gpu_filtered", "ookd_gpu_filter_cf", "ookd_gpu_synth",
+    "ookd_gpu_edges", "ookd_gpu_bits", "ookd_gpu_filtered", "ookd_gpu_filter_cf", "ookd_gpu_synth", "ookd_gpu_synth_ex",
     "ookd_gpu_host_alloc", "ookd_gpu_host_free", "ookd_gpu_dev_alloc", "ookd_gpu_dev_free",
-    "ookd_gpu_memcpy_h2d", "ookd_gpu_memcpy_d2h",
+    "ookd_gpu_memcpy_h2d", "ookd_gpu_memcpy_d2h", "ookd_gpu_filtered_sc16q11",
+    "ookd_gpu_multi_create", "ookd_gpu_multi_destroy", "ookd_gpu_multi_halo", "ookd_gpu_multi_n_gpus",
+    "ookd_gpu_multi_handle", "ookd_gpu_multi_shards_used", "ookd_gpu_multi_last_error", "ookd_gpu_multi_shard_range",
+    "ookd_gpu_multi_decode", "ookd_gpu_multi_edges",
 ]
 
 
@@ -194,6 +198,33 @@ def lib():
         L.ookd_gpu_synth.restype = C.c_int
         L.ookd_gpu_synth.argtypes = [C.c_int32, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p,
                                      C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
+        L.ookd_gpu_synth_ex.restype = C.c_int
+        L.ookd_gpu_synth_ex.argtypes = [C.c_int32, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p,
+                                        C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32]
+        L.ookd_gpu_filtered_sc16q11.restype = C.c_int
+        L.ookd_gpu_filtered_sc16q11.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.ookd_gpu_multi_create.restype = C.c_int
+        L.ookd_gpu_multi_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(GpuConfig), C.POINTER(C.c_int32), C.c_uint32]
+        L.ookd_gpu_multi_destroy.argtypes = [C.c_void_p]
+        L.ookd_gpu_multi_halo.restype = C.c_uint32
+        L.ookd_gpu_multi_halo.argtypes = [C.c_void_p]
+        L.ookd_gpu_multi_n_gpus.restype = C.c_uint32
+        L.ookd_gpu_multi_n_gpus.argtypes = [C.c_void_p]
+        L.ookd_gpu_multi_handle.restype = C.c_void_p
+        L.ookd_gpu_multi_handle.argtypes = [C.c_void_p, C.c_uint32]
+        L.ookd_gpu_multi_shards_used.restype = C.c_uint32
+        L.ookd_gpu_multi_shards_used.argtypes = [C.c_void_p]
+        L.ookd_gpu_multi_last_error.restype = C.c_char_p
+        L.ookd_gpu_multi_last_error.argtypes = [C.c_void_p]
+        L.ookd_gpu_multi_shard_range.restype = C.c_int
+        L.ookd_gpu_multi_shard_range.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64),
+                                                 C.POINTER(C.c_uint64)]
+        L.ookd_gpu_multi_decode.restype = C.c_int
+        L.ookd_gpu_multi_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_int,
+                                            C.POINTER(SmCarry), C.POINTER(SmCarry), C.POINTER(GpuResult)]
+        L.ookd_gpu_multi_edges.restype = C.c_int
+        L.ookd_gpu_multi_edges.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64),
+                                           C.POINTER(C.c_uint32)]
         L.ookd_gpu_host_alloc.restype = C.c_void_p
         L.ookd_gpu_host_alloc.argtypes = [C.c_size_t]
         L.ookd_gpu_host_free.argtypes = [C.c_void_p]
@@ -443,6 +474,14 @@ class Gpu:
                     "ookd_gpu_filtered")
         return out
 
+    def filtered_sc16q11(self):
+        """Filtered samples of the last decode's shard as the reference's post-filter recorder writes them."""
+        m = C.c_uint64()
+        self._check(lib().ookd_gpu_filtered_sc16q11(self.h, None, 0, C.byref(m)), "ookd_gpu_filtered_sc16q11")
+        out = np.empty((m.value, 2), dtype=np.int16)
+        self._check(lib().ookd_gpu_filtered_sc16q11(self.h, out.ctypes.data, m.value, C.byref(m)), "ookd_gpu_filtered_sc16q11")
+        return out
+
     def filter_cf(self, iq_f32):
         x = np.ascontiguousarray(iq_f32, dtype=np.float32).reshape(-1, 2)
         m = C.c_uint64()
@@ -454,17 +493,107 @@ class Gpu:
         return out
 
 
-def synth(n_samples, toggles, i_on, q_on, noise_scale, seed, first_sample=0, device_id=-1, device_ptr=None):
+class MultiGpu:
+    """One ookd_gpu_multi handle: a window time-sharded over several GPUs of this process."""
+
+    def __init__(self, gpu_ids, filter_stages=None, sm=None, threshold=0.1, samples_per_buffer=8192, flags=0,
+                 sm_chunk_buffers=0):
+        L = lib()
+        cfg = GpuConfig()
+        self._keep = []
+        if filter_stages:
+            fd, k = make_filter_desc(filter_stages)
+            self._keep += [fd, k]
+            cfg.filter = C.pointer(fd)
+        if sm is not None:
+            sd, k = make_sm_desc(sm["states"], sm["num_bits"], sm["sample_rate"])
+            self._keep += [sd, k]
+            cfg.sm = C.pointer(sd)
+            self.msg_bytes = (sm["num_bits"] + 7) // 8
+        else:
+            self.msg_bytes = 0
+        cfg.threshold = threshold
+        cfg.samples_per_buffer = samples_per_buffer
+        cfg.flags = flags
+        cfg.sm_chunk_buffers = sm_chunk_buffers
+        ids = (C.c_int32 * len(gpu_ids))(*gpu_ids)
+        self.h = C.c_void_p()
+        rc = L.ookd_gpu_multi_create(C.byref(self.h), C.byref(cfg), ids, len(gpu_ids))
+        if rc != 0:
+            self.h = None
+            raise OokdError(f"ookd_gpu_multi_create: {L.ookd_gpu_strerror(rc).decode()}")
+        self.n_gpus = len(gpu_ids)
+
+    def close(self):
+        if getattr(self, "h", None) and lib is not None:
+            lib().ookd_gpu_multi_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def halo(self):
+        return int(lib().ookd_gpu_multi_halo(self.h))
+
+    def shard_range(self, first_sample, n_samples, g):
+        a, b = C.c_uint64(), C.c_uint64()
+        lib().ookd_gpu_multi_shard_range(self.h, first_sample, n_samples, g, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def decode(self, iq, first_sample=0, n_samples=None, last=True, entry=None, device_ptrs=None):
+        """iq: numpy int16 host array starting at sample first_sample - min(halo, first_sample); or device_ptrs:
+        list of per-GPU device pointers.  -> (result dict, exit carry tuple)."""
+        if device_ptrs is not None:
+            arr = (C.c_void_p * len(device_ptrs))(*[int(p) for p in device_ptrs])
+            p, is_dev, keep = C.cast(arr, C.c_void_p), 1, arr
+        else:
+            keep = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
+            p, is_dev = C.c_void_p(keep.ctypes.data), 0
+            if n_samples is None:
+                n_samples = keep.size // 2 - min(self.halo, first_sample)
+        res = GpuResult()
+        ex = SmCarry()
+        en = SmCarry.fromtuple(entry) if entry is not None else None
+        rc = lib().ookd_gpu_multi_decode(self.h, p, is_dev, first_sample, n_samples, int(last),
+                                         C.byref(en) if en is not None else None, C.byref(ex), C.byref(res))
+        if rc != 0:
+            raise OokdError(f"ookd_gpu_multi_decode: {lib().ookd_gpu_strerror(rc).decode()} "
+                            f"({lib().ookd_gpu_multi_last_error(self.h).decode()})")
+        n = int(res.n_msgs)
+        if n:
+            raw = np.ctypeslib.as_array(C.cast(res.msgs, C.POINTER(C.c_uint8)), shape=(n * C.sizeof(Msg),)).copy()
+            rec = raw.view(MSG_DTYPE)
+        else:
+            rec = np.zeros(0, dtype=MSG_DTYPE)
+        return dict(msgs_raw=rec, msgs=msgs_to_tuples(rec, self.msg_bytes), n_in=int(res.n_in), n_out=int(res.n_out),
+                    n_buffers=int(res.n_buffers), n_edges=int(res.n_edges), first_bit=int(res.first_bit),
+                    sm_rounds=int(res.sm_rounds), kernel_ms=float(res.kernel_ms), gpu_launches=int(res.gpu_launches),
+                    shards_used=int(lib().ookd_gpu_multi_shards_used(self.h))), ex.astuple()
+
+    def edges(self):
+        p = C.POINTER(C.c_uint64)()
+        n = C.c_uint64()
+        fb = C.c_uint32()
+        rc = lib().ookd_gpu_multi_edges(self.h, C.byref(p), C.byref(n), C.byref(fb))
+        if rc != 0:
+            raise OokdError(f"ookd_gpu_multi_edges: {lib().ookd_gpu_multi_last_error(self.h).decode()}")
+        e = np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint64)
+        return int(fb.value), e
+
+
+def synth(n_samples, toggles, i_on, q_on, noise_scale, seed, first_sample=0, device_id=-1, device_ptr=None,
+          noise_terms=4):
     """Synthetic capture on the GPU.  Returns numpy (n,2) int16, or fills device_ptr when given."""
     tg = np.ascontiguousarray(toggles, dtype=np.uint64)
     if device_ptr is not None:
-        rc = lib().ookd_gpu_synth(device_id, C.c_void_p(int(device_ptr)), 1, first_sample, n_samples,
-                                  tg.ctypes.data, len(tg), int(i_on), int(q_on), int(noise_scale), int(seed))
+        rc = lib().ookd_gpu_synth_ex(device_id, C.c_void_p(int(device_ptr)), 1, first_sample, n_samples,
+                                     tg.ctypes.data, len(tg), int(i_on), int(q_on), int(noise_scale), int(seed),
+                                     int(noise_terms))
         out = None
     else:
         out = np.empty((n_samples, 2), dtype=np.int16)
-        rc = lib().ookd_gpu_synth(device_id, out.ctypes.data, 0, first_sample, n_samples, tg.ctypes.data, len(tg),
-                                  int(i_on), int(q_on), int(noise_scale), int(seed))
+        rc = lib().ookd_gpu_synth_ex(device_id, out.ctypes.data, 0, first_sample, n_samples, tg.ctypes.data, len(tg),
+                                     int(i_on), int(q_on), int(noise_scale), int(seed), int(noise_terms))
     if rc != 0:
         raise OokdError(f"ookd_gpu_synth: {lib().ookd_gpu_strerror(rc).decode()}")
     return out

@@ -62,6 +62,9 @@ struct ookd_gpu {
     bool persist = false;
     bool tma = false;                 // TMA-staged screening kernel (screen_tma.cuh)
     bool screen2 = false;             // dec4 shape: screen + refine (else the exact tiled two-stage kernel)
+    int screen_regs = 64;             // register cap of the TMA screening kernel (64 / 56 / 48)
+    bool fused_sm = true;             // state-machine stage as ONE cooperative kernel (sm_fused_kernel)
+    unsigned fused_grid_max = 0;      // CTAs of it that can be co-resident on this device
     unsigned n_sm = 148;
 
     bool have_sm = false;
@@ -278,6 +281,16 @@ encode_tiled_fn tensor_map_encoder()
     return fn;
 }
 
+typedef void (*screen_tma_kernel_t)(const CUtensorMap, const ScreenTmaArgs, const ScreenParams);
+
+screen_tma_kernel_t screen_tma_fn(int dec, int regs)
+{
+    if (dec == 1) {
+        return regs <= 48 ? fir_screen_tma_kernel<1, 48> : regs <= 56 ? fir_screen_tma_kernel<1, 56> : fir_screen_tma_kernel<1, 64>;
+    }
+    return regs <= 48 ? fir_screen_tma_kernel<4, 48> : regs <= 56 ? fir_screen_tma_kernel<4, 56> : fir_screen_tma_kernel<4, 64>;
+}
+
 // OOKD_FLAG_SHARE_SMS: the persistent screening kernels of different handles on one device must not overlap
 // EACH OTHER (two of them would fight over the same three quarters of every SM); what should overlap is one
 // decode's screening kernel with the other decode's tail.  A per-device event chains them: a screening launch
@@ -358,11 +371,7 @@ int launch_screen_tma(ookd_gpu *h, const ScreenArgs &sa, const ScreenParams &sp,
     cudaEvent_t *tok = (share && use_token) ? screen_token(h->device) : nullptr;
     if (tok) CU(h, cudaStreamWaitEvent(h->s_compute, *tok, 0));
     const unsigned grid = (unsigned) (tiles < ctas ? tiles : ctas);
-    if (dec == 1) {
-        fir_screen_tma_kernel<1><<<grid, STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(tmap, ta, sp);
-    } else {
-        fir_screen_tma_kernel<4><<<grid, STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(tmap, ta, sp);
-    }
+    screen_tma_fn(dec, h->screen_regs)<<<grid, STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(tmap, ta, sp);
     if (tok) CU(h, cudaEventRecord(*tok, h->s_compute));
     return OOKD_OK;
 }
@@ -541,6 +550,18 @@ int run_generic_chain(ookd_gpu *h, const void *d_in, bool in_is_i16, i64 in_base
         src = a.out_cf; src_i16 = false; src_base = lo[s]; src_end = hi[s];
     }
     return OOKD_OK;
+}
+
+// complexf_to_sc16q11 (src/complexf.h:87-96): (int16_t) (x * 2048.0f), i.e. rounded multiply, truncation towards
+// zero, low 16 bits -- what the reference's post-filter recorder writes (sdr_bladerf_file_tx).
+__global__ void __launch_bounds__(256) cf_to_sc16q11_kernel(const float2 *in, uint32_t *out, u64 n)
+{
+    const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2 v = in[i];
+    const uint32_t re = (uint32_t) (uint16_t) (int16_t) __float2int_rz(__fmul_rn(v.x, 2048.0f));
+    const uint32_t im = (uint32_t) (uint16_t) (int16_t) __float2int_rz(__fmul_rn(v.y, 2048.0f));
+    out[i] = re | (im << 16);
 }
 
 // ---- state machine stage + message gather; fills res ----
@@ -969,7 +990,6 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     if (n_copy > msg_cap) n_copy = msg_cap;
     if (h->h_msgs_pin_cap < n_copy) {
         if (h->h_msgs_pin) cudaFreeHost(h->h_msgs_pin);
-    if (h->tail_graph) cudaGraphExecDestroy(h->tail_graph);
         h->h_msgs_pin = nullptr;
         h->h_msgs_pin_cap = 0;
         CU(h, cudaHostAlloc((void **) &h->h_msgs_pin, sizeof(SmMsg) * n_copy, cudaHostAllocDefault));
@@ -1021,6 +1041,39 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
         CU(h, cudaGetLastError());
     }
 
+    if (h->fused_sm) {
+        // ---- state machine: anchors, rounds until resolved, link / walk, scan and gather in one cooperative launch ----
+        SmFusedArgs f{};
+        f.a = a;
+        f.cnt_done = (uint32_t *) h->tab_cnt[0].p;
+        f.cnt_alloc = (uint32_t *) h->tab_cnt[1].p;
+        f.bar = (uint32_t *) ((char *) h->scalars.p + 336);
+        f.max_rounds = 16;
+        f.rounds_out = (uint32_t *) ((char *) h->scalars.p + 52);
+        f.offsets = (uint32_t *) h->slot_off.p;
+        f.msgs_out = (SmMsg *) h->msgs_dev.p;
+        f.msgs_cap = msg_cap;
+        f.n_msgs_out = (u64 *) h->scalars.p + 1;
+        f.msgs_base = 0;
+        static const bool debug_stamps = getenv("OOKD_DEBUG") != nullptr;
+        f.stamps = debug_stamps ? (long long *) ((char *) h->scalars.p + 384) : nullptr;
+        unsigned grid = (nc + (SM_FUSED_NT / 32) - 1) / (SM_FUSED_NT / 32);
+        if (grid > h->fused_grid_max) grid = h->fused_grid_max;
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(grid);
+        lc.blockDim = dim3(SM_FUSED_NT);
+        lc.dynamicSmemBytes = 0;
+        lc.stream = h->s_compute;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative;
+        at[0].val.cooperative = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        CU(h, cudaLaunchKernelEx(&lc, sm_fused_kernel, f));
+        h->launches++;
+        rounds = 0;                                         // (reported by the kernel: scalars + 52)
+        cur = 1;                                            // tab_cnt[1] = slots handed out; [0] = complete pairs
+    } else {
     // ---- state machine burst ----
     sm_anchor_kernel<<<nc, 32, 0, h->s_compute>>>(a);
     h->launches++;
@@ -1056,8 +1109,12 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     sm_gather_table_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a, (const uint32_t *) h->slot_off.p,
                                                                        (SmMsg *) h->msgs_dev.p, msg_cap);
     h->launches += 2;
+    }
     CU(h, cudaGetLastError());
-    CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 512, cudaMemcpyDeviceToHost, h->s_compute));
+    CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 336, cudaMemcpyDeviceToHost, h->s_compute));
+    if (getenv("OOKD_DEBUG")) {
+        CU(h, cudaMemcpyAsync((char *) h->h_scalars + 384, (char *) h->scalars.p + 384, 128, cudaMemcpyDeviceToHost, h->s_compute));
+    }
     if (n_copy) {
         CU(h, cudaMemcpyAsync(h->h_msgs_pin, h->msgs_dev.p, sizeof(SmMsg) * n_copy, cudaMemcpyDeviceToHost, h->s_compute));
     }
@@ -1075,7 +1132,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
         add(n_bits); add(nc); add(eg); add(h->burst_rounds); add(msg_cap); add(n_copy); add((u64) h->bit_base); add(h->pre);
         add((u64) h->report_lo); add((u64) h->out_lo); add((u64) h->out_hi); add(h->first_buffer); add(h->spb);
         add(h->total_dec); add(h->chunk_buffers); add(h->warm ? 1 : 0); add(h->slot_cap); add(x.cap); add(h->n_sm);
-        add(entry0.state); add(entry0.k); add(entry0.num_bits); add(entry0.prev);
+        add(entry0.state); add(entry0.k); add(entry0.num_bits); add(entry0.prev); add(h->fused_sm ? 1 : 0);
         for (int i = 0; i < 4; i++) add(entry0.data[i]);
         const void *ptrs[] = {h->bits.p, h->edges.p, h->block_counts.p, h->edge_tmp.p, h->scalars.p, h->h_scalars, h->h_msgs_pin,
                               h->msgs_dev.p, h->slots.p, h->slot_count.p, h->slot_off.p, h->tab_entry.p, h->tab_exit.p,
@@ -1162,7 +1219,15 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
     // The chain did not resolve within the burst (several consecutive chunks entered in a state no table holds
     // yet): keep the edges, anchors and tables and add rounds one at a time, each with its own link / walk /
     // gather and one synchronisation, instead of starting over on the synchronous path.
-    while (overflow == 0 && walk_complete != 1 && rounds < 16) {
+    if (h->fused_sm) rounds = *(const uint32_t *) (hs + 52);
+    if (h->fused_sm && getenv("OOKD_DEBUG")) {
+        const long long *st = (const long long *) (hs + 384);
+        fprintf(stderr, "[ookd] fused sm (cycles of CTA 0): prologue %lld, anchors %lld, barrier %lld, round %lld, barrier+links %lld, "
+                        "walk+scan %lld, barrier %lld, gather %lld; total %lld; %u round(s), %u chunks\n",
+                st[0] - st[8] - 0, st[0] - st[8], st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4],
+                st[7] - st[5], st[7] - st[8], rounds, nc);
+    }
+    while (!h->fused_sm && overflow == 0 && walk_complete != 1 && rounds < 16) {
         SmArgs a = fast_sm_args(h, h->pend.e0);
         a.round = rounds;
         a.counter_idx = rounds & 15;
@@ -1184,7 +1249,7 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
         h->launches += 5;
         CU(h, cudaGetLastError());
         // keep [0, 8) of the host mirror (edge total) -- the device copy still holds it
-        CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 512, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 336, cudaMemcpyDeviceToHost, h->s_compute));
         if (n_copy) {
             CU(h, cudaMemcpyAsync(h->h_msgs_pin, h->msgs_dev.p, sizeof(SmMsg) * n_copy, cudaMemcpyDeviceToHost, h->s_compute));
         }
@@ -1268,6 +1333,8 @@ void ookd_gpu_destroy(ookd_gpu *h)
     cudaSetDevice(h->device);
     if (h->s_compute) cudaStreamSynchronize(h->s_compute);
     if (h->s_copy) cudaStreamSynchronize(h->s_copy);
+    if (h->tail_graph) cudaGraphExecDestroy(h->tail_graph);     // before the buffers its nodes point at go away
+    h->tail_graph = nullptr;
     for (auto &st : h->stages) if (st.d_taps) cudaFree(st.d_taps);
     if (h->d_tab) cudaFree(h->d_tab);
     DevBuf *all[] = {&h->in, &h->bits, &h->inter[0], &h->inter[1], &h->block_counts, &h->edges, &h->scalars,
@@ -1330,6 +1397,14 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     CUC(cudaEventCreate(&h->ev_s1));
     CUC(cudaHostAlloc(&h->h_scalars, 512, cudaHostAllocDefault));
     if (ensure(h, h->scalars, 512) != OOKD_OK) CREATE_FAIL(OOKD_ERR_NOMEM);
+    CUC(cudaMemset(h->scalars.p, 0, 512));               // (incl. the grid barrier words of sm_fused_kernel at +336)
+    {
+        int per_sm = 0, coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sm_fused_kernel, SM_FUSED_NT, 0) != cudaSuccess) per_sm = 0;
+        h->fused_grid_max = (unsigned) per_sm * (unsigned) prop.multiProcessorCount;
+        h->fused_sm = coop != 0 && h->fused_grid_max > 0 && !(h->flags & OOKD_FLAG_UNFUSED_SM);
+    }
 
     // ---- filter ----
     const ookd_filter_desc *f = cfg->filter;
@@ -1390,15 +1465,18 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
         h->screen2 = !(h->flags & OOKD_FLAG_NO_SCREEN) && pstar_ok;
     }
     h->n_sm = (unsigned) prop.multiProcessorCount;
+    if (const char *e = getenv("OOKD_SCREEN_REGS")) h->screen_regs = atoi(e);
     h->persist = (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) == 0;
     h->tma = h->persist && !(h->flags & OOKD_FLAG_NO_TMA);       // both screened shapes (one stage 32/1, dec4)
     if (h->tma) {
-        if (cudaFuncSetAttribute(fir_screen_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, STMA_SMEM_BYTES) !=
-                cudaSuccess ||
-            cudaFuncSetAttribute(fir_screen_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, STMA_SMEM_BYTES) !=
-                cudaSuccess) {
-            cudaGetLastError();
-            h->tma = false;
+        for (int dec : {1, 4}) {
+            for (int regs : {48, 56, 64}) {
+                if (cudaFuncSetAttribute(screen_tma_fn(dec, regs), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         STMA_SMEM_BYTES) != cudaSuccess) {
+                    cudaGetLastError();
+                    h->tma = false;
+                }
+            }
         }
     }
     // the screen needs a finite positive power threshold (thr <= 0 decides 1 everywhere, NaN 0 everywhere;
@@ -1827,6 +1905,36 @@ int ookd_gpu_filtered(ookd_gpu *h, const int16_t *iq, uint64_t n_samples, int iq
     return filtered_common(h, iq, true, iq_is_device_ptr != 0, n_samples, true, out_iq_host, max_out, n_out);
 }
 
+int ookd_gpu_filtered_sc16q11(ookd_gpu *h, int16_t *out_host, uint64_t max_out, uint64_t *n_out)
+{
+    if (!h || !n_out) return OOKD_ERR_ARG;
+    if (!h->have_last || h->pend.active) return fail(h, OOKD_ERR_STATE, "filtered_sc16q11: no completed decode");
+    CU(h, cudaSetDevice(h->device));
+    const u64 n = (u64) (h->out_hi - h->report_lo);
+    *n_out = n;
+    if (!out_host || n == 0) return OOKD_OK;
+    const u64 lim = n < max_out ? n : max_out;
+    const u64 step = 1ull << 24;                             // outputs per pass (bounds the float staging)
+    DevBuf cf, q;
+    int rc = ensure(h, cf, (lim < step ? lim : step) * sizeof(float2));
+    if (!rc) rc = ensure(h, q, (lim < step ? lim : step) * 4);
+    for (u64 o = 0; !rc && o < lim; o += step) {
+        const u64 cnt = (lim - o < step) ? lim - o : step;
+        const i64 o_lo = h->report_lo + (i64) o;
+        rc = run_generic_chain(h, h->pend.d_in, true, h->pend.in_base, h->pend.in_valid_end, o_lo, o_lo + (i64) cnt,
+                               (float2 *) cf.p, nullptr, 0);
+        if (rc) break;
+        cf_to_sc16q11_kernel<<<(unsigned) ((cnt + 255) / 256), 256, 0, h->s_compute>>>((const float2 *) cf.p, (uint32_t *) q.p, cnt);
+        cudaError_t e = cudaMemcpyAsync(out_host + 2 * o, q.p, cnt * 4, cudaMemcpyDeviceToHost, h->s_compute);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->s_compute);
+        if (e != cudaSuccess) rc = fail(h, OOKD_ERR_CUDA, "filtered_sc16q11: %s", cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize(h->s_compute);
+    release(cf);
+    release(q);
+    return rc;
+}
+
 int ookd_gpu_filter_cf(ookd_gpu *h, const float *in_iq_host, uint64_t n_samples, float *out_iq_host, uint64_t max_out,
                        uint64_t *n_out)
 {
@@ -1837,6 +1945,15 @@ int ookd_gpu_synth(int32_t device_id, int16_t *dst, int dst_is_device_ptr, uint6
                    const uint64_t *toggles_host, uint64_t n_toggles, int32_t i_on, int32_t q_on, int32_t noise_scale,
                    uint64_t seed)
 {
+    return ookd_gpu_synth_ex(device_id, dst, dst_is_device_ptr, first_sample, n_samples, toggles_host, n_toggles, i_on, q_on,
+                             noise_scale, seed, 4);
+}
+
+int ookd_gpu_synth_ex(int32_t device_id, int16_t *dst, int dst_is_device_ptr, uint64_t first_sample, uint64_t n_samples,
+                      const uint64_t *toggles_host, uint64_t n_toggles, int32_t i_on, int32_t q_on, int32_t noise_scale,
+                      uint64_t seed, uint32_t noise_terms)
+{
+    if (noise_terms != 4 && noise_terms != 12) return OOKD_ERR_ARG;
     if (!dst && n_samples) return OOKD_ERR_ARG;
     if (device_id >= 0 && cudaSetDevice(device_id) != cudaSuccess) return OOKD_ERR_CUDA;
     if (n_samples == 0) return OOKD_OK;
@@ -1854,7 +1971,7 @@ int ookd_gpu_synth(int32_t device_id, int16_t *dst, int dst_is_device_ptr, uint6
         const u64 threads = (n_samples + SYNTH_SPT - 1) / SYNTH_SPT;
         const unsigned grid = (unsigned) ((threads + 255) / 256);
         synth_kernel<<<grid, 256>>>(d_dst, first_sample, n_samples, d_tog, n_toggles, i_on, q_on, noise_scale,
-                                    synth_mix64(seed));
+                                    synth_mix64(seed), noise_terms);
         if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) rc = OOKD_ERR_CUDA;
     }
     if (!rc && !dst_is_device_ptr) {

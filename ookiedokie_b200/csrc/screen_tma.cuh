@@ -118,8 +118,11 @@ __device__ __forceinline__ int stma_chunk_off(int u, int v)
 // DEC = 4: two stages 16/2 + 32/2 (fs128_fs16_dec4): 4 outputs per thread, composite window of 78 inputs = 5 spans
 //          back (the proofs and the elements needed are those of fir2_screen_kernel, fir_kernels.cuh section 4).
 // Tiles, a.out_lo / out_hi / bit_base are in OUTPUT indices; a tile is 4096 INPUT samples = 4096 / DEC outputs.
-template <int DEC>
-__global__ void __launch_bounds__(STMA_NT, OOKD_STMA_MINB)
+// MAXR: register cap per thread.  64 = all the registers four resident CTAs can have; 56 / 48 leave 8 K / 16 K
+// registers per SM free, so that the latency-bound tail kernels of the PREVIOUS window (exact refine, edges, state
+// machine) can be resident beside the four screening CTAs of the current one (pipelined windows, ookd_gpu.cu).
+template <int DEC, int MAXR>
+__global__ void __maxnreg__(MAXR)
 fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaArgs ta, const ScreenParams sp)
 {
     static_assert(DEC == 1 || DEC == 4, "shapes with a screening proof");

@@ -59,6 +59,7 @@ struct SmArgs {
     uint32_t round;           // 0 => speculative first round
     uint32_t counter_idx;     // slot of n_ran this launch reports into
     SmCarry entry0;
+    const SmCarry *entry_ptr; // non-null: the shard's true entry lives in device memory (exit of the previous window)
     const SmCarry *exit_prev;
     SmCarry *exit_cur;
     SmCarry *ran_with;
@@ -828,17 +829,34 @@ __global__ void fill_u32_kernel(uint32_t *p, uint32_t n, uint32_t v)
 // as a real entry: when the previous chunk's run indeed arrives idle, the chain links up after round 0.
 // A chunk without an anchor keeps its fixed boundary and is seeded with RESET at its first sample (a guess
 // that usually lands mid-message; later rounds replace it).
-__global__ void __launch_bounds__(32) sm_anchor_kernel(const SmArgs a)
+// 32-ary lower bound by a whole warp: four dependent loads for 2^20 edges instead of twenty (the chunk's first
+// edge is the first thing every anchor warp needs).
+__device__ __forceinline__ u64 warp_edge_lower_bound(const u64 *edges, u64 n, u64 pos, uint32_t lane)
 {
-    OOKD_SM_EDGE_HDR(a)
-    __shared__ SmTable T;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t c = blockIdx.x;
-    if (c >= a.n_chunks) return;
-    load_table(T, a.tab);
+    u64 lo = 0, hi = n;                                      // answer in [lo, hi]
+    while (hi - lo > 32) {
+        const u64 step = (hi - lo + 32) / 33;                // 32 pivots lo + step*(lane+1) - 1
+        const u64 idx = lo + step * (lane + 1) - 1;
+        const bool less = idx < hi && edges[idx] < pos;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, less);
+        const uint32_t cnt = (uint32_t) __popc(m);           // pivots are ascending: `less` is a prefix
+        const u64 new_lo = cnt ? lo + step * cnt : lo;
+        const u64 new_hi = (cnt < 32) ? ((lo + step * (cnt + 1) - 1 < hi) ? lo + step * (cnt + 1) - 1 : hi) : hi;
+        lo = new_lo;
+        hi = new_hi;
+    }
+    const u64 idx = lo + lane;
+    const bool less = idx < hi && edges[idx] < pos;
+    return lo + (u64) __popc(__ballot_sync(0xFFFFFFFFu, less));
+}
+
+// One warp, one chunk (T: the compiled machine, in shared or global memory).
+__device__ __forceinline__ void sm_anchor_chunk(const SmArgs &a, const SmTable &T, uint32_t c, uint32_t lane, const u64 n_edges,
+                                                const uint32_t base_bit)
+{
     i64 start, end;
     chunk_bounds_fixed(a, c, start, end);
-    const u64 e = edge_lower_bound(a.edges, n_edges, (u64) start);
+    const u64 e = warp_edge_lower_bound(a.edges, n_edges, (u64) start, lane);
     const uint32_t tb = base_bit ^ (uint32_t) (e & 1);       // true decision at start-1
     bool have_anchor = false;
     u64 anchor_e = 0;
@@ -890,37 +908,29 @@ __global__ void __launch_bounds__(32) sm_anchor_kernel(const SmArgs a)
     a.seed_kind[c] = kind;
 }
 
-// One WARP per (chunk, slot); only lane 0 runs the machine.  The work is a chain of dependent
-// steps, so what matters is latency, not lanes: giving every run its own warp keeps runs from
-// serialising each other through divergence (8 runs sharing a warp cost ~8x the latency).
-constexpr int SM_ROUND_WARPS = 4;                            // (chunk, slot) pairs per CTA
-
-__global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(const SmArgs a)
+__global__ void __launch_bounds__(32) sm_anchor_kernel(const SmArgs a)
 {
     OOKD_SM_EDGE_HDR(a)
     __shared__ SmTable T;
-    __shared__ int s_any;
-    const uint32_t K = a.tab_k;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t KR = (a.round == 0) ? 1u : K;             // warps per chunk this round
-    const uint32_t gid = blockIdx.x * SM_ROUND_WARPS + (threadIdx.x >> 5);
-    const uint32_t c = gid / KR, j = gid % KR;
-    if (a.round >= 1 && a.walk_status[1]) return;            // an earlier walk of this burst already resolved the chain
-    // cheap rejection before anything is staged: most (chunk, slot) pairs have nothing new to run
-    bool live = c < a.n_chunks;
-    if (live && a.round != 0) live = (c != 0) && j < a.cnt_in[c - 1];
-    if (threadIdx.x == 0) s_any = 0;
-    __syncthreads();
-    if (live && lane == 0) s_any = 1;
-    __syncthreads();
-    if (!s_any) return;                                      // (CTA-uniform)
+    const uint32_t c = blockIdx.x;
+    if (c >= a.n_chunks) return;
     load_table(T, a.tab);
-    if (!live) return;
+    sm_anchor_chunk(a, T, c, threadIdx.x & 31, n_edges, base_bit);
+}
+
+// One WARP per (chunk, slot): the work is a chain of dependent steps, so what matters is latency, not lanes; giving
+// every run its own warp keeps runs from serialising each other through divergence.
+// sm_round_pair is the body for pair (c, j) of round a.round; cnt_in = pairs complete before this round, cnt_out = slots
+// handed out (initialised to cnt_in; atomically incremented).  T: compiled machine in shared or global memory.
+constexpr int SM_ROUND_WARPS = 4;                            // (chunk, slot) pairs per CTA
+
+__device__ __forceinline__ void sm_round_pair(const SmArgs &a, const SmTable &T, const WarpSm &W, const bool warp_capable,
+                                              uint32_t c, uint32_t j, uint32_t lane, const u64 n_edges, const uint32_t base_bit)
+{
+    const uint32_t K = a.tab_k;
     i64 start, end, lo;
     chunk_bounds(a, c, start, end, lo);
-    const bool warp_ok = warp_sm_supported(a.tab) && (end - lo) < (1ll << 31);
-    WarpSm W;
-    if (warp_ok) warp_sm_load(W, &T, lane);
+    const bool warp_ok = warp_capable && (end - lo) < (1ll << 31);
 
     u64 e = a.chunk_e[c];
     uint32_t tb = base_bit ^ (uint32_t) (e & 1);             // true decision at start-1
@@ -929,14 +939,15 @@ __global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(con
     i64 pos = start;
     uint32_t slot;
     if (a.round == 0) {
-        // one speculative seed per chunk, prepared by sm_anchor_kernel
+        // one speculative seed per chunk, prepared by sm_anchor_chunk
         if (!warp_ok && lane != 0) return;
         const uint32_t kind = a.seed_kind[c];
         pos = a.seed_pos[c];
         e = a.seed_e[c];
         tb = base_bit ^ (uint32_t) (e & 1);
         if (kind == OOKD_SEED_TRUE) {
-            s = a.entry0;
+            s = a.entry_ptr ? *a.entry_ptr : a.entry0;
+            if (s.state < T.num_states && s.k > T.states[s.state].ksat) s.k = T.states[s.state].ksat;
             entry = s;
         } else if (kind == OOKD_SEED_CANON) {
             s = a.canon;
@@ -965,7 +976,7 @@ __global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(con
         }
         slot = 0;
         if (lane == 0) slot = atomicAdd(&a.cnt_out[c], 1u);
-        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);            // (warp_ok: all lanes are here; else only lane 0)
+        if (warp_ok) slot = __shfl_sync(0xFFFFFFFFu, slot, 0);   // (warp_ok: all lanes are here; else only lane 0)
         if (slot >= K) {
             if (lane == 0) atomicExch(a.overflow, 2u);      // table full: host falls back
             return;
@@ -1035,6 +1046,33 @@ __global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(con
     }
 }
 
+__global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(const SmArgs a)
+{
+    OOKD_SM_EDGE_HDR(a)
+    __shared__ SmTable T;
+    __shared__ int s_any;
+    const uint32_t K = a.tab_k;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t KR = (a.round == 0) ? 1u : K;             // warps per chunk this round
+    const uint32_t gid = blockIdx.x * SM_ROUND_WARPS + (threadIdx.x >> 5);
+    const uint32_t c = gid / KR, j = gid % KR;
+    if (a.round >= 1 && a.walk_status[1]) return;            // an earlier walk of this burst already resolved the chain
+    // cheap rejection before anything is staged: most (chunk, slot) pairs have nothing new to run
+    bool live = c < a.n_chunks;
+    if (live && a.round != 0) live = (c != 0) && j < a.cnt_in[c - 1];
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    if (live && lane == 0) s_any = 1;
+    __syncthreads();
+    if (!s_any) return;                                      // (CTA-uniform)
+    load_table(T, a.tab);
+    if (!live) return;
+    const bool capable = warp_sm_supported(a.tab);
+    WarpSm W;
+    if (capable) warp_sm_load(W, &T, lane);
+    sm_round_pair(a, T, W, capable, c, j, lane, n_edges, base_bit);
+}
+
 // Resolve: a corrected entry for chunk 0 (the shard's true entry state arrived from the previous
 // shard).  Every other pair of every table stays valid -- pairs are functions of their entry only --
 // so just chunk 0 gains a pair (unless it already has this entry) and the walk restarts from it.
@@ -1070,17 +1108,13 @@ __global__ void __launch_bounds__(32) sm_table_add_entry_kernel(const SmArgs a)
 }
 
 // link[c][i] = slot of chunk c+1 whose entry equals exit[c][i] (0xFF if none)
-__global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
+__device__ __forceinline__ void sm_link_pair(const SmArgs &a, const uint32_t *cnt, uint32_t c, uint32_t i)
 {
     const uint32_t K = a.tab_k;
-    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t c = gid / K, i = gid % K;
-    if (c >= a.n_chunks) return;
-    if (a.walk_status[1]) return;                            // already resolved: keep the links the walk used
     uint8_t l = 0xFF;
-    if (c + 1 < a.n_chunks && i < a.cnt_in[c]) {
+    if (c + 1 < a.n_chunks && i < min(cnt[c], K)) {
         const SmCarry x = a.tab_exit[(u64) c * K + i];
-        const uint32_t n_next = a.cnt_in[c + 1];
+        const uint32_t n_next = min(cnt[c + 1], K);
         for (uint32_t q = 0; q < n_next; q++) {
             if (carry_equal(x, a.tab_entry[(u64) (c + 1) * K + q])) { l = (uint8_t) q; break; }
         }
@@ -1088,22 +1122,32 @@ __global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
     a.link[(u64) c * K + i] = l;
 }
 
+__global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
+{
+    const uint32_t K = a.tab_k;
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c = gid / K, i = gid % K;
+    if (c >= a.n_chunks) return;
+    if (a.walk_status[1]) return;                            // already resolved: keep the links the walk used
+    sm_link_pair(a, a.cnt_in, c, i);
+}
+
 // One CTA resolves the chain from chunk first_chunk / slot *start_slot.  Chasing 1 link per step through global
-// memory would serialise n_chunks L2 latencies, so the link rows of a block of 4096 chunks are first staged in
+// memory would serialise n_chunks L2 latencies, so the link rows of a block of BLK chunks are first staged in
 // shared memory (one coalesced pass), composed over segments of SEG chunks (one thread per segment, all K start
 // slots at once), the short chain over segments is walked by one thread, and every segment thread then replays
-// its own segment from its now-known entry slot.
+// its own segment from its now-known entry slot.  Needs blockDim.x >= BLK / 32.
 constexpr int SM_WALK_NT = 1024;
 
-__global__ void __launch_bounds__(SM_WALK_NT) sm_walk_kernel(const SmArgs a)
+template <uint32_t BLK>
+__device__ __forceinline__ void sm_walk_cta(const SmArgs &a)
 {
-    constexpr uint32_t SEG = 32, BLK = 4096, NSEG = BLK / SEG;
+    constexpr uint32_t SEG = 32, NSEG = BLK / SEG;
     __shared__ uint2 s_link[BLK];                            // link rows of the block (8 slots x 1 byte)
     __shared__ uint8_t s_map[NSEG * 8];                      // composed map of each segment
     __shared__ uint8_t s_in[NSEG];                           // entry slot of each segment (0xFF = unreachable)
     __shared__ uint32_t s_carry, s_max;
     const uint32_t K = a.tab_k;                              // == 8 (one 8-byte link row per chunk)
-    if (a.walk_status[1]) return;                            // resolved by an earlier walk of this burst
     if (threadIdx.x == 0) { s_carry = *a.start_slot; s_max = 0; }
     __syncthreads();
     uint32_t done = 0;
@@ -1182,6 +1226,12 @@ __global__ void __launch_bounds__(SM_WALK_NT) sm_walk_kernel(const SmArgs a)
     }
 }
 
+__global__ void __launch_bounds__(SM_WALK_NT) sm_walk_kernel(const SmArgs a)
+{
+    if (a.walk_status[1]) return;                            // resolved by an earlier walk of this burst
+    sm_walk_cta<4096>(a);
+}
+
 __global__ void sm_gather_table_kernel(const SmArgs a, const uint32_t *offsets, SmMsg *out, u64 out_cap)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1192,6 +1242,178 @@ __global__ void sm_gather_table_kernel(const SmArgs a, const uint32_t *offsets, 
     for (uint32_t i = 0; i < n; i++) {
         if ((u64) offsets[c] + i < out_cap) out[offsets[c] + i] = src[i];
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused form of the whole state-machine stage: anchors, seed round, link, walk, repair rounds UNTIL the chain
+// resolves, message scan and gather in ONE cooperative launch.  The separate kernels above cost a launch boundary
+// each (about a dozen per decode, all on the critical path behind the last sample) and had to enqueue repair rounds
+// blindly; here the convergence loop runs on the device and the phases are separated by a grid barrier.
+// Warp w of the grid owns chunks w, w + W, ...; the compiled machine is read from global memory (L1 resident), so
+// the kernel's only shared memory is the walk's staging area and its CTAs fit beside a running screening kernel.
+// ---------------------------------------------------------------------------------------
+struct SmFusedArgs {
+    SmArgs a;                 // hdr / tables / anchors as for the separate kernels (cnt_in / cnt_out are set here)
+    uint32_t *cnt_done;       // [n_chunks] pairs complete as of the last barrier
+    uint32_t *cnt_alloc;      // [n_chunks] slots handed out
+    uint32_t *bar;            // [2] grid barrier: arrivals, generation (zeroed once, at handle creation)
+    uint32_t max_rounds;
+    uint32_t *rounds_out;     // rounds run
+    uint32_t *offsets;        // [n_chunks] exclusive message offsets of the chosen pairs
+    SmMsg *msgs_out;          // ordered message list ...
+    u64 msgs_cap;
+    u64 *n_msgs_out;          // ... and its length (may exceed msgs_cap: then the host fetches again with room)
+    u64 msgs_base;            // messages of earlier windows already in msgs_out (0 for a whole-shard decode)
+    long long *stamps;        // null, or [16] phase time stamps (debug)
+};
+
+constexpr int SM_FUSED_NT = 128;
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All CTAs of the (co-resident: cooperative launch) grid arrive; the last one opens the next generation.
+__device__ __forceinline__ void sm_grid_barrier(uint32_t *bar, uint32_t n_ctas)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t gen = ld_acquire_u32(bar + 1);
+        __threadfence();
+        if (atomicAdd(bar, 1u) == n_ctas - 1) {
+            atomicExch(bar, 0u);
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1) : "memory");
+        } else {
+            while (ld_acquire_u32(bar + 1) == gen) __nanosleep(64);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Exclusive scan of the chosen pairs' message counts by one CTA (offsets[c], total); the copy itself is done by the
+// chunks' own warps after the next barrier.
+__device__ __forceinline__ void sm_scan_cta(const SmArgs &a, uint32_t *offsets, u64 base, u64 *total_out)
+{
+    __shared__ u64 s_w[32];
+    const uint32_t nt = blockDim.x, nc = a.n_chunks;
+    const uint32_t per = (nc + nt - 1) / nt;
+    const uint32_t lo = min(nc, threadIdx.x * per), hi = min(nc, lo + per);
+    u64 sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += a.msg_counts[i];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t) d) inc += up;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    u64 before = 0, all = 0;
+    for (uint32_t w = 0; w < (nt + 31) / 32; w++) {
+        if (w < warp) before += s_w[w];
+        all += s_w[w];
+    }
+    u64 run = before + inc - sum;
+    for (uint32_t c = lo; c < hi; c++) {
+        offsets[c] = (uint32_t) run;
+        run += a.msg_counts[c];
+    }
+    if (threadIdx.x == 0) *total_out = base + all;
+}
+
+// messages of chunk c's chosen pair -> their place in the ordered list (one warp)
+__device__ __forceinline__ void sm_gather_chunk(const SmArgs &a, const uint32_t *offsets, SmMsg *out, u64 base, u64 cap,
+                                                uint32_t c, uint32_t lane)
+{
+    const uint32_t n = a.msg_counts[c];
+    if (n == 0) return;
+    const u64 off = base + offsets[c];
+    const u64 *src = (const u64 *) (a.slots + ((u64) c * a.tab_k + a.chosen[c]) * a.slot_cap);
+    constexpr uint32_t W8 = sizeof(SmMsg) / 8;               // 8-byte words per message
+    for (uint32_t i = lane; i < n * W8; i += 32) {
+        if (off + i / W8 < cap) ((u64 *) (out + off))[i] = src[i];
+    }
+}
+
+// phase stamps of CTA 0 (SM clock), for OOKD_DEBUG: 0 anchors done, 1 past the barrier, 2 round done, 3 links done (past
+// the barrier), 4 walk + scan done, 5 past the barrier, 7 end; [8] = start
+#define STAMP(i) do { if (f.stamps && blockIdx.x == 0 && threadIdx.x == 0) f.stamps[i] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(SM_FUSED_NT) sm_fused_kernel(const SmFusedArgs f)
+{
+    STAMP(8);
+    SmArgs a = f.a;
+    OOKD_SM_EDGE_HDR(a)
+    const SmTable &T = *a.tab;
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr uint32_t WPC = SM_FUSED_NT / 32;
+    const uint32_t gw = blockIdx.x * WPC + (threadIdx.x >> 5), n_gw = gridDim.x * WPC;
+    const uint32_t nc = a.n_chunks, K = a.tab_k;
+    const bool capable = warp_sm_supported(a.tab);
+    WarpSm W;
+    if (capable) warp_sm_load(W, a.tab, lane);
+    a.cnt_in = f.cnt_done;
+    a.cnt_out = f.cnt_alloc;
+
+    // ---- anchors; every chunk starts with one pair: its seed ----
+    for (uint32_t c = gw; c < nc; c += n_gw) {
+        sm_anchor_chunk(a, T, c, lane, n_edges, base_bit);
+        if (lane == 0) {
+            f.cnt_alloc[c] = 1u;
+            f.cnt_done[c] = 1u;
+        }
+    }
+    STAMP(0);
+    sm_grid_barrier(f.bar, gridDim.x);
+    STAMP(1);
+
+    uint32_t round = 0, complete = 0;
+    for (;;) {
+        a.round = round;
+        a.counter_idx = round & 31;
+        if (round == 0) {
+            for (uint32_t c = gw; c < nc; c += n_gw) sm_round_pair(a, T, W, capable, c, 0, lane, n_edges, base_bit);
+        } else {
+            for (u64 g = gw; g < (u64) nc * K; g += n_gw) {
+                const uint32_t c = (uint32_t) (g / K), j = (uint32_t) (g % K);
+                if (c == 0 || j >= a.cnt_in[c - 1]) continue;           // (warp-uniform) nothing new to run here
+                sm_round_pair(a, T, W, capable, c, j, lane, n_edges, base_bit);
+            }
+        }
+        STAMP(2);
+        sm_grid_barrier(f.bar, gridDim.x);
+        // ---- links over the pairs now complete; publish the counts for the next round ----
+        for (u64 g = (u64) blockIdx.x * blockDim.x + threadIdx.x; g < (u64) nc * K; g += (u64) gridDim.x * blockDim.x) {
+            const uint32_t c = (uint32_t) (g / K), i = (uint32_t) (g % K);
+            sm_link_pair(a, f.cnt_alloc, c, i);
+            if (i == 0) f.cnt_done[c] = min(f.cnt_alloc[c], K);
+        }
+        sm_grid_barrier(f.bar, gridDim.x);
+        STAMP(3);
+        if (blockIdx.x == 0) {
+            sm_walk_cta<1024>(a);
+            __syncthreads();
+            if (a.walk_status[1]) sm_scan_cta(a, f.offsets, f.msgs_base, f.n_msgs_out);   // (written by this CTA's thread 0)
+        }
+        STAMP(4);
+        sm_grid_barrier(f.bar, gridDim.x);
+        STAMP(5);
+        round++;
+        complete = ld_acquire_u32(a.walk_status + 1);
+        if (complete || ld_acquire_u32(a.overflow) != 0 || round >= f.max_rounds) break;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *f.rounds_out = round;
+    if (complete) {
+        // (the walk's CTA has already scanned the counts, in front of the last barrier)
+        for (uint32_t c = gw; c < nc; c += n_gw) sm_gather_chunk(a, f.offsets, f.msgs_out, f.msgs_base, f.msgs_cap, c, lane);
+    }
+    STAMP(7);
 }
 
 // ---------------------------------------------------------------------------------------

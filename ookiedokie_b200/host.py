@@ -22,7 +22,7 @@ EXPORTS = [
     "ookd_fir_init", "ookd_fir_deinit", "ookd_fir_get_total_decimation", "ookd_fir_desc",
     "ookd_device_init", "ookd_device_deinit", "ookd_device_sm_desc", "ookd_device_num_bits", "ookd_device_name",
     "ookd_device_format", "ookd_device_message", "ookd_device_generate_runs", "ookd_device_toggles",
-    "ookd_cfg_init", "ookd_rx", "ookd_tx", "ookd_rx_print",
+    "ookd_cfg_init", "ookd_rx", "ookd_tx", "ookd_rx_print", "ookd_rx_request_stop",
 ]
 
 

@@ -23,6 +23,9 @@
 #define OPT_SYNC_TIMEOUT 0x95
 #define OPT_VERSION 0x250
 #define OPT_GPU 0x251
+#define OPT_GPUS 0x252
+#define OPT_WINDOW 0x253
+#define OPT_GPU_IDS 0x254
 
 static const struct option long_options[] = {
     { "rx", required_argument, 0, 'r' },
@@ -51,6 +54,9 @@ static const struct option long_options[] = {
     { "help", no_argument, 0, 'h' },
     { "version", no_argument, 0, OPT_VERSION },
     { "gpu", required_argument, 0, OPT_GPU },
+    { "gpus", required_argument, 0, OPT_GPUS },
+    { "window", required_argument, 0, OPT_WINDOW },
+    { "gpu-ids", required_argument, 0, OPT_GPU_IDS },
     { 0, 0, 0, 0 }
 };
 
@@ -69,6 +75,8 @@ static void usage(const char *argv0)
     printf("Receive options:\n");
     printf("  -T, --rx-threshold <value>    On/Off threshold. Range is 0.0 to 1.0. Default: 0.1\n");
     printf("  -F, --rx-filter <filename>    Filter name or path; \"none\" disables filtering.\n");
+    printf("  -R, --rx-rec <[type,]file>    Record the filtered samples (SC16Q11) to a file.\n");
+    printf("  --rx-rec-input                Record the input samples instead of the filtered ones.\n");
     printf("  -B, --rx-rec-dig <filename>   Save the digital signal transitions to a CSV file.\n");
     printf("  --rx-fmt <fmt>                \"csv\" or \"pretty\" (default).\n\n");
     printf("SDR configuration options:\n");
@@ -77,7 +85,10 @@ static void usage(const char *argv0)
     printf("Sample stream options:\n");
     printf("  --samples-per-buffer <n>      Buffer size the decode semantics are defined on.\n\n");
     printf("Other options:\n");
-    printf("  --gpu <n>                     CUDA device ordinal.\n");
+    printf("  --gpu <n>                     CUDA device ordinal (first one with --gpus).\n");
+    printf("  --gpus <n>                    Time-shard every window over n GPUs (FIR halos, carries stitched on the host).\n");
+    printf("  --gpu-ids <a,b,...>           The same with explicit CUDA ordinals.\n");
+    printf("  --window <samples>            Samples per decode window (default 2^26 per GPU).\n");
     printf("  -v, --verbosity <level>       verbose, debug, info, warning, error, critical, silent.\n");
     printf("  -h, --help                    Show this help text.\n\n");
 }
@@ -168,10 +179,26 @@ int main(int argc, char *argv[])
                 cfg.rx_threshold = (float) v;
                 break;
             }
-            case 'R':
-            case OPT_RX_REC_INPUT:
-                fprintf(stderr, "Error: --rx-rec is not supported by this build.\n");
-                return EXIT_FAILURE;
+            case 'R': {                                 /* get_rx_recorder, src/main.c:209-242: [type,]filename */
+                if (cfg.rx_rec) {
+                    fprintf(stderr, "Error: RX recording parameters already specified.\n");
+                    return EXIT_FAILURE;
+                }
+                char *sep = strchr(optarg, ',');
+                if (sep) {
+                    *sep = '\0';
+                    if (strcasecmp(optarg, "bladerf_file")) {
+                        fprintf(stderr, "Error: recorder type \"%s\" is not available; this build supports bladerf_file.\n",
+                                optarg);
+                        return EXIT_FAILURE;
+                    }
+                    cfg.rx_rec = sep + 1;
+                } else {
+                    cfg.rx_rec = optarg;
+                }
+                break;
+            }
+            case OPT_RX_REC_INPUT: cfg.rx_rec_input = true; break;
             case 'B': cfg.rx_rec_dig = optarg; break;
             case 'F':
                 if (cfg.rx_filter) {
@@ -213,6 +240,40 @@ int main(int argc, char *argv[])
             case OPT_NUM_BUFFERS: case OPT_NUM_TRANSFERS: case OPT_STREAM_TIMEOUT: case OPT_SYNC_TIMEOUT:
                 break;                                  /* live-hardware settings: no effect on files */
             case OPT_GPU: cfg.gpu_id = atoi(optarg); break;
+            case OPT_GPUS: {
+                const long v = strtol(optarg, &end, 0);
+                if (end == optarg || *end || v < 1 || v > 64) {
+                    fprintf(stderr, "Invalid number of GPUs: %s\n", optarg);
+                    return EXIT_FAILURE;
+                }
+                cfg.n_gpus = (unsigned int) v;
+                break;
+            }
+            case OPT_GPU_IDS: {                         /* explicit ordinals, e.g. 0,2,4,6 (a device may repeat) */
+                static int32_t ids[64];
+                unsigned int n = 0;
+                char *tok = strtok(optarg, ",");
+                while (tok && n < 64) {
+                    ids[n++] = atoi(tok);
+                    tok = strtok(NULL, ",");
+                }
+                if (n == 0 || tok) {
+                    fprintf(stderr, "Invalid GPU list.\n");
+                    return EXIT_FAILURE;
+                }
+                cfg.gpu_ids = ids;
+                cfg.n_gpus = n;
+                break;
+            }
+            case OPT_WINDOW: {
+                const unsigned long long v = strtoull(optarg, &end, 0);
+                if (end == optarg || *end || v < 1) {
+                    fprintf(stderr, "Invalid window size (in samples): %s\n", optarg);
+                    return EXIT_FAILURE;
+                }
+                cfg.window_samples = v;
+                break;
+            }
             case 'v': {
                 enum ookd_log_level lvl;
                 if (!parse_level(optarg, &lvl)) {
@@ -230,7 +291,7 @@ int main(int argc, char *argv[])
 
     int status;
     if (direction == 0) {
-        if (!cfg.device && !cfg.rx_rec_dig) {            /* validate_cfg, src/main.c:244-283 */
+        if (!cfg.device && !cfg.rx_rec_dig && !cfg.rx_rec) {    /* validate_cfg, src/main.c:244-283 */
             fprintf(stderr, "Error: Either a target device or recording parameters must be specified.\n");
             return EXIT_FAILURE;
         }
@@ -238,6 +299,10 @@ int main(int argc, char *argv[])
     } else if (direction == 1) {
         if (!cfg.device) {
             fprintf(stderr, "Error: A target device must be specified.\n");
+            return EXIT_FAILURE;
+        }
+        if (cfg.rx_rec) {
+            fprintf(stderr, "Error: --rx-rec cannot be specified with --tx\n");
             return EXIT_FAILURE;
         }
         if (cfg.rx_filter) {

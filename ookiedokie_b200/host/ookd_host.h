@@ -102,6 +102,11 @@ struct ookd_cfg {                       /* the fields of struct ookiedokie_cfg t
     const char *device;                 /* device name / path, may be NULL (edges only)       */
     const char *rx_filter;              /* NULL => default "fs128_fs16_dec4"; "none" => off   */
     const char *rx_rec_dig;             /* --rx-rec-dig CSV, may be NULL                      */
+    const char *rx_rec;                 /* --rx-rec SC16Q11 recording, may be NULL (src/ookiedokie.c:248-270) */
+    bool     rx_rec_input;              /* --rx-rec-input: record the input instead of the filtered samples   */
+    unsigned int n_gpus;                /* --gpus / --gpu-ids: GPUs a window is time-sharded over (0/1 => one) */
+    const int32_t *gpu_ids;             /* --gpu-ids: their CUDA ordinals; NULL => gpu_id, gpu_id + 1, ...     */
+    uint64_t window_samples;            /* samples per decode window, 0 => default (2^26 per GPU)             */
     enum ookd_rx_fmt rx_fmt;
     float    rx_threshold;
     unsigned int samplerate;
@@ -115,6 +120,7 @@ struct ookd_cfg {                       /* the fields of struct ookiedokie_cfg t
 void ookd_cfg_init(struct ookd_cfg *cfg);               /* defaults of src/ookiedokie_cfg.c:27-38 */
 int  ookd_rx(const struct ookd_cfg *cfg);               /* 0 on success */
 int  ookd_tx(const struct ookd_cfg *cfg);
+void ookd_rx_request_stop(void);                        /* what SIGINT / SIGTERM do: finish the window, then stop */
 
 /* rx_print (src/ookiedokie.c:181-220) */
 void ookd_rx_print(FILE *out, enum ookd_rx_fmt fmt, bool *first_print, const struct ookd_keyval_list *kv);

@@ -130,7 +130,7 @@ class _ShmExchange:
 
 
 _shm = {}
-SHM_SLOT_BYTES = 112 + 16384 * 56
+SHM_SLOT_BYTES = 112 + 65536 * 56
 
 
 def _same_host(world):
@@ -145,14 +145,23 @@ def _shm_exchange(rank, world):
     key = world
     if key not in _shm:
         ex = None
-        try:
-            ok = os.path.isdir("/dev/shm") and _same_host(world)
-            flags = [None] * world
-            dist.all_gather_object(flags, bool(ok))
-            if all(flags):
+        import platform
+        # plain stores publish the payload before the sequence number: only on x86-64 (total store order)
+        ok = os.path.isdir("/dev/shm") and platform.machine() in ("x86_64", "AMD64") and _same_host(world)
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok))
+        if all(flags):
+            try:
                 ex = _ShmExchange(rank, world, SHM_SLOT_BYTES)
-        except Exception:
-            ex = None
+                made = True
+            except Exception:
+                ex, made = None, False
+            # the constructor's outcome is agreed on collectively too: one rank without the mapping would take the
+            # collective path while the others spin on the slots
+            flags = [None] * world
+            dist.all_gather_object(flags, made)
+            if not all(flags):
+                ex = None
         _shm[key] = ex
     return _shm[key]
 
@@ -173,7 +182,11 @@ def stitch_and_gather(runner, rank, world, msg_cap=None, decoded=None):
     isz = MSG_DTYPE.itemsize
     rec = res["msgs_raw"]
     ex = _shm_exchange(rank, world) if msg_cap is None else None
-    if ex is not None and REC_BYTES + len(rec) * isz <= SHM_SLOT_BYTES:
+    if ex is not None and REC_BYTES + len(rec) * isz > SHM_SLOT_BYTES:
+        # a rank-local fallback would leave the other ranks spinning on the shared-memory slots: refuse loudly instead
+        raise RuntimeError(f"shared-memory stitch: {len(rec)} messages exceed the slot capacity "
+                           f"({(SHM_SLOT_BYTES - REC_BYTES) // isz}); raise shard.SHM_SLOT_BYTES")
+    if ex is not None:
         # ranks of one host: records and message lists go through shared memory, no device round trip
         hdr = carry_to_bytes(exit_c) + carry_to_bytes(entry_used) + np.array([0, len(rec), 0, 0], dtype=np.uint32).tobytes()
         payload = np.concatenate([np.frombuffer(hdr, dtype=np.uint8), rec.view(np.uint8).reshape(-1)])
@@ -341,3 +354,199 @@ class GpuShardRunner:
         res, ex = self.gpu.resolve(entry)
         self._acc(res)
         return res, ex
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Stitch WITHOUT a per-step rendezvous (ranks of one host).
+#
+# stitch_and_gather() makes every rank wait, every step, until the slowest rank has published: the per-GPU decode
+# takes the same ~1 ms everywhere, so what the lock-step adds is the jitter of N host processes.  Here a rank
+# publishes its record for step s into slot s % RING of a shared-memory ring and goes on; the record of step s-1 is
+# confirmed one step later, when everybody has normally long published it:
+#
+#   record  = state (1 provisional / 2 final) | exit carry | entry used | message count | messages
+#   rank r's record for step s is FINAL as soon as the records of ranks 0..r for that step are consistent (each
+#   entry used equals the predecessor's exit): no rank has to wait for anybody's confirmation, only for data.
+#   Otherwise the lowest inconsistent rank re-runs its state-machine stage from its predecessor's (final) exit and
+#   republishes; the ranks above it wait for their predecessor's FINAL record and do the same if needed.
+#   Rank 0 assembles the message list of step s from the FINAL records of all ranks.
+#
+# A handle's tables must survive until its step is confirmed (resolve re-uses them), hence two handles used
+# alternately and confirmation of step s-1 before step s+1 is enqueued (bench.py run_steps_multi).
+# ---------------------------------------------------------------------------------------------------------------
+class _ShmRing:
+    HDR = 64
+    RING = 4
+
+    def __init__(self, rank, world, slot_bytes):
+        import mmap
+        import uuid
+        self.rank, self.world, self.slot = rank, world, self.HDR + slot_bytes
+        name = [f"/dev/shm/ookd_ring_{os.getpid()}_{uuid.uuid4().hex}" if rank == 0 else None]
+        dist.broadcast_object_list(name, src=0)
+        self.path = name[0]
+        size = self.RING * world * self.slot
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(size)
+        dist.barrier()
+        self.f = open(self.path, "r+b")
+        self.mm = mmap.mmap(self.f.fileno(), size)
+        self.buf = np.frombuffer(self.mm, dtype=np.uint8)
+        dist.barrier()
+        if rank == 0:
+            os.unlink(self.path)
+        self.step = 0                        # steps published so far by this rank (same on every rank by construction)
+
+    def slot_of(self, step, r):
+        o = ((step % self.RING) * self.world + r) * self.slot
+        return self.buf[o:o + self.slot]
+
+    def publish(self, step, state, payload):
+        sl = self.slot_of(step, self.rank)
+        n = payload.size
+        if n > self.slot - self.HDR:
+            raise RuntimeError("shared-memory stitch: record exceeds the slot capacity; raise shard.SHM_SLOT_BYTES")
+        sl[0:8].view(np.uint64)[0] = 0                               # invalidate while the payload changes
+        sl[self.HDR:self.HDR + n] = payload
+        sl[8:16].view(np.uint64)[0] = n
+        sl[0:8].view(np.uint64)[0] = (step + 1) * 4 + state          # published (x86-64: stores are not reordered)
+
+    def read(self, step, r, want_final, timeout_s=120.0):
+        """Record of rank r for `step` (waits for it; with want_final for its FINAL version).  -> (state, bytes copy)."""
+        import time
+        sl = self.slot_of(step, r)
+        seq = sl[0:8].view(np.uint64)
+        t0, spins = None, 0
+        while True:
+            v = int(seq[0])
+            if v // 4 == step + 1 and (v % 4 == 2 or (not want_final and v % 4 == 1)):
+                ln = int(sl[8:16].view(np.uint64)[0])
+                data = sl[self.HDR:self.HDR + ln].copy()
+                if int(seq[0]) == v:                                  # not republished while we copied
+                    return v % 4, data
+                continue
+            spins += 1
+            if spins > 2000:
+                if t0 is None:
+                    t0 = time.perf_counter()
+                elif time.perf_counter() - t0 > timeout_s:
+                    raise RuntimeError(f"shared-memory stitch: rank {r} did not publish step {step}")
+                time.sleep(0)
+
+
+_ring = {}
+_last_path = ["none"]
+
+
+def stitch_description():
+    """Which exchange the last multi-rank steps really used (recorded in the bench line)."""
+    return _last_path[0]
+
+
+def _shm_ring(rank, world):
+    key = world
+    if key not in _ring:
+        import platform
+        ok = os.path.isdir("/dev/shm") and platform.machine() in ("x86_64", "AMD64") and _same_host(world)
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(ok))
+        ring = None
+        if all(flags):
+            try:
+                ring = _ShmRing(rank, world, SHM_SLOT_BYTES)
+                made = True
+            except Exception:
+                ring, made = None, False
+            flags = [None] * world
+            dist.all_gather_object(flags, made)
+            if not all(flags):
+                ring = None
+        _ring[key] = ring
+    return _ring[key]
+
+
+class PipelinedStitcher:
+    """finish(runner, decoded) once per step, in step order; drain() before the results are used."""
+
+    def __init__(self, rank, world):
+        self.rank, self.world = rank, world
+        self.ring = _shm_ring(rank, world) if world > 1 else None
+        self.pending = []                    # [step, runner, result, exit carry, entry used, final?]
+        self.last_messages = None
+        self.last = None
+        self.resolves = 0
+        _last_path[0] = ("shared-memory ring, no per-step rendezvous (records confirmed one step later); NCCL only for "
+                         "the barriers and the timing all-reduce" if self.ring is not None else
+                         "lock-step: one all-gather (NCCL) of carries + message blocks per step" if world > 1 else "n/a")
+
+    @staticmethod
+    def _payload(exit_c, entry_used, rec):
+        hdr = carry_to_bytes(exit_c) + carry_to_bytes(entry_used) + np.array([0, len(rec), 0, 0], dtype=np.uint32).tobytes()
+        return np.concatenate([np.frombuffer(hdr, dtype=np.uint8), rec.view(np.uint8).reshape(-1)])
+
+    def confirm_pending(self):
+        """Confirm every step published so far (normally the previous one, whose records everybody has long published).
+        Must run before the handle of such a step is given new work: a wrong entry is repaired on its tables."""
+        while self.pending:
+            self._confirm(self.pending.pop(0))
+
+    def publish(self, runner, decoded):
+        """Publish this step's record without waiting for anybody.  -> (result, exit)."""
+        res, exit_c = decoded if decoded is not None else runner.decode(None)
+        if self.world == 1:
+            self.last_messages = res["msgs_raw"]
+            return res, exit_c
+        if self.ring is None:
+            res, exit_c, rounds, msgs = stitch_and_gather(runner, self.rank, self.world, decoded=(res, exit_c))
+            self.last_messages = msgs
+            return res, exit_c
+        ring = self.ring
+        step = ring.step
+        ring.step += 1
+        entry_used = tuple(res["entry_used"])
+        ring.publish(step, 1, self._payload(exit_c, entry_used, res["msgs_raw"]))
+        self.pending.append([step, runner, res, exit_c, entry_used])
+        return res, exit_c
+
+    def finish(self, runner, decoded, confirm_now=False):
+        """confirm_pending() + publish() (+ immediate confirmation: needed when the step's handle is re-used at once).
+        -> (result, exit, rounds, messages or None): the confirmed message list of a step appears in last_messages
+        (rank 0) once that step has been confirmed."""
+        self.confirm_pending()
+        res, exit_c = self.publish(runner, decoded)
+        if confirm_now:
+            self.confirm_pending()
+        return res, exit_c, 1, self.last_messages
+
+    def _confirm(self, item):
+        from .binding import MSG_DTYPE
+        step, runner, res, exit_c, entry_used = item
+        ring, rank, world = self.ring, self.rank, self.world
+        if rank > 0:
+            # records of ranks 0..rank-1 as published (provisional is enough while everything is consistent)
+            recs = [ring.read(step, r, False)[1] for r in range(rank)]
+            mine = carry_to_bytes(entry_used)
+            ok = recs[rank - 1][:48].tobytes() == mine and all(
+                recs[r][48:96].tobytes() == recs[r - 1][:48].tobytes() for r in range(1, rank))
+            if not ok:
+                # somebody below (or this rank) entered its shard in the wrong state: wait for the predecessor's FINAL
+                # record and re-run the state-machine stage from its exit if that is not what was assumed
+                _, pred = ring.read(step, rank - 1, True)
+                true_entry = carry_from_bytes(pred[:48].tobytes())
+                if true_entry != entry_used:
+                    res, exit_c = runner.resolve(true_entry)
+                    entry_used = true_entry
+                    self.resolves += 1
+        ring.publish(step, 2, self._payload(exit_c, entry_used, res["msgs_raw"]))
+        self.last = (res, exit_c)
+        if rank == 0:
+            parts = [res["msgs_raw"].view(np.uint8).reshape(-1)]
+            for r in range(1, world):
+                _, d = ring.read(step, r, True)
+                parts.append(d[REC_BYTES:])
+            self.last_messages = np.concatenate(parts).view(MSG_DTYPE)
+
+    def drain(self):
+        while self.pending:
+            self._confirm(self.pending.pop(0))

@@ -539,11 +539,19 @@ static inline uint64_t oo_mix64(uint64_t z)
     return z ^ (z >> 31);
 }
 
-static inline int32_t oo_noise(uint64_t seed, uint64_t ctr, int32_t scale)
+static inline int64_t oo_ih4(uint64_t r)
 {
-    const uint64_t r = oo_mix64(oo_mix64(seed) ^ (ctr * 0xD1342543DE82EF95ull));
-    const int64_t s = (int64_t) ((r & 0xFFFF) + ((r >> 16) & 0xFFFF) +
-                                 ((r >> 32) & 0xFFFF) + ((r >> 48) & 0xFFFF)) - 131070;
+    return (int64_t) ((r & 0xFFFF) + ((r >> 16) & 0xFFFF) + ((r >> 32) & 0xFFFF) + ((r >> 48) & 0xFFFF)) - 131070;
+}
+
+static inline int32_t oo_noise(uint64_t seed, uint64_t ctr, int32_t scale, uint32_t terms)
+{
+    const uint64_t base = oo_mix64(seed) ^ (ctr * 0xD1342543DE82EF95ull);
+    int64_t s = oo_ih4(oo_mix64(base));
+    if (terms == 12) {
+        s += oo_ih4(oo_mix64(base ^ (1ull * 0xA24BAED4963EE407ull)));
+        s += oo_ih4(oo_mix64(base ^ (2ull * 0xA24BAED4963EE407ull)));
+    }
     const int64_t v = s * (int64_t) scale + (1 << 23);
     return (int32_t) (v >> 24);         /* arithmetic shift: floor => round half up */
 }
@@ -556,6 +564,13 @@ static inline int16_t oo_clip(int32_t v)
 void ookd_oracle_synth(int16_t *iq, uint64_t first_sample, uint64_t n_samples,
                        const uint64_t *toggles, uint64_t n_toggles,
                        int32_t i_on, int32_t q_on, int32_t noise_scale, uint64_t seed)
+{
+    ookd_oracle_synth_ex(iq, first_sample, n_samples, toggles, n_toggles, i_on, q_on, noise_scale, seed, 4);
+}
+
+void ookd_oracle_synth_ex(int16_t *iq, uint64_t first_sample, uint64_t n_samples,
+                          const uint64_t *toggles, uint64_t n_toggles,
+                          int32_t i_on, int32_t q_on, int32_t noise_scale, uint64_t seed, uint32_t noise_terms)
 {
     /* k = number of toggles <= n */
     uint64_t lo = 0, hi = n_toggles;
@@ -572,8 +587,8 @@ void ookd_oracle_synth(int16_t *iq, uint64_t first_sample, uint64_t n_samples,
         const int on = (int) (k & 1);
         int32_t vi = on ? i_on : 0, vq = on ? q_on : 0;
         if (noise_scale != 0) {
-            vi += oo_noise(seed, 2 * n, noise_scale);
-            vq += oo_noise(seed, 2 * n + 1, noise_scale);
+            vi += oo_noise(seed, 2 * n, noise_scale, noise_terms);
+            vq += oo_noise(seed, 2 * n + 1, noise_scale, noise_terms);
         }
         iq[2 * j] = oo_clip(vi);
         iq[2 * j + 1] = oo_clip(vq);

@@ -108,6 +108,10 @@ void ookd_oracle_rx_free(ookd_oracle_rx_result *res);
 void ookd_oracle_synth(int16_t *iq, uint64_t first_sample, uint64_t n_samples,
                        const uint64_t *toggles, uint64_t n_toggles,
                        int32_t i_on, int32_t q_on, int32_t noise_scale, uint64_t seed);
+/* noise_terms = 4 (as above) or 12 (three draws: Irwin-Hall(12), close to Gaussian, tails to +-6 sigma) */
+void ookd_oracle_synth_ex(int16_t *iq, uint64_t first_sample, uint64_t n_samples,
+                          const uint64_t *toggles, uint64_t n_toggles,
+                          int32_t i_on, int32_t q_on, int32_t noise_scale, uint64_t seed, uint32_t noise_terms);
 
 #ifdef __cplusplus
 }

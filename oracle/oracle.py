@@ -87,6 +87,8 @@ def lib():
         L.ookd_oracle_rx_free.argtypes = [C.POINTER(_RxResult)]
         L.ookd_oracle_synth.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64,
                                         C.c_int32, C.c_int32, C.c_int32, C.c_uint64]
+        L.ookd_oracle_synth_ex.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64,
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32]
         _lib = L
     return _lib
 
@@ -271,11 +273,11 @@ def rx(iq_i16, filter_stages, device, threshold_=0.1, samples_per_buffer=8192, s
     return out
 
 
-def synth(n_samples, toggles, i_on, q_on, noise_scale, seed, first_sample=0):
+def synth(n_samples, toggles, i_on, q_on, noise_scale, seed, first_sample=0, noise_terms=4):
     tg = np.ascontiguousarray(toggles, dtype=np.uint64)
     iq = np.empty((n_samples, 2), dtype=np.int16)
-    lib().ookd_oracle_synth(iq.ctypes.data, first_sample, n_samples, tg.ctypes.data, len(tg),
-                            int(i_on), int(q_on), int(noise_scale), int(seed))
+    lib().ookd_oracle_synth_ex(iq.ctypes.data, first_sample, n_samples, tg.ctypes.data, len(tg),
+                               int(i_on), int(q_on), int(noise_scale), int(seed), int(noise_terms))
     return iq
 
 
@@ -283,9 +285,10 @@ def synth(n_samples, toggles, i_on, q_on, noise_scale, seed, first_sample=0):
 _IH4_STD = (4.0 * (65536.0 ** 2 - 1.0) / 12.0) ** 0.5
 
 
-def noise_scale_for_sigma(sigma):
+def noise_scale_for_sigma(sigma, noise_terms=4):
     """Q24 multiplier that makes the integer noise have std `sigma` (in full-scale units, 1.0 = 2048 LSB)."""
-    return int(round(sigma * 2048.0 / _IH4_STD * (1 << 24)))
+    std = _IH4_STD * (noise_terms / 4.0) ** 0.5
+    return int(round(sigma * 2048.0 / std * (1 << 24)))
 
 
 def on_level(amplitude, phase_rad):

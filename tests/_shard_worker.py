@@ -76,6 +76,33 @@ def main():
             msgs = msgs_to_tuples(raw, nbytes) if rank == 0 else None
             if rank == 0:
                 assert [tuple(m) for m in msgs] == [tuple(m) for m in full["msgs"]], cap
+    elif len(sys.argv) > 2 and sys.argv[2] == "pipelined":
+        # the rendezvous-free form bench.py uses at N > 1: records published into the shared-memory ring, each step
+        # confirmed one step later; more steps than ring slots, fresh runner per step (as handles alternate)
+        from ookiedokie_b200.binding import msgs_to_tuples
+        st = S.PipelinedStitcher(rank, world)
+        assert st.ring is not None, "shared-memory ring unavailable"
+        seen = 0
+        for step in range(7):
+            r = OracleShardRunner(dev, 3000000, full["bits"][lo:hi], lo, spb)
+            decoded = r.decode(None)
+            st.confirm_pending()
+            if rank == 0 and step > 0:
+                assert [tuple(m) for m in msgs_to_tuples(st.last_messages, nbytes)] == [tuple(m) for m in full["msgs"]], step
+                seen += 1
+            st.publish(r, decoded)
+            runner.calls += r.calls
+        st.drain()
+        rounds = 1
+        msgs = msgs_to_tuples(st.last_messages, nbytes) if rank == 0 else None
+        if rank == 0:
+            assert seen == 6
+        # a second stitcher on the same ring continues the step numbering
+        st2 = S.PipelinedStitcher(rank, world)
+        r = OracleShardRunner(dev, 3000000, full["bits"][lo:hi], lo, spb)
+        st2.finish(r, r.decode(None), confirm_now=True)
+        if rank == 0:
+            assert [tuple(m) for m in msgs_to_tuples(st2.last_messages, nbytes)] == [tuple(m) for m in full["msgs"]]
     else:
         res, exit_c, rounds = S.stitch(runner, rank, world)
         msgs = S.gather_messages(res["msgs"], rank, world, nbytes)

@@ -25,6 +25,13 @@ def test_synth_matches_oracle():
         ref = O.synth(total, tog, 1376, 1375, scale, seed)
         got = B.synth(total, tog, 1376, 1375, scale, seed)
         assert np.array_equal(ref, got)
+    # twelve-term (near-Gaussian) noise
+    sc = O.noise_scale_for_sigma(0.1, 12)
+    ref = O.synth(total, tog, 600, -100, sc, 11, noise_terms=12)
+    got = B.synth(total, tog, 600, -100, sc, 11, noise_terms=12)
+    assert np.array_equal(ref, got)
+    resid = ref[:12000, 0].astype(np.float64)                 # lead-in silence: pure noise
+    assert abs(resid.std() / 204.8 - 1.0) < 0.05 and np.abs(resid).max() > 3.5 * 204.8
     # offset window
     ref = O.synth(5000, tog, 1945, 0, O.noise_scale_for_sigma(0.05), 3, first_sample=11000)
     got = B.synth(5000, tog, 1945, 0, O.noise_scale_for_sigma(0.05), 3, first_sample=11000)
@@ -241,7 +248,8 @@ def test_every_code_path_gives_the_same_decode(devname, filt):
     stages = O.load_filter(filt)
     ref = O.rx(iq, stages, dev, samples_per_buffer=8192, want_bits=True)
     for flags in (0, B.FLAG_SYNC_TAIL, B.FLAG_NO_TMA, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_SHARE_SMS,
-                  B.FLAG_FORCE_GENERIC, B.FLAG_NO_TMA | B.FLAG_SYNC_TAIL, B.FLAG_NO_GRAPH):
+                  B.FLAG_FORCE_GENERIC, B.FLAG_NO_TMA | B.FLAG_SYNC_TAIL, B.FLAG_NO_GRAPH, B.FLAG_UNFUSED_SM,
+                  B.FLAG_UNFUSED_SM | B.FLAG_NO_GRAPH):
         for chunk_buffers in (0, 5):
             g = B.Gpu(filter_stages=stages, sm=util.sm_spec(dev, stages), threshold=0.1, samples_per_buffer=8192, flags=flags,
                       sm_chunk_buffers=chunk_buffers)

@@ -143,3 +143,71 @@ def test_shard_count_invariance_at_scale():
             prev_exit = ex
         assert np.array_equal(np.concatenate(got_msgs), whole_msgs), shards
         assert np.array_equal(np.concatenate(got_edges), whole_edges), shards
+
+
+@pytest.mark.parametrize("devname,filt,spb", [("p3l-nexa2012", "fs32_fs4", 8192), ("unknown-remote1", "fs128_fs16_dec4", 1001),
+                                              ("p3l-nexa2012", "fs64_fs8", 4096)])
+def test_multi_gpu_api_matches_oracle(devname, filt, spb):
+    """ookd_gpu_multi_*: one window time-sharded over several handles of ONE process (the same device repeated on a
+    one-GPU box), stitched in C; host input, device input, and two consecutive windows chained through the carry."""
+    import torch
+    dev = O.load_device(devname)
+    fields = util.nexa_fields if "nexa" in devname else util.remote_fields
+    iq, msgs, _ = util.capture(dev, 9, sigma=0.03, amplitude=0.8, phase=0.4, seed=21, fields=fields, glitches=((9000, 100),))
+    stages = O.load_filter(filt)
+    sm = util.sm_spec(dev, stages)
+    ref = O.rx(iq, stages, dev, samples_per_buffer=spb)
+    assert len(ref["msgs"]) >= 3
+    for ids in ([0], [0, 0], [0, 0, 0, 0, 0]):
+        m = B.MultiGpu(ids, filter_stages=stages, sm=sm, samples_per_buffer=spb, sm_chunk_buffers=5)
+        got, _ = m.decode(iq)
+        assert got["msgs"] == ref["msgs"], ids
+        fb, edges = m.edges()
+        assert fb == ref["first_bit"] and np.array_equal(edges, ref["edges"]), ids
+        assert got["n_out"] == ref["n_out"] and got["shards_used"] == len(ids)
+        # two windows: [0, cut) not last, [cut, n) last, entered with the first one's exit
+        halo = m.halo
+        align = int(np.lcm(spb, O.filter_total_decimation(stages)))
+        cut = max(align, (len(iq) * 3 // 5) // align * align)
+        while cut < halo:
+            cut += align
+        a, carry = m.decode(iq[:cut], 0, cut, last=False)
+        e1 = m.edges()[1]
+        b, _ = m.decode(iq[cut - halo:], cut, len(iq) - cut, last=True, entry=carry)
+        assert a["msgs"] + b["msgs"] == ref["msgs"], ids
+        assert np.array_equal(np.concatenate([e1, m.edges()[1]]), ref["edges"]), ids
+        # device-resident shards: one pointer per handle
+        n = len(iq)
+        bufs, ptrs = [], []
+        flat = np.ascontiguousarray(iq).reshape(-1)
+        for g in range(len(ids)):
+            first, cnt = m.shard_range(0, n, g)
+            h = min(halo, first)
+            t = torch.from_numpy(flat[2 * (first - h): 2 * (first + cnt)].copy()).cuda() if cnt else torch.zeros(2, dtype=torch.int16).cuda()
+            bufs.append(t)
+            ptrs.append(t.data_ptr())
+        got_d, _ = m.decode(None, 0, n, last=True, device_ptrs=ptrs)
+        assert got_d["msgs"] == ref["msgs"], ids
+        m.close()
+
+
+def test_filtered_sc16q11_matches_recorder_semantics():
+    """ookd_gpu_filtered_sc16q11 = (int16_t)(x * 2048.0f) of the exact filtered samples, per shard"""
+    dev = O.load_device("unknown-remote1")
+    iq, _, _ = util.capture(dev, 3, sigma=0.05, amplitude=0.3, phase=0.9, seed=3, fields=util.remote_fields)
+    for filt, spb in (("fs128_fs16_dec4", 8192), ("fs32_fs4", 4096)):
+        stages = O.load_filter(filt)
+        f = O.rx(iq, stages, None, samples_per_buffer=spb, want_filtered=True)["filtered"]
+        want = np.trunc(f * np.float32(2048.0)).astype(np.int32).astype(np.int16)
+        g = B.Gpu(filter_stages=stages, sm=util.sm_spec(dev, stages), samples_per_buffer=spb)
+        g.decode(iq)
+        assert np.array_equal(g.filtered_sc16q11(), want)
+        # as two shards
+        dec, halo = g.total_decimation, g.halo
+        align = int(np.lcm(spb, dec))
+        cut = (len(iq) // 2) // align * align
+        _, carry = g.decode_shard(iq[:cut], 0, cut, False, None)
+        a = g.filtered_sc16q11()
+        g.decode_shard(iq[cut - halo:], cut, len(iq) - cut, True, carry)
+        b = g.filtered_sc16q11()
+        assert np.array_equal(np.concatenate([a, b]), want)

@@ -99,3 +99,31 @@ def test_rx_matches_reference(case):
     else:
         assert header == want[0]
         assert rows == want[1:]
+
+
+REC = json.load(open(os.path.join(GOLD, "rec.json")))
+
+
+def recorder_bytes(case, rec_input):
+    """What the reference's recorder writes (src/ookiedokie.c:248-270 + complexf_to_sc16q11, src/complexf.h:87-96),
+    restated on the oracle's filtered samples."""
+    dev, iq, _ = build_capture(case)
+    stages = None if case["filter"] == "none" else O.load_filter(case["filter"] or "fs128_fs16_dec4")
+    spb = case["spb"]
+    if rec_input or stages is None:                     # no filter forces input recording (src/main.c:668-671)
+        n_eff = (len(iq) + spb - 1) // spb * spb
+        out = np.zeros((n_eff, 2), np.int16)
+        out[:len(iq)] = iq                              # int16 -> float -> (int16_t)(x * 2048.0f) is the identity
+        return out
+    f = O.rx(iq, stages, None, samples_per_buffer=spb, want_filtered=True)["filtered"]
+    return np.trunc(f * np.float32(2048.0)).astype(np.int32).astype(np.int16)
+
+
+@pytest.mark.parametrize("rec", REC, ids=lambda r: r["name"])
+def test_recorder_restatement_matches_reference(rec):
+    import hashlib
+    case = next(c for c in RX if c["name"] == rec["name"])
+    out = recorder_bytes(case, rec["rec_input"])
+    assert len(out) == rec["n_samples"]
+    assert out[rec["probe_at"]:rec["probe_at"] + 16].reshape(-1).tolist() == rec["probe"]
+    assert hashlib.sha256(out.tobytes()).hexdigest() == rec["sha256"]

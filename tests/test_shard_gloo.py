@@ -50,3 +50,21 @@ def test_fused_stitch_and_gather(world, tmp_path):
         assert p.wait(timeout=300) == 0
     res = json.load(open(out))
     assert res["ok"] and res["n"] == res["want"] == 5, res
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pipelined_ring_stitch(world, tmp_path):
+    """PipelinedStitcher (no per-step rendezvous; shared-memory ring; confirmation one step later, incl. the repair of
+    shards entered in the wrong state) gives the sequential decode at every step."""
+    out = str(tmp_path / "result.json")
+    port = _free_port()
+    procs = []
+    for rank in range(world):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_shard_worker.py"), out, "pipelined"], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    res = json.load(open(out))
+    assert res["ok"] and res["n"] == res["want"] == 5, res
+    calls0 = json.load(open(out + ".rank0"))["calls"]
+    assert all(c == "decode" for c in calls0)

@@ -145,9 +145,45 @@ def make_rx():
     json.dump(out, open(os.path.join(GOLD, "rx.json"), "w"), indent=0)
 
 
+REC_CASES = [("nexa_awgn02_fs32", False), ("remote1_snr_dec4", False), ("remote1_spb1001", False), ("nexa_nofilter", False),
+             ("nexa_spb5000", True), ("nexa_default_filter", False)]
+
+
+def make_rec():
+    """--rx-rec / --rx-rec-input recordings of the reference (src/ookiedokie.c:248-270): SHA-256, length and the first
+    samples of the SC16Q11 file it writes."""
+    import hashlib
+    out = []
+    by_name = {c["name"]: c for c in RX_CASES}
+    for name, rec_input in REC_CASES:
+        case = by_name[name]
+        dev, iq, msgs = build_capture(case)
+        with tempfile.TemporaryDirectory() as td:
+            cap, rec = os.path.join(td, "c.sc16q11"), os.path.join(td, "rec.sc16q11")
+            iq.tofile(cap)
+            args = [REF, "--rx", "bladerf_file", "-A", cap, "-d", case["device"], "--rx-fmt", "csv", "-R", rec,
+                    "--samples-per-buffer", str(case["spb"]), "-T", str(case["thr"])]
+            if case["filter"] is not None:
+                args += ["-F", case["filter"]]
+            if rec_input:
+                args += ["--rx-rec-input"]
+            subprocess.run(args, check=True, capture_output=True, text=True)
+            data = open(rec, "rb").read()
+        x = np.frombuffer(data, dtype=np.int16).reshape(-1, 2)
+        nz = int(np.flatnonzero(np.abs(x).sum(1) > 100)[0]) if np.any(np.abs(x).sum(1) > 100) else 0
+        out.append(dict(name=name, rec_input=rec_input, n_samples=int(len(x)), sha256=hashlib.sha256(data).hexdigest(),
+                        probe_at=nz, probe=x[nz:nz + 16].reshape(-1).tolist()))
+        print("rec", name, rec_input, len(x))
+    json.dump(out, open(os.path.join(GOLD, "rec.json"), "w"), indent=0)
+
+
 if __name__ == "__main__":
     assert REF and FIR_TEST, "build oracle/_ref first (make -C oracle)"
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "rec":
+        make_rec()
+        sys.exit(0)
     make_fir()
     make_tx()
     make_rx()
+    make_rec()
