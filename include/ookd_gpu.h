@@ -180,9 +180,11 @@ struct ookd_gpu_config {
                                                 each SM so that the other decode's tail kernels can run beside it */
 #define OOKD_FLAG_NO_GRAPH       64u         /* enqueue the decode tail (edges, state machine, gather, read-back)
                                                 operation by operation instead of replaying its CUDA graph      */
-#define OOKD_FLAG_UNFUSED_SM    128u          /* state-machine stage as separate kernels (anchors, rounds, link, walk,
-                                                scan, gather) with blindly enqueued repair rounds instead of the one
-                                                cooperative kernel that iterates on the device until the chain resolves */
+#define OOKD_FLAG_FUSED_SM      128u          /* experimental: the whole state-machine stage (anchors, rounds until the
+                                                chain resolves, link, walk, scan, gather) as ONE cooperative kernel with
+                                                grid barriers instead of a dozen launches.  Same results; measured slower
+                                                on B200 (a grid barrier costs what a launch boundary costs, and the seed
+                                                round runs 1.7x longer inside it), so it is off by default */
 #define OOKD_FLAG_NO_SCREEN      2u          /* no screening: the exact tiled kernels compute every output with the
                                                 reference's in-order MACs (same decisions, fp32-issue bound)        */
 

@@ -25,7 +25,7 @@ FLAG_NO_TMA = 8
 FLAG_SYNC_TAIL = 16
 FLAG_SHARE_SMS = 32
 FLAG_NO_GRAPH = 64
-FLAG_UNFUSED_SM = 128
+FLAG_FUSED_SM = 128
 
 # every symbol include/ookd_gpu.h declares
 EXPORTS = [

@@ -122,6 +122,10 @@ struct ookd_gpu {
         u64 edge_cap = 0, msg_cap = 0, n_copy = 0;
         uint32_t rounds = 0;
         int cur = 0;
+        // the call's own arguments (a warm decode whose tables do not resolve is repeated without warm-up)
+        const int16_t *arg_iq = nullptr;
+        int arg_is_dev = 0, arg_last = 0;
+        u64 arg_first = 0, arg_n = 0;
     } pend;
 
     char err[256] = {0};
@@ -857,13 +861,13 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
                     // chunk-long latency
                     a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
                     sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
-                    sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a);
+                    sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a, nullptr, nullptr, 0, nullptr);
                     h->launches += 2;
                 }
             }
             a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
             sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
-            sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a);
+            sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a, nullptr, nullptr, 0, nullptr);
             h->launches += 2;
             CU(h, cudaGetLastError());
             CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 256, cudaMemcpyDeviceToHost, h->s_compute));
@@ -1032,6 +1036,10 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     cur = 0;
     rounds = 0;
     CU(h, cudaMemsetAsync((char *) h->scalars.p + 24, 0, 232, h->s_compute));      // [24, 256): keeps the refine counters
+    if (getenv("OOKD_DEBUG")) {
+        CU(h, cudaMemsetAsync((char *) h->scalars.p + 384, 0xFF, 8, h->s_compute));    // earliest start: atomicMin
+        CU(h, cudaMemsetAsync((char *) h->scalars.p + 392, 0, 120, h->s_compute));
+    }
     {
         const unsigned ctas = h->n_sm * (unsigned) edge_ctas_per_sm;
         edge_local_kernel<<<eg < ctas ? eg : ctas, EDGE_NT, 0, h->s_compute>>>(x);
@@ -1075,9 +1083,9 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
         cur = 1;                                            // tab_cnt[1] = slots handed out; [0] = complete pairs
     } else {
     // ---- state machine burst ----
+    a.cnt_out = (uint32_t *) h->tab_cnt[0].p;               // (the anchor kernel gives every chunk its seed's slot 0)
     sm_anchor_kernel<<<nc, 32, 0, h->s_compute>>>(a);
     h->launches++;
-    fill_u32_kernel<<<(nc + 255) / 256, 256, 0, h->s_compute>>>((uint32_t *) h->tab_cnt[0].p, nc, 1u);     // slot 0 = the seed
     for (uint32_t r = 0; r < h->burst_rounds; r++) {
         a.round = rounds;
         a.counter_idx = rounds & 31;
@@ -1099,16 +1107,12 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
         {
             a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
             sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
-            sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a);
+            // (the walk that completes the chain also scans the message counts and writes the ordered list)
+            sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a, (uint32_t *) h->slot_off.p, (SmMsg *) h->msgs_dev.p, msg_cap,
+                                                               (u64 *) h->scalars.p + 1);
             h->launches += 2;
         }
     }
-    // ---- ordered gather of the chosen pairs' messages ----
-    CU(h, cudaMemcpyAsync(h->slot_off.p, h->slot_count.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice, h->s_compute));
-    scan_u32_kernel<<<1, SCAN_NT, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
-    sm_gather_table_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a, (const uint32_t *) h->slot_off.p,
-                                                                       (SmMsg *) h->msgs_dev.p, msg_cap);
-    h->launches += 2;
     }
     CU(h, cudaGetLastError());
     CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 336, cudaMemcpyDeviceToHost, h->s_compute));
@@ -1222,10 +1226,10 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
     if (h->fused_sm) rounds = *(const uint32_t *) (hs + 52);
     if (h->fused_sm && getenv("OOKD_DEBUG")) {
         const long long *st = (const long long *) (hs + 384);
-        fprintf(stderr, "[ookd] fused sm (cycles of CTA 0): prologue %lld, anchors %lld, barrier %lld, round %lld, barrier+links %lld, "
-                        "walk+scan %lld, barrier %lld, gather %lld; total %lld; %u round(s), %u chunks\n",
-                st[0] - st[8] - 0, st[0] - st[8], st[1] - st[0], st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4],
-                st[7] - st[5], st[7] - st[8], rounds, nc);
+        auto us = [&](int i) { return (double) (st[1 + i] - st[0]) * 1e-3; };
+        fprintf(stderr, "[ookd] fused sm, last CTA past each point (us from the first CTA's start): anchors %.1f, barrier %.1f, "
+                        "round %.1f, barrier %.1f, links %.1f, barrier %.1f, walk+scan %.1f, barrier %.1f, end %.1f; %u round(s), %u chunks\n",
+                us(0), us(1), us(2), us(8), us(9), us(3), us(4), us(5), us(7), rounds, nc);
     }
     while (!h->fused_sm && overflow == 0 && walk_complete != 1 && rounds < 16) {
         SmArgs a = fast_sm_args(h, h->pend.e0);
@@ -1241,7 +1245,7 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
         rounds++;
         a.cnt_in = (const uint32_t *) h->tab_cnt[cur].p;
         sm_link_kernel<<<(unsigned) (((u64) nc * TAB_K + 127) / 128), 128, 0, h->s_compute>>>(a);
-        sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a);
+        sm_walk_kernel<<<1, SM_WALK_NT, 0, h->s_compute>>>(a, nullptr, nullptr, 0, nullptr);
         CU(h, cudaMemcpyAsync(h->slot_off.p, h->slot_count.p, sizeof(uint32_t) * nc, cudaMemcpyDeviceToDevice, h->s_compute));
         scan_u32_kernel<<<1, SCAN_NT, 0, h->s_compute>>>((uint32_t *) h->slot_off.p, nc, (u64 *) h->scalars.p + 1);
         sm_gather_table_kernel<<<(nc + 127) / 128, 128, 0, h->s_compute>>>(a, (const uint32_t *) h->slot_off.p,
@@ -1403,7 +1407,7 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sm_fused_kernel, SM_FUSED_NT, 0) != cudaSuccess) per_sm = 0;
         h->fused_grid_max = (unsigned) per_sm * (unsigned) prop.multiProcessorCount;
-        h->fused_sm = coop != 0 && h->fused_grid_max > 0 && !(h->flags & OOKD_FLAG_UNFUSED_SM);
+        h->fused_sm = coop != 0 && h->fused_grid_max > 0 && (h->flags & OOKD_FLAG_FUSED_SM) != 0;
     }
 
     // ---- filter ----
@@ -1642,6 +1646,11 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     h->base_bit = 0;
     SmCarry e0{};
     if (entry) carry_to_dev(*entry, e0);
+    h->pend.arg_iq = iq;
+    h->pend.arg_is_dev = iq_is_device_ptr;
+    h->pend.arg_first = first_sample;
+    h->pend.arg_n = n_samples;
+    h->pend.arg_last = last;
     h->pend.d_in = d_in;
     h->pend.in_base = in_base;
     h->pend.in_valid_end = in_valid_end;
@@ -1659,7 +1668,27 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     return OOKD_OK;
 }
 
+static int decode_end_once(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd_gpu_result *res);
+
 int ookd_gpu_decode_end(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd_gpu_result *res)
+{
+    if (!h) return OOKD_ERR_ARG;
+    if (!h->pend.active) return fail(h, OOKD_ERR_STATE, "decode_end without decode_begin");
+    const bool was_warm = h->warm;
+    int rc = decode_end_once(h, exit_, res);
+    if (rc == OOKD_ERR_STATE && was_warm && h->pend.arg_iq) {
+        // The chunk tables of a shard entered from warm-up history did not resolve (a long cascade of chunks entered in
+        // unforeseen states).  Decode it again from an explicit RESET entry: that path always terminates (Jacobi
+        // fallback); result.entry_used then says RESET and the caller's stitch corrects it with ookd_gpu_resolve.
+        ookd_sm_carry reset;
+        memset(&reset, 0, sizeof(reset));
+        rc = ookd_gpu_decode_begin(h, h->pend.arg_iq, h->pend.arg_is_dev, h->pend.arg_first, h->pend.arg_n, h->pend.arg_last, &reset);
+        if (!rc) rc = decode_end_once(h, exit_, res);
+    }
+    return rc;
+}
+
+static int decode_end_once(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd_gpu_result *res)
 {
     if (!h) return OOKD_ERR_ARG;
     if (!h->pend.active) return fail(h, OOKD_ERR_STATE, "decode_end without decode_begin");

@@ -149,7 +149,15 @@ int ookd_gpu_multi_decode(ookd_gpu_multi *m, const void *iq, int iq_is_device_pt
     // ---- stitch: shard g must have been entered in the state shard g-1 was left in ----
     for (uint32_t g = 1; g < used; g++) {
         if (memcmp(&m->res[g].entry_used, &m->exits[g - 1], sizeof(ookd_sm_carry)) != 0) {
-            const int rc = ookd_gpu_resolve(m->h[g], &m->exits[g - 1], &m->exits[g], &m->res[g]);
+            int rc = ookd_gpu_resolve(m->h[g], &m->exits[g - 1], &m->exits[g], &m->res[g]);
+            if (rc == OOKD_ERR_STATE) {
+                // the shard's tables cannot take the corrected entry (a long cascade): decode it again, entered explicitly
+                const uint64_t ha = sf[g] < m->halo ? sf[g] : m->halo;
+                const int16_t *p = iq_is_device_ptrs ? ((const int16_t *const *) iq)[g]
+                                                     : (const int16_t *) iq + 2 * ((sf[g] - ha) - (first_sample - halo_avail0));
+                rc = ookd_gpu_decode_shard(m->h[g], p, iq_is_device_ptrs ? 1 : 0, sf[g], sn[g], (last && g + 1 == used) ? 1 : 0,
+                                           &m->exits[g - 1], &m->exits[g], &m->res[g]);
+            }
             if (rc) return mfail(m, rc, "resolve of shard %u: %s", g, ookd_gpu_last_error(m->h[g]));
             m->resolves++;
         }

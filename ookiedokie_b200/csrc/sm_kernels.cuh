@@ -916,6 +916,7 @@ __global__ void __launch_bounds__(32) sm_anchor_kernel(const SmArgs a)
     if (c >= a.n_chunks) return;
     load_table(T, a.tab);
     sm_anchor_chunk(a, T, c, threadIdx.x & 31, n_edges, base_bit);
+    if (threadIdx.x == 0 && a.cnt_out) a.cnt_out[c] = 1u;    // every chunk starts with one pair: its seed (slot 0)
 }
 
 // One WARP per (chunk, slot): the work is a chain of dependent steps, so what matters is latency, not lanes; giving
@@ -1130,6 +1131,10 @@ __global__ void __launch_bounds__(128) sm_link_kernel(const SmArgs a)
     if (c >= a.n_chunks) return;
     if (a.walk_status[1]) return;                            // already resolved: keep the links the walk used
     sm_link_pair(a, a.cnt_in, c, i);
+    // the common case -- every seed pair links to the next chunk's seed pair -- is recognised without walking
+    if (i == 0 && c >= a.first_chunk && c + 1 < a.n_chunks && a.link[(u64) c * K] != 0) {
+        atomicAdd(&a.n_ran[8 + (a.round & 7)], 1u);
+    }
 }
 
 // One CTA resolves the chain from chunk first_chunk / slot *start_slot.  Chasing 1 link per step through global
@@ -1226,10 +1231,73 @@ __device__ __forceinline__ void sm_walk_cta(const SmArgs &a)
     }
 }
 
-__global__ void __launch_bounds__(SM_WALK_NT) sm_walk_kernel(const SmArgs a)
+// Exclusive scan of the chosen pairs' message counts by one CTA (offsets[c], total); the copy itself is done by the
+// chunks' own warps after the next barrier.
+__device__ __forceinline__ void sm_scan_cta(const SmArgs &a, uint32_t *offsets, u64 base, u64 *total_out)
+{
+    __shared__ u64 s_w[32];
+    const uint32_t nt = blockDim.x, nc = a.n_chunks;
+    const uint32_t per = (nc + nt - 1) / nt;
+    const uint32_t lo = min(nc, threadIdx.x * per), hi = min(nc, lo + per);
+    u64 sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += a.msg_counts[i];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u64 up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (uint32_t) d) inc += up;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    u64 before = 0, all = 0;
+    for (uint32_t w = 0; w < (nt + 31) / 32; w++) {
+        if (w < warp) before += s_w[w];
+        all += s_w[w];
+    }
+    u64 run = before + inc - sum;
+    for (uint32_t c = lo; c < hi; c++) {
+        offsets[c] = (uint32_t) run;
+        run += a.msg_counts[c];
+    }
+    if (threadIdx.x == 0) *total_out = base + all;
+}
+
+// gather_out != null: a walk that completes the chain also scans the chosen pairs' message counts and writes the
+// ordered message list (the single-synchronisation tail: no separate scan / gather launches).
+__global__ void __launch_bounds__(SM_WALK_NT) sm_walk_kernel(const SmArgs a, uint32_t *offsets, SmMsg *gather_out, u64 gather_cap,
+                                                             u64 *n_msgs_out)
 {
     if (a.walk_status[1]) return;                            // resolved by an earlier walk of this burst
-    sm_walk_cta<4096>(a);
+    const uint32_t K = a.tab_k;
+    if (a.n_ran[8 + (a.round & 7)] == 0 && *a.start_slot == 0 && a.cnt_in[a.first_chunk] >= 1) {
+        // every seed pair links to the next one: the chain is the seed pairs
+        for (uint32_t c = threadIdx.x; c < a.n_chunks; c += blockDim.x) {
+            a.chosen[c] = 0;
+            a.msg_counts[c] = (c >= a.first_chunk) ? a.tab_nmsg[(u64) c * K] : 0u;
+        }
+        if (threadIdx.x == 0) {
+            a.n_ran[16 + (a.round & 15)] = a.n_chunks;
+            a.walk_status[0] = a.n_chunks;
+            a.walk_status[1] = 1u;
+            *a.final_exit = a.tab_exit[(u64) (a.n_chunks - 1) * K];
+            if (a.warm && a.first_chunk == 0) *a.final_entry = a.tab_exit[0];
+        }
+    } else {
+        sm_walk_cta<4096>(a);
+    }
+    if (!gather_out) return;
+    __syncthreads();
+    if (!a.walk_status[1]) return;                           // (written by this CTA's thread 0)
+    sm_scan_cta(a, offsets, 0, n_msgs_out);
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < a.n_chunks; c += blockDim.x) {
+        const uint32_t n = a.msg_counts[c];
+        const SmMsg *src = a.slots + ((u64) c * K + a.chosen[c]) * a.slot_cap;
+        for (uint32_t i = 0; i < n; i++) {
+            if ((u64) offsets[c] + i < gather_cap) gather_out[offsets[c] + i] = src[i];
+        }
+    }
 }
 
 __global__ void sm_gather_table_kernel(const SmArgs a, const uint32_t *offsets, SmMsg *out, u64 out_cap)
@@ -1288,43 +1356,15 @@ __device__ __forceinline__ void sm_grid_barrier(uint32_t *bar, uint32_t n_ctas)
             __threadfence();
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1) : "memory");
         } else {
-            while (ld_acquire_u32(bar + 1) == gen) __nanosleep(64);
+            uint32_t ns = 32;
+            while (ld_acquire_u32(bar + 1) == gen) {
+                __nanosleep(ns);
+                if (ns < 512) ns *= 2;                       // (hundreds of pollers on one line: back off)
+            }
         }
         __threadfence();
     }
     __syncthreads();
-}
-
-// Exclusive scan of the chosen pairs' message counts by one CTA (offsets[c], total); the copy itself is done by the
-// chunks' own warps after the next barrier.
-__device__ __forceinline__ void sm_scan_cta(const SmArgs &a, uint32_t *offsets, u64 base, u64 *total_out)
-{
-    __shared__ u64 s_w[32];
-    const uint32_t nt = blockDim.x, nc = a.n_chunks;
-    const uint32_t per = (nc + nt - 1) / nt;
-    const uint32_t lo = min(nc, threadIdx.x * per), hi = min(nc, lo + per);
-    u64 sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += a.msg_counts[i];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 inc = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const u64 up = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-        if (lane >= (uint32_t) d) inc += up;
-    }
-    if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
-    u64 before = 0, all = 0;
-    for (uint32_t w = 0; w < (nt + 31) / 32; w++) {
-        if (w < warp) before += s_w[w];
-        all += s_w[w];
-    }
-    u64 run = before + inc - sum;
-    for (uint32_t c = lo; c < hi; c++) {
-        offsets[c] = (uint32_t) run;
-        run += a.msg_counts[c];
-    }
-    if (threadIdx.x == 0) *total_out = base + all;
 }
 
 // messages of chunk c's chosen pair -> their place in the ordered list (one warp)
@@ -1343,11 +1383,18 @@ __device__ __forceinline__ void sm_gather_chunk(const SmArgs &a, const uint32_t 
 
 // phase stamps of CTA 0 (SM clock), for OOKD_DEBUG: 0 anchors done, 1 past the barrier, 2 round done, 3 links done (past
 // the barrier), 4 walk + scan done, 5 past the barrier, 7 end; [8] = start
-#define STAMP(i) do { if (f.stamps && blockIdx.x == 0 && threadIdx.x == 0) f.stamps[i] = clock64(); } while (0)
+__device__ __forceinline__ long long global_ns()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// debug: [0] = earliest start, [1 + i] = time the LAST CTA passed point i (global timer, ns)
+#define STAMP(i) do { if (f.stamps && threadIdx.x == 0) atomicMax((unsigned long long *) f.stamps + 1 + (i), (unsigned long long) global_ns()); } while (0)
 
 __global__ void __launch_bounds__(SM_FUSED_NT) sm_fused_kernel(const SmFusedArgs f)
 {
-    STAMP(8);
+    if (f.stamps && threadIdx.x == 0) atomicMin((unsigned long long *) f.stamps, (unsigned long long) global_ns());
     SmArgs a = f.a;
     OOKD_SM_EDGE_HDR(a)
     const SmTable &T = *a.tab;
@@ -1388,12 +1435,14 @@ __global__ void __launch_bounds__(SM_FUSED_NT) sm_fused_kernel(const SmFusedArgs
         }
         STAMP(2);
         sm_grid_barrier(f.bar, gridDim.x);
+        STAMP(8);
         // ---- links over the pairs now complete; publish the counts for the next round ----
         for (u64 g = (u64) blockIdx.x * blockDim.x + threadIdx.x; g < (u64) nc * K; g += (u64) gridDim.x * blockDim.x) {
             const uint32_t c = (uint32_t) (g / K), i = (uint32_t) (g % K);
             sm_link_pair(a, f.cnt_alloc, c, i);
             if (i == 0) f.cnt_done[c] = min(f.cnt_alloc[c], K);
         }
+        STAMP(9);
         sm_grid_barrier(f.bar, gridDim.x);
         STAMP(3);
         if (blockIdx.x == 0) {

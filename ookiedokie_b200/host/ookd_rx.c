@@ -455,6 +455,10 @@ int ookd_rx(const struct ookd_cfg *cfg)
             if (rc == OOKD_OK && w > 0 && o.dev && memcmp(&res.entry_used, &prev_exit, sizeof(prev_exit)) != 0) {
                 /* the warm-up history led somewhere else than the previous window really ended: redo the state machine */
                 rc = ookd_gpu_resolve(g, &prev_exit, &exit_carry, &res);
+                if (rc == OOKD_ERR_STATE) {
+                    /* its tables cannot take the corrected entry (a long cascade): decode the window again, entered explicitly */
+                    rc = ookd_gpu_decode_shard(g, p, 0, cur->first_sample, cur->have, cur->last, &prev_exit, &exit_carry, &res);
+                }
             }
             if (rc != OOKD_OK) {
                 log_error("GPU decode failed: %s (%s)\n", ookd_gpu_strerror(rc), ookd_gpu_last_error(g));

@@ -248,8 +248,8 @@ def test_every_code_path_gives_the_same_decode(devname, filt):
     stages = O.load_filter(filt)
     ref = O.rx(iq, stages, dev, samples_per_buffer=8192, want_bits=True)
     for flags in (0, B.FLAG_SYNC_TAIL, B.FLAG_NO_TMA, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_SHARE_SMS,
-                  B.FLAG_FORCE_GENERIC, B.FLAG_NO_TMA | B.FLAG_SYNC_TAIL, B.FLAG_NO_GRAPH, B.FLAG_UNFUSED_SM,
-                  B.FLAG_UNFUSED_SM | B.FLAG_NO_GRAPH):
+                  B.FLAG_FORCE_GENERIC, B.FLAG_NO_TMA | B.FLAG_SYNC_TAIL, B.FLAG_NO_GRAPH, B.FLAG_FUSED_SM,
+                  B.FLAG_FUSED_SM | B.FLAG_NO_GRAPH):
         for chunk_buffers in (0, 5):
             g = B.Gpu(filter_stages=stages, sm=util.sm_spec(dev, stages), threshold=0.1, samples_per_buffer=8192, flags=flags,
                       sm_chunk_buffers=chunk_buffers)
