@@ -442,7 +442,7 @@ def main():
     fir = H.Fir(FILTER_NAME)
     dev = H.Device(DEVICE_NAME, FS // fir.total_decimation)
     depth = max(1, args.pipeline)
-    n_handles = max(depth, args.pipelined_depth, args.e2e_depth, 2 if world > 1 else 1)
+    n_handles = max(depth, args.pipelined_depth, args.e2e_depth, 3 if world > 1 else 1)
     flags = args.flags | (B.FLAG_SHARE_SMS if args.share else 0)
     gpus = [B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
                   flags=flags, sm_chunk_buffers=args.chunk_buffers, sm_warmup=1 if world > 1 else 0)
@@ -529,20 +529,33 @@ def main():
             out[0], out[1] = res, msgs
 
         if depth <= 1:
-            # One decode at a time on the GPU; the cross-rank exchange of step i (host only) is published without
-            # waiting for the other ranks and checked while the GPU already works on step i+1 (two handles: the tables
-            # of step i stay intact until its stitch is confirmed).
-            cur = S.GpuShardRunner(gpus[0], iq_arg, first, n, last)
-            cur.begin()
+            # One decode at a time on the GPU.  Step i+1 is enqueued the moment step i has completed (three handles used in
+            # turn: the tables of a step stay intact until its stitch is confirmed, one step later); everything else --
+            # reading the message list, publishing this step's record into the shared-memory ring without waiting for
+            # the other ranks, confirming the previous step, rank 0's concatenation -- happens while the GPU works.
+            res, ex = B.GpuResult(), B.SmCarry()
+            if isinstance(iq_arg, tuple):
+                p, is_dev = C.c_void_p(iq_arg[0]), 1
+            else:
+                p, is_dev = C.c_void_p(iq_arg.ctypes.data), 0
+            nh = min(3, len(gpus))
+            if L.ookd_gpu_decode_begin(gpus[0].h, p, is_dev, first, n, int(last), None):
+                raise SystemExit(f"decode_begin failed: {L.ookd_gpu_last_error(gpus[0].h).decode()}")
             for i in range(n_steps):
-                decoded = cur.decode(None)                    # waits for step i
-                st.confirm_pending()                          # step i-1: its handle is the one step i+1 goes to
-                nxt = None
+                g = gpus[i % nh]
+                if L.ookd_gpu_decode_end(g.h, C.byref(ex), C.byref(res)):                # waits for step i
+                    raise SystemExit(f"decode_end failed: {L.ookd_gpu_last_error(g.h).decode()}")
+                if nh < 3:
+                    st.confirm_pending()                      # (with two handles step i-1 must be settled before its handle is reused)
                 if i + 1 < n_steps:
-                    nxt = S.GpuShardRunner(gpus[(i + 1) % 2], iq_arg, first, n, last)
-                    nxt.begin()
-                finish(cur, decoded)
-                cur = nxt
+                    g2 = gpus[(i + 1) % nh]
+                    if L.ookd_gpu_decode_begin(g2.h, p, is_dev, first, n, int(last), None):
+                        raise SystemExit(f"decode_begin failed: {L.ookd_gpu_last_error(g2.h).decode()}")
+                runner = S.GpuShardRunner(g, iq_arg, first, n, last)
+                decoded = (g._result(res), ex.astuple())
+                runner._acc(decoded[0])
+                st.confirm_pending()
+                finish(runner, decoded)
         else:
             pending = []
             for i in range(n_steps):

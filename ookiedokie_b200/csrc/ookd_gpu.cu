@@ -63,6 +63,7 @@ struct ookd_gpu {
     bool tma = false;                 // TMA-staged screening kernel (screen_tma.cuh)
     bool screen2 = false;             // dec4 shape: screen + refine (else the exact tiled two-stage kernel)
     int screen_regs = 64;             // register cap of the TMA screening kernel (64 / 56 / 48)
+    bool screen_v2 = true;            // span statistics through dp2a, sums of I / Q only for loud spans (OOKD_SCREEN_V2=0: first form)
     bool fused_sm = true;             // state-machine stage as ONE cooperative kernel (sm_fused_kernel)
     unsigned fused_grid_max = 0;      // CTAs of it that can be co-resident on this device
     unsigned n_sm = 148;
@@ -287,12 +288,12 @@ encode_tiled_fn tensor_map_encoder()
 
 typedef void (*screen_tma_kernel_t)(const CUtensorMap, const ScreenTmaArgs, const ScreenParams);
 
-screen_tma_kernel_t screen_tma_fn(int dec, int regs)
+screen_tma_kernel_t screen_tma_fn(int dec, int regs, bool v2)
 {
-    if (dec == 1) {
-        return regs <= 48 ? fir_screen_tma_kernel<1, 48> : regs <= 56 ? fir_screen_tma_kernel<1, 56> : fir_screen_tma_kernel<1, 64>;
-    }
-    return regs <= 48 ? fir_screen_tma_kernel<4, 48> : regs <= 56 ? fir_screen_tma_kernel<4, 56> : fir_screen_tma_kernel<4, 64>;
+#define OOKD_PICK(D, V) (regs <= 48 ? fir_screen_tma_kernel<D, 48, V> : regs <= 56 ? fir_screen_tma_kernel<D, 56, V> : fir_screen_tma_kernel<D, 64, V>)
+    if (dec == 1) return v2 ? OOKD_PICK(1, true) : OOKD_PICK(1, false);
+    return v2 ? OOKD_PICK(4, true) : OOKD_PICK(4, false);
+#undef OOKD_PICK
 }
 
 // OOKD_FLAG_SHARE_SMS: the persistent screening kernels of different handles on one device must not overlap
@@ -375,7 +376,7 @@ int launch_screen_tma(ookd_gpu *h, const ScreenArgs &sa, const ScreenParams &sp,
     cudaEvent_t *tok = (share && use_token) ? screen_token(h->device) : nullptr;
     if (tok) CU(h, cudaStreamWaitEvent(h->s_compute, *tok, 0));
     const unsigned grid = (unsigned) (tiles < ctas ? tiles : ctas);
-    screen_tma_fn(dec, h->screen_regs)<<<grid, STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(tmap, ta, sp);
+    screen_tma_fn(dec, h->screen_regs, h->screen_v2)<<<grid, STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(tmap, ta, sp);
     if (tok) CU(h, cudaEventRecord(*tok, h->s_compute));
     return OOKD_OK;
 }
@@ -1470,15 +1471,18 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     }
     h->n_sm = (unsigned) prop.multiProcessorCount;
     if (const char *e = getenv("OOKD_SCREEN_REGS")) h->screen_regs = atoi(e);
+    if (const char *e = getenv("OOKD_SCREEN_V2")) h->screen_v2 = atoi(e) != 0;
     h->persist = (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) == 0;
     h->tma = h->persist && !(h->flags & OOKD_FLAG_NO_TMA);       // both screened shapes (one stage 32/1, dec4)
     if (h->tma) {
         for (int dec : {1, 4}) {
             for (int regs : {48, 56, 64}) {
-                if (cudaFuncSetAttribute(screen_tma_fn(dec, regs), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         STMA_SMEM_BYTES) != cudaSuccess) {
-                    cudaGetLastError();
-                    h->tma = false;
+                for (bool v2 : {false, true}) {
+                    if (cudaFuncSetAttribute(screen_tma_fn(dec, regs, v2), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             STMA_SMEM_BYTES) != cudaSuccess) {
+                        cudaGetLastError();
+                        h->tma = false;
+                    }
                 }
             }
         }

@@ -118,10 +118,75 @@ __device__ __forceinline__ int stma_chunk_off(int u, int v)
 // DEC = 4: two stages 16/2 + 32/2 (fs128_fs16_dec4): 4 outputs per thread, composite window of 78 inputs = 5 spans
 //          back (the proofs and the elements needed are those of fir2_screen_kernel, fir_kernels.cuh section 4).
 // Tiles, a.out_lo / out_hi / bit_base are in OUTPUT indices; a tile is 4096 INPUT samples = 4096 / DEC outputs.
+// ---- span statistics, second form (V2) ----
+// |x|^2 = I*I + Q*Q through two dp2a per sample: with I = 256 I_hi + I_lo (I_hi = I >> 8 signed, I_lo = I & 255 unsigned),
+//   lo += I*I_lo + Q*Q_lo   (dp2a.lo, signed halves x unsigned bytes),   hi += I*I_hi + Q*Q_hi   (dp2a.hi, signed x signed)
+// and the running prefix is lo + 256 hi -- PRMT + 2 IDP + 1 shift-add per sample instead of two extractions, two IMADs,
+// the range guard and the add.  Every hi term is >= 0 and at most 2^23, so hi cannot overflow whatever the int16 input,
+// and hi_total < 2^20 implies a true span total below 2^28 + 2^27 < 2^29: the guard is ONE compare per span.
+__device__ __forceinline__ int dp2a_lo_s16_u8(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ int dp2a_hi_s16_s8(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ void screen_span_energy(const uint32_t (&w)[16], uint32_t (&pre)[16], uint32_t &hi_total)
+{
+    int lo = 0, hi = 0;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const uint32_t b = __byte_perm(w[e], 0u, 0x3120);      // bytes (I_lo, Q_lo, I_hi, Q_hi)
+        lo = dp2a_lo_s16_u8(w[e], b, lo);
+        hi = dp2a_hi_s16_s8(w[e], b, hi);
+        pre[e] = (uint32_t) (lo + (hi << 8));
+    }
+    hi_total = (uint32_t) hi;
+}
+
+__device__ __forceinline__ void screen_span_sums(const uint32_t (&w)[16], int &sx, int &sy)
+{
+    int xs = 0, ys = 0;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        xs += (int) (short) (w[e] & 0xFFFFu);
+        ys += ((int) w[e]) >> 16;
+    }
+    sx = xs;
+    sy = ys;
+}
+
+// The sums of I and Q only serve the "on" proof, which cannot succeed when one of the spans it covers is quiet (its
+// mean would sit far from part of the samples); a span whose whole energy is below the "off" bound skips them and
+// stores this marker instead.  Skipping is always safe: it can only leave outputs to the exact kernel.
+#define OOKD_XY_QUIET ((int) 0x80000000)
+
+// V2 statistics of one span: prefix energies, guarded total (bit 31 = out of range), sums or the quiet marker
+__device__ __forceinline__ void screen_span_stats_v2(const uint32_t (&w)[16], uint32_t (&pre)[16], int &sx, int &sy, uint32_t &tot,
+                                                     uint32_t k0)
+{
+    uint32_t hi_total;
+    screen_span_energy(w, pre, hi_total);
+    tot = (hi_total >= (1u << 20)) ? 0xFFFFFFFFu : pre[15];
+    if (tot >= k0) {
+        screen_span_sums(w, sx, sy);
+    } else {
+        sx = OOKD_XY_QUIET;
+        sy = 0;
+    }
+}
+
 // MAXR: register cap per thread.  64 = all the registers four resident CTAs can have; 56 / 48 leave 8 K / 16 K
 // registers per SM free, so that the latency-bound tail kernels of the PREVIOUS window (exact refine, edges, state
 // machine) can be resident beside the four screening CTAs of the current one (pipelined windows, ookd_gpu.cu).
-template <int DEC, int MAXR>
+template <int DEC, int MAXR, bool V2>
 __global__ void __maxnreg__(MAXR)
 fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaArgs ta, const ScreenParams sp)
 {
@@ -192,8 +257,14 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
         uint32_t w[16], p[16], gd;
         int xs, ys;
         load_span_slow(tile_in0(t_begin) - HT * SPT + (i64) u * SPT, w);
-        screen_span_stats(w, p, xs, ys, gd);
-        if (gd >> 25) p[15] = 0xFFFFFFFFu;
+        if constexpr (V2) {
+            uint32_t tot;
+            screen_span_stats_v2(w, p, xs, ys, tot, sp.k0);
+            p[15] = tot;
+        } else {
+            screen_span_stats(w, p, xs, ys, gd);
+            if (gd >> 25) p[15] = 0xFFFFFFFFu;
+        }
         store_row(0, u - HT, p, xs, ys);
     }
 
@@ -222,10 +293,15 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
         } else {
             load_span_slow(tile_in0(tile) + (i64) u * SPT, w);
         }
-        uint32_t pre[SPT], guard;
+        uint32_t pre[SPT], tot_own;                                         // tot_own bit 31 = "span out of range"
         int sx, sy;
-        screen_span_stats(w, pre, sx, sy, guard);
-        const uint32_t tot_own = (guard >> 25) ? 0xFFFFFFFFu : pre[15];     // bit 31 = "span out of range"
+        if constexpr (V2) {
+            screen_span_stats_v2(w, pre, sx, sy, tot_own, sp.k0);
+        } else {
+            uint32_t guard;
+            screen_span_stats(w, pre, sx, sy, guard);
+            tot_own = (guard >> 25) ? 0xFFFFFFFFu : pre[15];
+        }
         {
             uint32_t p[16];
 #pragma unroll
@@ -279,6 +355,7 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
                     const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
                     const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
                     on = fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi;
+                    if (V2 && (sx == OOKD_XY_QUIET || x1 == OOKD_XY_QUIET || x2 == OOKD_XY_QUIET)) on = false;
                 }
                 if (on) {
                     bits16 = 0xFFFFu;
@@ -338,6 +415,7 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
                 und = (e0 < sp.k0 ? 0u : 1u) | (e1 < sp.k0 ? 0u : 2u) | (e2 < sp.k0 ? 0u : 4u) | (e3 < sp.k0 ? 0u : 8u);
                 if (und) {
                     int X = sx, Y = sy;
+                    bool quiet = V2 && sx == OOKD_XY_QUIET;
 #pragma unroll
                     for (int k = 1; k <= 5; k++) {
                         int xk, yk;
@@ -345,6 +423,7 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
                                      : "r"(xy0 + (s * STMA_XY_ROWS + u - k + HT) * 8));
                         X += xk;
                         Y += yk;
+                        quiet = quiet || (V2 && xk == OOKD_XY_QUIET);
                     }
                     const float Xf = (float) X, Yf = (float) Y;
                     const float Q = (float) (t5 + mid4 + pre[15]);
@@ -352,7 +431,7 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
                     const float mu = sqrt_approx(m2) * sp.inv_n;
                     const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
                     const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
-                    if (fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi) {
+                    if (!quiet && fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi) {
                         bits4 = 0xF;
                         und = 0;
                     }

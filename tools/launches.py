@@ -1,5 +1,5 @@
-"""Summarise an ncu --csv launch list (gpu__time_duration.sum) of bench.py: one decode step = the launches up
-to and including sm_gather_table_kernel.  Prints the second step (shard resident in HBM) launch by launch and
+"""Summarise an ncu --csv launch list (gpu__time_duration.sum) of bench.py: one decode step = the launches from one
+FIR / threshold launch (or run of them) up to the next.  Prints the second step (shard resident in HBM) launch by launch and
 the last step (host input: one screening launch per 64 MiB piece) aggregated by kernel."""
 import collections
 import csv
@@ -11,13 +11,18 @@ h = rows[hdr]
 ki, vi = h.index('Kernel Name'), h.index('Metric Value')
 seq = [(r[ki].split('(')[0].replace('void ', ''), float(r[vi].replace(',', ''))) for r in rows[hdr + 2:] if len(r) > vi]
 steps, cur = [], []
+prev_screen = False
 for n, v in seq:
     if 'synth' in n:
         continue
-    cur.append((n, v))
-    if 'sm_gather' in n:
+    is_screen = 'fir_screen' in n or 'exact_tiled' in n
+    if is_screen and not prev_screen and cur:          # a decode starts with its first FIR / threshold launch
         steps.append(cur)
         cur = []
+    prev_screen = is_screen
+    cur.append((n, v))
+if cur:
+    steps.append(cur)
 print(f"{len(steps)} decode steps in the list")
 dev_step = steps[1] if len(steps) > 1 else steps[0]
 tot = sum(v for _, v in dev_step)
