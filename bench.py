@@ -319,11 +319,12 @@ def measure_c3(local_rank, peak):
            "ms_per_step": 1e3 * dt, "value": n / dt / 1e6, "unit": UNIT,
            "messages_transmitted": int(n // 210900), "messages_decoded": int(len(r["msgs_raw"])),
            "edges": r["n_edges"], "sm_rounds": r["sm_rounds"],
-           "screened": bool(r["refined_tiles"] == 0 and first["refined_tiles"] == 0),
+           "fir_mode": ["generic", "energy screen", "fma screen + exact refine of the rounding band", "exact"][r["fir_mode"]],
+           "refined_fraction": r["refined_blocks"] / (n / fir.total_decimation / 8.0),
            "fir_kernel_ms": fir_ms / steps,
            "hbm_frac_job": 4.0 * n / dt / 1e9 / peak,
            "fp32_issue_frac_fir": (64.0 * n / (fir_ms / steps * 1e-3)) / FP32_ISSUE_PER_S if fir_ms > 0 else None,
-           "note": "64 exact fp32 mul/add per input sample for this filter shape (32 with FMA screening)"}
+           "note": "fp32_issue_frac counts the reference's own 64 fp32 mul/add per input sample (the FMA pass issues 32)"}
     g.close()
     del d
     torch.cuda.empty_cache()

@@ -185,6 +185,9 @@ struct ookd_gpu_config {
                                                 grid barriers instead of a dozen launches.  Same results; measured slower
                                                 on B200 (a grid barrier costs what a launch boundary costs, and the seed
                                                 round runs 1.7x longer inside it), so it is off by default */
+#define OOKD_FLAG_FMA_SCREEN    256u          /* start with FMA screening (fused multiply-add pass, rigorous rounding band,
+                                                exact recomputation inside the band) instead of the energy proofs; a
+                                                handle switches to it by itself when the energy proofs decide too little */
 #define OOKD_FLAG_NO_SCREEN      2u          /* no screening: the exact tiled kernels compute every output with the
                                                 reference's in-order MACs (same decisions, fp32-issue bound)        */
 
@@ -210,7 +213,12 @@ struct ookd_gpu_result {
                                                 launch .. last, before the exact refine pass); with host input
                                                 this span also contains waiting for the H2D pieces            */
     uint32_t host_syncs;                     /* host<->device synchronisations the call needed            */
+    uint32_t fir_mode;                       /* how the decisions were taken: OOKD_FIR_*                   */
 };
+#define OOKD_FIR_GENERIC  0u                 /* shape-agnostic exact kernels, one launch per stage         */
+#define OOKD_FIR_SCREEN   1u                 /* energy proofs + exact refine of the undecided groups       */
+#define OOKD_FIR_FMA      2u                 /* fused multiply-add pass + exact refine inside the rounding band */
+#define OOKD_FIR_EXACT    3u                 /* tiled exact kernels for every output                       */
 
 typedef struct ookd_gpu ookd_gpu;
 

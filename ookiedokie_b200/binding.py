@@ -26,6 +26,7 @@ FLAG_SYNC_TAIL = 16
 FLAG_SHARE_SMS = 32
 FLAG_NO_GRAPH = 64
 FLAG_FUSED_SM = 128
+FLAG_FMA_SCREEN = 256
 
 # every symbol include/ookd_gpu.h declares
 EXPORTS = [
@@ -129,7 +130,7 @@ class GpuResult(C.Structure):
                 ("first_bit", C.c_uint32), ("sm_rounds", C.c_uint32), ("kernel_ms", C.c_float),
                 ("fir_ms", C.c_float), ("gpu_launches", C.c_uint32), ("refined_tiles", C.c_uint32),
                 ("refined_blocks", C.c_uint32), ("entry_is_provisional", C.c_uint32), ("entry_used", SmCarry),
-                ("screen_ms", C.c_float), ("host_syncs", C.c_uint32)]
+                ("screen_ms", C.c_float), ("host_syncs", C.c_uint32), ("fir_mode", C.c_uint32)]
 
 
 class Capture(C.Structure):
@@ -391,7 +392,7 @@ class Gpu:
                     screen_ms=float(res.screen_ms), host_syncs=int(res.host_syncs),
                     gpu_launches=int(res.gpu_launches), refined_tiles=int(res.refined_tiles),
                     refined_blocks=int(res.refined_blocks), entry_is_provisional=int(res.entry_is_provisional),
-                    entry_used=res.entry_used.astuple())
+                    entry_used=res.entry_used.astuple(), fir_mode=int(res.fir_mode))
 
     @property
     def halo(self):

@@ -107,9 +107,67 @@ struct TiledArgs {
     const uint32_t *tile_count;  // with tile_list: number of entries
 };
 
-template <int T, int R>
+// (parameter blocks of the screening kernels of section 3; the work list is shared with the FMA form below)
+struct ScreenParams {
+    uint32_t k0;             // off test: window energy (LSB^2) strictly below this => decision 0
+    float g_lo;              // |sum t_i| rounded down
+    float t2;                // ||t||_2 rounded up
+    float cg;                // gamma * ||t||_2 rounded up
+    float theta_hi;          // sqrt(P*) * 2048 grown by 1e-5
+    float inv_n;             // 1/48
+};
+
+struct ScreenArgs {
+    TiledArgs t;
+    uint32_t *work_list;     // OUTPUT: indices of 8-output groups (relative to t.bit_base) left to the exact path
+    uint32_t *work_count;    // number of groups pushed (may exceed work_cap: then the host redoes the range exactly)
+    uint32_t work_cap;
+    uint32_t tile_offset;    // first (4096-output) tile of this launch, numbered from t.out_lo
+    uint32_t n_tiles;        // tiles of this launch (persistent variant)
+};
+
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));      // max relative error 2^-23
+    return r;
+}
+
+// FMA screening (filter-and-refine): the same tiled kernel with ONE fused multiply-add per tap instead of a
+// rounded multiply and a rounded add -- half the fp32 instructions -- followed by a rigorous test of whether the reference's
+// decision can differ.  With y the exact sum, y_ref the reference's value (2T roundings) and y_f the fused one (T roundings),
+//     |y_ref - y_f| <= (g_ref + g_f) sum_i |t_i||x_i| <= (g_ref + g_f) ||t||_2 sqrt(E)       (both components together)
+// where E = window energy <= W m^2 (W samples in the window, m^2 = largest |x|^2 staged for the tile), g_* the usual
+// recursive-summation factors (host: make_fma_band, in double).  The reference decides 1 iff fl(re^2 + im^2) >= P*, i.e.
+// iff its magnitude is at least theta = sqrt(P*) up to 3 ulp; so with p_f the fused value's computed power,
+//     p_f >= (theta_hi + D)^2  =>  reference decides 1,        p_f < (theta_lo - D)^2  =>  reference decides 0,
+// D = c sqrt(m^2) (c = (g_ref + g_f) ||t||_2 sqrt(W), rounded up).  Anything in between (a few outputs per million on
+// real captures) goes to the work list and is recomputed by the exact group kernel: decisions stay bit-identical.
+struct FmaBand {
+    float c;                 // D = c * sqrt(m^2)
+    float theta_hi, theta_lo;    // sqrt(P*) grown / shrunk by the power's own rounding allowance
+};
+
+template <bool FMA>
+__device__ __forceinline__ float mac_sel(float acc, float tap, float x)
+{
+    if constexpr (FMA) {
+        return fmaf(tap, x, acc);
+    } else {
+        return mac_exact(acc, tap, x);
+    }
+}
+
+// classify one output of the fused path: 1 = surely on, 0 = surely off, 2 = the reference could decide either way
+__device__ __forceinline__ uint32_t fma_classify(float re, float im, float hi2, float lo2)
+{
+    const float p = fmaf(re, re, im * im);
+    return (p >= hi2) ? 1u : ((p < lo2) ? 0u : 2u);
+}
+
+template <int T, int R, bool FMA>
 __global__ void __launch_bounds__(256, 2)
-fir1_exact_tiled_kernel(const TiledArgs a, const TapsParam<T> taps)
+fir1_tiled_kernel(const ScreenArgs sa, const TapsParam<T> taps, const FmaBand band)
 {
     constexpr int NT = 256;
     constexpr int L = NT * R;                 // outputs per tile
@@ -117,8 +175,11 @@ fir1_exact_tiled_kernel(const TiledArgs a, const TapsParam<T> taps)
     constexpr int NS = L + HALO;              // staged samples
     constexpr int LOGR = (R == 8) ? 3 : 4;
     static_assert(R == 8 || R == 16, "R");
+    static_assert(!FMA || R == 8, "one thread = one 8-output group of the work list");
     __shared__ float2 s_x[NS + (NS >> LOGR) + 1];
+    __shared__ float s_m2[NT / 32];
 
+    const TiledArgs &a = sa.t;
     uint32_t n_tiles_here = gridDim.x;
     uint32_t stride = gridDim.x;
     uint32_t tile_it = blockIdx.x;
@@ -133,6 +194,7 @@ fir1_exact_tiled_kernel(const TiledArgs a, const TapsParam<T> taps)
 
         // ---- stage inputs: 4 samples (16 B) per thread per step ----
         const bool aligned = (((g0 - a.in_base) & 3) == 0) && ((((uintptr_t) a.in) & 15) == 0);
+        float m2 = 0.0f;
         for (int q = threadIdx.x; q < NS / 4; q += NT) {
             const i64 g = g0 + 4 * q;
             uint32_t w[4];
@@ -149,8 +211,15 @@ fir1_exact_tiled_kernel(const TiledArgs a, const TapsParam<T> taps)
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const int s = 4 * q + e;
-                s_x[s + (s >> LOGR)] = sc16q11_to_float2(w[e]);
+                const float2 x = sc16q11_to_float2(w[e]);
+                s_x[s + (s >> LOGR)] = x;
+                if constexpr (FMA) m2 = fmaxf(m2, fmaf(x.x, x.x, x.y * x.y));
             }
+        }
+        if constexpr (FMA) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xFFFFFFFFu, m2, d));
+            if ((threadIdx.x & 31) == 0) s_m2[threadIdx.x >> 5] = m2;
         }
         __syncthreads();
 
@@ -173,23 +242,55 @@ fir1_exact_tiled_kernel(const TiledArgs a, const TapsParam<T> taps)
         for (int i = 0; i < T; i++) {
 #pragma unroll
             for (int j = 0; j < R; j++) {
-                re[j] = mac_exact(re[j], taps.t[i], win[j + T - 1 - i].x);
-                im[j] = mac_exact(im[j], taps.t[i], win[j + T - 1 - i].y);
+                re[j] = mac_sel<FMA>(re[j], taps.t[i], win[j + T - 1 - i].x);
+                im[j] = mac_sel<FMA>(im[j], taps.t[i], win[j + T - 1 - i].y);
             }
         }
 
         uint32_t bits = 0;
+        bool unsure = false;
+        if constexpr (FMA) {
+            float mm = s_m2[0];
 #pragma unroll
-        for (int j = 0; j < R; j++) {
-            bits |= (power_exact(re[j], im[j]) >= a.pstar ? 1u : 0u) << j;
+            for (int q = 1; q < NT / 32; q++) mm = fmaxf(mm, s_m2[q]);
+            // D rounded up: sqrt.approx is within 2^-22, the products within a few ulp
+            const float D = band.c * sqrt_approx(mm) * 1.00001f;
+            const float hi = band.theta_hi + D, lo = fmaxf(band.theta_lo - D, 0.0f);
+            const float hi2 = hi * hi * 1.000001f, lo2 = lo * lo * 0.999999f;
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const uint32_t c = fma_classify(re[j], im[j], hi2, lo2);
+                bits |= (c & 1u) << j;
+                unsure = unsure || (c == 2u);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                bits |= (power_exact(re[j], im[j]) >= a.pstar ? 1u : 0u) << j;
+            }
         }
         const i64 o = o0 + (i64) threadIdx.x * R;
-        if (o < a.out_hi) {
+        const bool in_range = o < a.out_hi;
+        if (in_range) {
             // outputs past out_hi inside the last byte are masked by the consumers
             const i64 byte = (o - a.bit_base) >> 3;
             a.out_bits[byte] = (uint8_t) bits;
             if (R == 16) {
                 a.out_bits[byte + 1] = (uint8_t) (bits >> 8);
+            }
+        }
+        if constexpr (FMA) {
+            const bool push = unsure && in_range;
+            const uint32_t m_push = __ballot_sync(0xFFFFFFFFu, push);
+            if (m_push) {
+                const int lane = threadIdx.x & 31;
+                uint32_t slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(sa.work_count, (uint32_t) __popc(m_push));
+                slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+                if (push) {
+                    const uint32_t sl = slot0 + __popc(m_push & ((1u << lane) - 1));
+                    if (sl < sa.work_cap) sa.work_list[sl] = (uint32_t) ((o - a.bit_base) >> 3);
+                }
             }
         }
         __syncthreads();     // s_x is reused by the next tile of this CTA
@@ -227,31 +328,6 @@ fir1_exact_tiled_kernel(const TiledArgs a, const TapsParam<T> taps)
 //    If more groups are undecided than the work list holds (low-SNR captures), the host redoes the
 //    range with fir1_exact_tiled_kernel and stops screening on that handle.
 // =======================================================================================
-struct ScreenParams {
-    uint32_t k0;             // off test: window energy (LSB^2) strictly below this => decision 0
-    float g_lo;              // |sum t_i| rounded down
-    float t2;                // ||t||_2 rounded up
-    float cg;                // gamma * ||t||_2 rounded up
-    float theta_hi;          // sqrt(P*) * 2048 grown by 1e-5
-    float inv_n;             // 1/48
-};
-
-struct ScreenArgs {
-    TiledArgs t;
-    uint32_t *work_list;     // OUTPUT: indices of 8-output groups (relative to t.bit_base) left to the exact path
-    uint32_t *work_count;    // number of groups pushed (may exceed work_cap: then the host redoes the range exactly)
-    uint32_t work_cap;
-    uint32_t tile_offset;    // first (4096-output) tile of this launch, numbered from t.out_lo
-    uint32_t n_tiles;        // tiles of this launch (persistent variant)
-};
-
-__device__ __forceinline__ float sqrt_approx(float x)
-{
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));      // max relative error 2^-23
-    return r;
-}
-
 #ifndef OOKD_SCREEN_MINB
 #define OOKD_SCREEN_MINB 5
 #endif
@@ -887,16 +963,20 @@ __global__ void __launch_bounds__(256) fir2_refine_kernel(const ScreenArgs sa, c
 // ~77 instructions per input sample against the 64 the arithmetic itself needs.
 constexpr int F2X_NT = 288, F2X_M = 512, F2X_IN = 4 * F2X_M + 80, F2X_NS = 2 * F2X_M + 30;
 
-__global__ void __launch_bounds__(F2X_NT, 2) fir2_exact_tiled_kernel(const TiledArgs a, const Taps2Param taps)
+template <bool FMA>
+__global__ void __launch_bounds__(F2X_NT, 2) fir2_tiled_kernel(const ScreenArgs sa, const Taps2Param taps, const FmaBand band)
 {
     __shared__ float2 s_x[F2X_IN + F2X_IN / 8 + 8];        // (+8: the last phase-1 thread reads a few slots past its valid window)
     __shared__ float2 s_s[(F2X_NS + 3) / 4 * 5 + 1];
+    __shared__ float s_m2[F2X_NT / 32];
+    const TiledArgs &a = sa.t;
     const int t = (int) threadIdx.x;
     const i64 m0 = a.out_lo + (i64) blockIdx.x * F2X_M;       // first output of the tile (a.out_lo % 8 == a.bit_base % 8)
     const i64 g0 = 4 * m0 - 80;                               // first staged input
 
     // ---- stage inputs: 4 samples (16 B) per thread per step ----
     const bool aligned = (((g0 - a.in_base) & 3) == 0) && ((((uintptr_t) a.in) & 15) == 0);
+    float m2 = 0.0f;
     for (int q = t; q < F2X_IN / 4; q += F2X_NT) {
         const i64 g = g0 + 4 * q;
         uint32_t w[4];
@@ -913,8 +993,15 @@ __global__ void __launch_bounds__(F2X_NT, 2) fir2_exact_tiled_kernel(const Tiled
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const int x = 4 * q + e;
-            s_x[x + (x >> 3)] = sc16q11_to_float2(w[e]);
+            const float2 v = sc16q11_to_float2(w[e]);
+            s_x[x + (x >> 3)] = v;
+            if constexpr (FMA) m2 = fmaxf(m2, fmaf(v.x, v.x, v.y * v.y));
         }
+    }
+    if constexpr (FMA) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xFFFFFFFFu, m2, d));
+        if ((t & 31) == 0) s_m2[t >> 5] = m2;
     }
     __syncthreads();
 
@@ -931,8 +1018,8 @@ __global__ void __launch_bounds__(F2X_NT, 2) fir2_exact_tiled_kernel(const Tiled
             float sr = 0.0f, si = 0.0f;
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                sr = mac_exact(sr, taps.t1[i], win[2 * c + 15 - i].x);       // local 2v+21-i = 8t + 6 + (2c + 15 - i)
-                si = mac_exact(si, taps.t1[i], win[2 * c + 15 - i].y);
+                sr = mac_sel<FMA>(sr, taps.t1[i], win[2 * c + 15 - i].x);       // local 2v+21-i = 8t + 6 + (2c + 15 - i)
+                si = mac_sel<FMA>(si, taps.t1[i], win[2 * c + 15 - i].y);
             }
             const int v = 4 * t + c;
             if (2 * m0 - 30 + v < 0) {                        // stage-1 outputs before the capture: the zeros of fir_reset
@@ -945,7 +1032,7 @@ __global__ void __launch_bounds__(F2X_NT, 2) fir2_exact_tiled_kernel(const Tiled
     __syncthreads();
 
     // ---- phase 2: y[m0 + 2t + q] = sum_j t2[j] s[2m+1-j], local v = 4t + 2q + 31 - j ----
-    uint32_t bits2 = 0;
+    uint32_t bits2 = 0, unsure = 0;
     if (t < F2X_M / 2) {
         float2 sw[34];                                        // local v 4t .. 4t + 33
 #pragma unroll
@@ -953,15 +1040,31 @@ __global__ void __launch_bounds__(F2X_NT, 2) fir2_exact_tiled_kernel(const Tiled
             const int v = 4 * t + q;
             sw[q] = s_s[v + (v >> 2)];
         }
+        float hi2 = 0.0f, lo2 = 0.0f;
+        if constexpr (FMA) {
+            float mm = s_m2[0];
+#pragma unroll
+            for (int q = 1; q < F2X_NT / 32; q++) mm = fmaxf(mm, s_m2[q]);
+            const float D = band.c * sqrt_approx(mm) * 1.00001f;
+            const float hi = band.theta_hi + D, lo = fmaxf(band.theta_lo - D, 0.0f);
+            hi2 = hi * hi * 1.000001f;
+            lo2 = lo * lo * 0.999999f;
+        }
 #pragma unroll
         for (int q = 0; q < 2; q++) {
             float re = 0.0f, im = 0.0f;
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-                re = mac_exact(re, taps.t2[j], sw[2 * q + 31 - j].x);
-                im = mac_exact(im, taps.t2[j], sw[2 * q + 31 - j].y);
+                re = mac_sel<FMA>(re, taps.t2[j], sw[2 * q + 31 - j].x);
+                im = mac_sel<FMA>(im, taps.t2[j], sw[2 * q + 31 - j].y);
             }
-            bits2 |= (power_exact(re, im) >= a.pstar ? 1u : 0u) << q;
+            if constexpr (FMA) {
+                const uint32_t c = fma_classify(re, im, hi2, lo2);
+                bits2 |= (c & 1u) << q;
+                unsure |= (c >> 1);
+            } else {
+                bits2 |= (power_exact(re, im) >= a.pstar ? 1u : 0u) << q;
+            }
         }
     }
     // four threads share a byte of decisions (warps 0..7 are complete; warp 8 has no outputs)
@@ -970,9 +1073,27 @@ __global__ void __launch_bounds__(F2X_NT, 2) fir2_exact_tiled_kernel(const Tiled
         const uint32_t b2 = __shfl_down_sync(0xFFFFFFFFu, bits2, 2);
         const uint32_t b3 = __shfl_down_sync(0xFFFFFFFFu, bits2, 3);
         const i64 o = m0 + 2 * t;
-        if ((t & 3) == 0 && o < a.out_hi) {
+        const bool writer = (t & 3) == 0 && o < a.out_hi;
+        if (writer) {
             // outputs past out_hi inside the last byte are masked by the consumers
             a.out_bits[(o - a.bit_base) >> 3] = (uint8_t) (bits2 | (b1 << 2) | (b2 << 4) | (b3 << 6));
+        }
+        if constexpr (FMA) {
+            const uint32_t u1 = __shfl_down_sync(0xFFFFFFFFu, unsure, 1);
+            const uint32_t u2 = __shfl_down_sync(0xFFFFFFFFu, unsure, 2);
+            const uint32_t u3 = __shfl_down_sync(0xFFFFFFFFu, unsure, 3);
+            const bool push = writer && ((unsure | u1 | u2 | u3) != 0);
+            const uint32_t m_push = __ballot_sync(0xFFFFFFFFu, push);
+            if (m_push) {
+                const int lane = t & 31;
+                uint32_t slot0 = 0;
+                if (lane == 0) slot0 = atomicAdd(sa.work_count, (uint32_t) __popc(m_push));
+                slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
+                if (push) {
+                    const uint32_t sl = slot0 + __popc(m_push & ((1u << lane) - 1));
+                    if (sl < sa.work_cap) sa.work_list[sl] = (uint32_t) ((o - a.bit_base) >> 3);
+                }
+            }
         }
     }
 }

@@ -64,6 +64,9 @@ struct ookd_gpu {
     bool screen2 = false;             // dec4 shape: screen + refine (else the exact tiled two-stage kernel)
     int screen_regs = 64;             // register cap of the TMA screening kernel (64 / 56 / 48)
     bool screen_v2 = true;            // span statistics through dp2a, sums of I / Q only for loud spans (OOKD_SCREEN_V2=0: first form)
+    bool fma = false;                 // FMA screening (fused multiply-add pass + rigorous band, exact refine of the band):
+                                      // what a handle switches to when the energy proofs decide too little (low SNR)
+    bool fma_ok = false;              // ... and whether this handle's filter shape / threshold allow it
     bool fused_sm = true;             // state-machine stage as ONE cooperative kernel (sm_fused_kernel)
     unsigned fused_grid_max = 0;      // CTAs of it that can be co-resident on this device
     unsigned n_sm = 148;
@@ -267,6 +270,40 @@ void make_screen_params_dec4(const ookd_gpu *h, ScreenParams &sp)
     sp.inv_n = 1.0f / 96.0f;
 }
 
+// FMA screening band (fir_kernels.cuh: FmaBand): D = c sqrt(m^2), c = (G_ref + G_fused) * norm * sqrt(W), in double, rounded up.
+//   one stage : G = 2 (T + 2) u for either summation (twice the classical T u / (1 - T u)), norm = ||t||_2, W = T
+//   two stages: G = g1 + g2 + g1 g2 per summation, norm = ||habs||_2 (habs = |t1| (*) upsample(|t2|)), W = its length
+void make_fma_band(const ookd_gpu *h, FmaBand &b)
+{
+    const double u = ldexp(1.0, -24);
+    double G, norm, W;
+    if (h->stages.size() == 1) {
+        const Stage &st = h->stages[0];
+        double t2 = 0.0;
+        for (float t : st.taps) t2 += (double) t * (double) t;
+        G = 2.0 * (st.T + 2) * u;
+        norm = sqrt(t2);
+        W = st.T;
+    } else {
+        const Stage &s1 = h->stages[0], &s2 = h->stages[1];
+        const int n = (int) s1.T + (int) s1.D * ((int) s2.T - 1);
+        std::vector<double> ha(n, 0.0);
+        for (uint32_t j = 0; j < s2.T; j++) {
+            for (uint32_t i = 0; i < s1.T; i++) ha[s1.D * j + i] += fabs((double) s2.taps[j]) * fabs((double) s1.taps[i]);
+        }
+        double a2 = 0.0;
+        for (double v : ha) a2 += v * v;
+        const double g1 = 2.0 * (s1.T + 2) * u, g2 = 2.0 * (s2.T + 2) * u;
+        G = g1 + g2 + g1 * g2;
+        norm = sqrt(a2);
+        W = n;
+    }
+    const double theta = sqrt((double) h->pstar);
+    b.c = nextafterf((float) (2.0 * G * norm * sqrt(W) * (1.0 + 1e-6)), INFINITY);
+    b.theta_hi = nextafterf((float) (theta * (1.0 + 1e-6)), INFINITY);
+    b.theta_lo = nextafterf((float) (theta * (1.0 - 1e-6)), 0.0f);
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time libcuda dependency)
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -407,9 +444,15 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
                 fir1_screen_kernel<32><<<(unsigned) stiles, 256, 0, h->s_compute>>>(sa, sp);
             }
         } else {
-            TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
-            a.out_lo = o_begin; a.out_hi = o_end;
-            fir1_exact_tiled_kernel<32, TILE_R><<<(unsigned) tiles, 256, 0, h->s_compute>>>(a, tp);
+            ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
+            sa.t.out_lo = o_begin; sa.t.out_hi = o_end;
+            FmaBand band{};
+            if (h->fma) {
+                make_fma_band(h, band);
+                fir1_tiled_kernel<32, TILE_R, true><<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, tp, band);
+            } else {
+                fir1_tiled_kernel<32, TILE_R, false><<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, tp, band);
+            }
         }
         h->launches++;
         CU(h, cudaGetLastError());
@@ -421,10 +464,16 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
         memcpy(tp.t2, h->stages[1].taps.data(), sizeof(tp.t2));
         tp.d_t1 = h->stages[0].d_taps;
         tp.d_t2 = h->stages[1].d_taps;
-        TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
-        a.out_lo = o_begin; a.out_hi = o_end;
+        ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
+        sa.t.out_lo = o_begin; sa.t.out_hi = o_end;
         const u64 tiles = (u64) (o_end - o_begin + F2X_M - 1) / F2X_M;
-        fir2_exact_tiled_kernel<<<(unsigned) tiles, F2X_NT, 0, h->s_compute>>>(a, tp);
+        FmaBand band{};
+        if (h->fma) {
+            make_fma_band(h, band);
+            fir2_tiled_kernel<true><<<(unsigned) tiles, F2X_NT, 0, h->s_compute>>>(sa, tp, band);
+        } else {
+            fir2_tiled_kernel<false><<<(unsigned) tiles, F2X_NT, 0, h->s_compute>>>(sa, tp, band);
+        }
         h->launches++;
         CU(h, cudaGetLastError());
         return OOKD_OK;
@@ -453,7 +502,7 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
 // Second pass of the screened path: exact recomputation of the groups the screen left undecided.
 int launch_fir_refine(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
 {
-    if (h->path == FIR_SCREEN_DEC4 && !h->screen2) return OOKD_OK;
+    if (h->path == FIR_SCREEN_DEC4 && !(h->screen2 || h->fma)) return OOKD_OK;
     if (h->path == FIR_SCREEN_DEC4 && h->out_hi > h->bit_base) {
         Taps2Param tp;
         memcpy(tp.t1, h->stages[0].taps.data(), sizeof(tp.t1));
@@ -470,7 +519,7 @@ int launch_fir_refine(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_val
         CU(h, cudaGetLastError());
         return OOKD_OK;
     }
-    if (!(h->path == FIR_TILED_1STAGE_32 && h->screen) || h->out_hi <= h->bit_base) return OOKD_OK;
+    if (!(h->path == FIR_TILED_1STAGE_32 && (h->screen || h->fma)) || h->out_hi <= h->bit_base) return OOKD_OK;
     TapsParam<32> tp;
     memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
     ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
@@ -490,18 +539,10 @@ int run_generic_chain(ookd_gpu *h, const void *d_in, bool in_is_i16, i64 in_base
 
 int launch_fir_exact_all(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end)
 {
-    if (h->path == FIR_SCREEN_DEC4) {
-        h->screen2 = false;                                             // stop screening on this handle
-        return launch_fir(h, d_in, in_base, in_valid_end, h->bit_base, h->out_hi);
-    }
-    TapsParam<32> tp;
-    memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
-    TiledArgs a = tiled_args(h, d_in, in_base, in_valid_end);
-    const u64 tiles = (u64) (h->out_hi - h->bit_base + TILE_L - 1) / TILE_L;
-    fir1_exact_tiled_kernel<32, TILE_R><<<(unsigned) tiles, 256, 0, h->s_compute>>>(a, tp);
-    h->launches++;
-    CU(h, cudaGetLastError());
-    return OOKD_OK;
+    h->screen = false;                                                  // no screening of any kind on this handle from now on
+    h->screen2 = false;
+    h->fma = false;
+    return launch_fir(h, d_in, in_base, in_valid_end, h->bit_base, h->out_hi);
 }
 
 // ---- shape-agnostic chain: one launch per stage, intermediates in HBM ----
@@ -1219,7 +1260,7 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
     uint32_t walk_complete = *(const uint32_t *) (hs + 44);
     h->stat_refined_blocks = refined;
     h->stat_dense_tiles = 0;
-    if ((h->screen || h->screen2) && refined > h->work_cap) return OOKD_OK;      // work list overflowed
+    if ((h->screen || h->screen2 || h->fma) && refined > h->work_cap) return OOKD_OK;      // work list overflowed
     if (n_edges_total > h->pend.edge_cap || *(const uint32_t *) (hs + 28) != 0) return OOKD_OK;   // edge list / a tile region too small
     // The chain did not resolve within the burst (several consecutive chunks entered in a state no table holds
     // yet): keep the edges, anchors and tables and add rounds one at a time, each with its own link / walk /
@@ -1491,6 +1532,12 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     // the exact kernels handle those directly)
     h->screen = (h->path == FIR_TILED_1STAGE_32) && !(h->flags & OOKD_FLAG_NO_SCREEN) && h->pstar > 0.0f &&
                 h->pstar < 3.0e38f;
+    h->fma_ok = (h->path == FIR_TILED_1STAGE_32 || h->path == FIR_SCREEN_DEC4) && !(h->flags & OOKD_FLAG_NO_SCREEN) && pstar_ok;
+    if (h->fma_ok && (h->flags & OOKD_FLAG_FMA_SCREEN)) {               // start in FMA screening straight away
+        h->screen = false;
+        h->screen2 = false;
+        h->fma = true;
+    }
 
     // ---- state machine ----
     if (cfg->sm) {
@@ -1574,7 +1621,7 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     if ((rc = ensure(h, h->bits, (n_bits / 8 + 64 + 8) & ~7ull))) return rc;
 
     CU(h, cudaEventRecord(h->ev_t0, h->s_compute));
-    if (h->screen || h->screen2) {
+    if (h->screen || h->screen2 || h->fma) {
         // work list for undecided 8-output groups: room for 1/8 of all groups (beyond that the capture is
         // mostly "near the threshold" and screening is pointless)
         const u64 groups = n_bits / 8 + 1;
@@ -1712,11 +1759,21 @@ static int decode_end_once(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd
         // everything fit and resolved behind a single synchronisation
     } else if (n_bits > 0) {
         if ((rc = extract_edges(h, n_bits, res))) return rc;
-        if ((h->screen || h->screen2) && h->stat_refined_blocks > h->work_cap) {
-            // too many undecided groups for the work list: redo the decisions exactly, extract the edges again,
-            // and stop screening on this handle (the capture is not in the regime where it pays)
-            h->stat_dense_tiles = 1;
+        if ((h->screen || h->screen2) && h->stat_refined_blocks > h->work_cap && h->fma_ok) {
+            // The energy proofs leave too many groups undecided for the work list (low SNR: most windows are near the
+            // threshold in energy terms).  Switch the handle to FMA screening -- every output computed with fused
+            // multiply-adds, only those inside the rigorous rounding band recomputed exactly -- and redo the decisions.
             h->screen = false;
+            h->screen2 = false;
+            h->fma = true;
+            CU(h, cudaMemsetAsync((char *) h->scalars.p + 16, 0, 12, h->s_compute));
+            if ((rc = launch_fir(h, d_in, in_base, in_valid_end, h->bit_base, h->out_hi))) return rc;
+            if ((rc = launch_fir_refine(h, d_in, in_base, in_valid_end))) return rc;
+            if ((rc = extract_edges(h, n_bits, res))) return rc;
+            h->stat_dense_tiles = 1;
+        }
+        if ((h->screen || h->screen2 || h->fma) && h->stat_refined_blocks > h->work_cap) {
+            // still too many (or no FMA form for this shape): decide everything exactly, and keep doing so
             if ((rc = launch_fir_exact_all(h, d_in, in_base, in_valid_end))) return rc;
             if ((rc = extract_edges(h, n_bits, res))) return rc;
             h->stat_dense_tiles = 1;
@@ -1746,6 +1803,8 @@ static int decode_end_once(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd
         cudaEventElapsedTime(&res->fir_ms, h->ev_f0, h->ev_f1);
         cudaEventElapsedTime(&res->screen_ms, h->ev_f0, h->ev_s1);
         res->host_syncs = h->stat_syncs;
+        res->fir_mode = (h->path == FIR_GENERIC) ? OOKD_FIR_GENERIC
+                        : (h->screen || h->screen2) ? OOKD_FIR_SCREEN : h->fma ? OOKD_FIR_FMA : OOKD_FIR_EXACT;
     }
     return OOKD_OK;
 }

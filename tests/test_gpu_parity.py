@@ -135,7 +135,7 @@ def test_screen_decisions_equal_exact(filt, levels, sigma, thr, full):
     iq = _piecewise_capture(rng, 300001 if "dec4" in filt else 300000, levels, sigma, full_range=full)
     stages = O.load_filter(filt)
     ref = O.rx(iq, stages, None, threshold_=thr, samples_per_buffer=8192, want_bits=True)
-    for flags in (0, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_FORCE_GENERIC):
+    for flags in (0, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_FORCE_GENERIC, B.FLAG_FMA_SCREEN):
         g = B.Gpu(filter_stages=stages, threshold=thr, samples_per_buffer=8192, flags=flags)
         got = g.decode(iq)
         assert np.array_equal(g.bits(), ref["bits"]), (flags, got["refined_blocks"], got["refined_tiles"])
@@ -167,8 +167,11 @@ def test_screen_overflow_falls_back_to_exact_and_stays_correct():
         # the list holds 1/8 of all groups + 64 Ki: 2^21 fs32_fs4 outputs overflow it, 2^19 dec4 outputs do not
         assert first["refined_tiles"] == (1 if filt == "fs32_fs4" else 0)
         assert np.array_equal(g.bits(), ref["bits"])
-        again = g.decode(iq)                      # after an overflow: on the exact path from the start
+        again = g.decode(iq)                      # after an overflow: FMA screening from the start
         assert again["refined_tiles"] == 0 and np.array_equal(g.bits(), ref["bits"])
+        assert again["fir_mode"] == (2 if filt == "fs32_fs4" else 1)
+        if filt == "fs32_fs4":                    # levels sitting on the threshold: the rounding band really is visited
+            assert 0 < again["refined_blocks"] < 0.05 * (1 << 21) / 8
 
 
 @pytest.mark.parametrize("filt,log2n", [("fs32_fs4", 28), ("fs128_fs16_dec4", 27)])
@@ -247,7 +250,7 @@ def test_every_code_path_gives_the_same_decode(devname, filt):
                                glitches=((9000, 100),))
     stages = O.load_filter(filt)
     ref = O.rx(iq, stages, dev, samples_per_buffer=8192, want_bits=True)
-    for flags in (0, B.FLAG_SYNC_TAIL, B.FLAG_NO_TMA, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_SHARE_SMS,
+    for flags in (0, B.FLAG_SYNC_TAIL, B.FLAG_NO_TMA, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_SHARE_SMS, B.FLAG_FMA_SCREEN,
                   B.FLAG_FORCE_GENERIC, B.FLAG_NO_TMA | B.FLAG_SYNC_TAIL, B.FLAG_NO_GRAPH, B.FLAG_FUSED_SM,
                   B.FLAG_FUSED_SM | B.FLAG_NO_GRAPH):
         for chunk_buffers in (0, 5):

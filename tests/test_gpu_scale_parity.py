@@ -108,6 +108,7 @@ def test_c3_lowsnr_1000_messages_vs_oracle():
     for rep in range(2):                                           # (second decode: after the screen's verdict on the first)
         got = g.decode(iq)
         _compare(g, got, ref, rep)
+    assert got["fir_mode"] == 2                                    # the handle has switched to FMA screening by itself
     print(f"C3: {len(ref['msgs'])}/{len(sent)} messages, {len(ref['edges'])} edges, sm_rounds {got['sm_rounds']}, "
           f"refined_tiles {got['refined_tiles']}, refined groups {got['refined_blocks']}")
 
@@ -150,8 +151,9 @@ def test_screen_fuzz_decisions_equal_oracle(filt):
     rng = np.random.default_rng(20261018 + FUZZ_FILTERS.index(filt))
     thrs = [0.1, 0.05, 0.25, 0.6]
     gpus = {t: B.Gpu(filter_stages=stages, threshold=t, samples_per_buffer=8192) for t in thrs}
+    fma = {t: B.Gpu(filter_stages=stages, threshold=t, samples_per_buffer=8192, flags=B.FLAG_FMA_SCREEN) for t in thrs}
     n_cases, n = 208, 49152
-    refined = 0
+    refined = refined_fma = 0
     for case in range(n_cases):
         thr = thrs[case % len(thrs)]
         kind = case % 8
@@ -190,4 +192,13 @@ def test_screen_fuzz_decisions_equal_oracle(filt):
         fb, edges = g.edges()
         assert fb == ref["first_bit"] and np.array_equal(edges, ref["edges"]), (filt, case)
         refined += got["refined_blocks"]
+        # FMA screening: fused multiply-add decisions + exact recomputation inside the rounding band
+        gf = fma[thr]
+        got_f = gf.decode(iq)
+        assert got_f["fir_mode"] == 2
+        bits_f = gf.bits()
+        assert np.array_equal(bits_f, ref["bits"]), ("fma", filt, case, kind, thr, sigma,
+                                                     int(np.flatnonzero(bits_f != ref["bits"])[0]))
+        refined_fma += got_f["refined_blocks"]
     assert refined > 0
+    print(f"{filt}: energy screen refined {refined} groups, fma screen {refined_fma} of {n_cases * n // 8} (per decimation)")
