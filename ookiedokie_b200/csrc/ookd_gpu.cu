@@ -88,6 +88,7 @@ struct ookd_gpu {
     i64 report_lo = 0;               // first output that belongs to the shard (out_lo may start earlier)
     SmCarry entry_used{};
     uint32_t first_chunk = 0;
+    bool entry_explicit = false;      // the last state-machine run was a resolve from a caller-supplied entry
     void *h_scalars = nullptr;        // pinned, 512 B
     SmMsg *h_msgs_pin = nullptr;      // pinned message staging of the single-synchronisation path
     size_t h_msgs_pin_cap = 0;        // in messages
@@ -639,7 +640,7 @@ int finish_messages(ookd_gpu *h, const SmMsg *raw, u64 n_msgs, const SmCarry &la
         res->msgs = h->h_msgs.empty() ? nullptr : h->h_msgs.data();
         res->sm_rounds = rounds;
         carry_from_dev(h->entry_used, res->entry_used);
-        res->entry_is_provisional = (h->warm && h->first_chunk == 0) ? 1u : 0u;
+        res->entry_is_provisional = (h->warm && !h->entry_explicit) ? 1u : 0u;
     }
     return OOKD_OK;
 }
@@ -664,6 +665,9 @@ SmArgs base_sm_args(ookd_gpu *h, const SmCarry &entry0)
     a.overflow = (uint32_t *) ((char *) h->scalars.p + 32);
     a.warm = h->warm ? 1u : 0u;
     a.first_chunk = 0;
+    a.report_lo = h->report_lo;
+    a.mid_carry = h->final_entry.p ? (SmCarry *) h->final_entry.p + 1 : nullptr;
+    a.entry_at_report = 0;
     a.chunk_e = (u64 *) h->chunk_e.p;
     a.bound_pos = (i64 *) h->bound_pos.p;
     a.seed_pos = (i64 *) h->seed_pos.p;
@@ -816,7 +820,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
     if ((rc = ensure(h, h->tab_cnt[1], sizeof(uint32_t) * nc))) return rc;
     if ((rc = ensure(h, h->tab_link, (size_t) nc * TAB_K + 16))) return rc;
     if ((rc = ensure(h, h->tab_chosen, (size_t) nc + 16))) return rc;
-    if ((rc = ensure(h, h->final_entry, sizeof(SmCarry)))) return rc;
+    if ((rc = ensure(h, h->final_entry, sizeof(SmCarry) * (1 + TAB_K)))) return rc;
 
     const uint32_t *h_overflow = (const uint32_t *) ((const char *) h->h_scalars + 32);
     const uint32_t *h_walk = (const uint32_t *) ((const char *) h->h_scalars + 40);
@@ -838,7 +842,8 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
     }
     // With warm-up history chunk 0 lies in front of the shard.  A decode walks from its anchored seed and
     // reports the state it reaches at the shard's first output; a resolve (explicit entry) bypasses it.
-    h->first_chunk = (h->warm && incremental) ? 1u : 0u;
+    h->first_chunk = 0;
+    h->entry_explicit = incremental;                        // a resolve: entry0 is the state AT the shard's first output
     h->entry_used = entry0;
 
     for (int attempt = 0; attempt < 8 && !resolved; attempt++) {
@@ -847,6 +852,8 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
         a.start_slot = (uint32_t *) ((char *) h->scalars.p + 48);
         a.first_chunk = h->first_chunk;
         a.final_entry = (SmCarry *) h->final_entry.p;
+        a.mid_carry = (SmCarry *) h->final_entry.p + 1;
+        a.entry_at_report = (h->warm && incremental) ? 1u : 0u;
         a.tab_k = TAB_K;
         a.tab_entry = (SmCarry *) h->tab_entry.p;
         a.tab_exit = (SmCarry *) h->tab_exit.p;
@@ -948,7 +955,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
     const u64 n_msgs = ((const u64 *) h->h_scalars)[1];
     SmCarry last;
     memcpy(&last, (const char *) h->h_scalars + 192, sizeof(SmCarry));
-    if (h->warm && h->first_chunk == 0) {
+    if (h->warm && !h->entry_explicit) {
         CU(h, cudaMemcpyAsync(&h->entry_used, h->final_entry.p, sizeof(SmCarry), cudaMemcpyDeviceToHost, h->s_compute));
         if (!n_msgs) CU(h, cudaStreamSynchronize(h->s_compute));
     }
@@ -1022,7 +1029,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     if ((rc = ensure(h, h->tab_cnt[1], sizeof(uint32_t) * nc))) return rc;
     if ((rc = ensure(h, h->tab_link, (size_t) nc * TAB_K + 16))) return rc;
     if ((rc = ensure(h, h->tab_chosen, (size_t) nc + 16))) return rc;
-    if ((rc = ensure(h, h->final_entry, sizeof(SmCarry)))) return rc;
+    if ((rc = ensure(h, h->final_entry, sizeof(SmCarry) * (1 + TAB_K)))) return rc;
     if ((rc = ensure(h, h->chunk_e, sizeof(u64) * nc))) return rc;
     if ((rc = ensure(h, h->bound_pos, sizeof(i64) * nc))) return rc;
     if ((rc = ensure(h, h->seed_pos, sizeof(i64) * nc))) return rc;
@@ -1060,6 +1067,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     // ---- state machine arguments ----
     h->tables_valid = false;
     h->first_chunk = 0;
+    h->entry_explicit = false;
     h->entry_used = entry0;
     h->n_edges = 0;
     h->base_bit = 0;

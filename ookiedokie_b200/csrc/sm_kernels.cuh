@@ -81,9 +81,13 @@ struct SmArgs {
     uint32_t *msg_counts;     // [n_chunks] messages of the chosen pair
     SmCarry  *final_exit;     // exit of the last chunk's chosen pair (written by the walk)
     uint32_t *start_slot;     // slot of chunk first_chunk the walk starts from
-    uint32_t first_chunk;     // chunk the walk starts at (1 when chunk 0 is a warm-up chunk being bypassed)
+    uint32_t first_chunk;     // chunk the walk starts at (0)
     uint32_t warm;            // chunk 0 is a warm-up chunk in front of the shard: it has no true entry
-    SmCarry  *final_entry;    // warm: state at the shard's first output = exit of chunk 0's chosen pair
+    SmCarry  *final_entry;    // warm: state at the shard's first output, as the chosen run of chunk 0 passed it
+    i64 report_lo;            // warm: the shard's first output.  Chunk 0 starts one chunk of history earlier and runs THROUGH
+                              // it up to chunk 1's anchor; every run of chunk 0 records its state there in mid_carry[slot]
+    SmCarry  *mid_carry;      // [tab_k]
+    uint32_t entry_at_report; // resolve of a warm shard: entry0 is the state AT report_lo; the pair added to chunk 0 starts there
     u64 *chunk_e;             // [n_chunks] index of the first edge at or after each chunk's start (sm_anchor_kernel)
     // Boundaries moved to anchors (sm_anchor_kernel): chunk c covers [bound_pos[c], bound_pos[c+1]).
     i64 *bound_pos;           // [n_chunks]; null => the fixed buffer boundaries (Jacobi fallback)
@@ -95,7 +99,6 @@ struct SmArgs {
 
 #define OOKD_SEED_TRUE      0   /* the shard's true entry (chunk 0)                                             */
 #define OOKD_SEED_CANON     1   /* idle machine at the chunk's anchor; the chunk's boundary IS the anchor        */
-#define OOKD_SEED_ANCHOR    2   /* RESET at an anchor inside a chunk whose boundary stays fixed: source of exits */
 #define OOKD_SEED_RESET     3   /* no anchor: RESET at the chunk's first sample                                  */
 
 __device__ __forceinline__ i64 first_output_of_buffer(const SmArgs &a, u64 b)
@@ -891,13 +894,9 @@ __device__ __forceinline__ void sm_anchor_chunk(const SmArgs &a, const SmTable &
     } else if (have_anchor) {
         seed = (i64) a.edges[anchor_e];
         seed_e = anchor_e;
-        if (a.warm && c == 1) {
-            kind = OOKD_SEED_ANCHOR;                         // the shard's first output must stay a boundary
-        } else {
-            kind = OOKD_SEED_CANON;
-            bound = seed;
-            bound_e = seed_e;
-        }
+        kind = OOKD_SEED_CANON;
+        bound = seed;
+        bound_e = seed_e;
     } else {
         kind = OOKD_SEED_RESET;
     }
@@ -953,10 +952,6 @@ __device__ __forceinline__ void sm_round_pair(const SmArgs &a, const SmTable &T,
         } else if (kind == OOKD_SEED_CANON) {
             s = a.canon;
             entry = s;
-        } else if (kind == OOKD_SEED_ANCHOR) {
-            carry_reset(s, 0);
-            entry = s;
-            entry.state = OOKD_TAB_INVALID;                  // matches no real entry: it is only a source of exits
         } else {
             carry_reset(s, tb);
             entry = s;
@@ -997,10 +992,25 @@ __device__ __forceinline__ void sm_round_pair(const SmArgs &a, const SmTable &T,
         o.cap = a.slot_cap;
         o.n_msgs = 0;
         o.overflow = a.overflow;
+        i64 upto = end;
+        const bool through_report = a.warm && cc == 0 && pos < a.report_lo && a.report_lo <= end;
+        if (through_report) upto = a.report_lo;              // warm shard: note the state at the shard's first output
         if (warp_ok) {
-            warp_sm_run_span(a, n_edges, W, s, pos, end, e, tb, o, lo, lane);
+            warp_sm_run_span(a, n_edges, W, s, pos, upto, e, tb, o, lo, lane);
         } else {
-            sm_run_span<false>(a, n_edges, T, s, pos, end, e, tb, o, lo);
+            sm_run_span<false>(a, n_edges, T, s, pos, upto, e, tb, o, lo);
+        }
+        if (through_report) {
+            if (lane == 0) a.mid_carry[slot] = s;
+            if (upto < end) {
+                e = warp_ok ? warp_edge_lower_bound(a.edges, n_edges, (u64) upto, lane) : edge_lower_bound(a.edges, n_edges, (u64) upto);
+                tb = base_bit ^ (uint32_t) (e & 1);
+                if (warp_ok) {
+                    warp_sm_run_span(a, n_edges, W, s, upto, end, e, tb, o, lo, lane);
+                } else {
+                    sm_run_span<false>(a, n_edges, T, s, upto, end, e, tb, o, lo);
+                }
+            }
         }
         if (lane == 0) {
             a.tab_entry[(u64) cc * K + slot] = entry;
@@ -1020,7 +1030,7 @@ __device__ __forceinline__ void sm_round_pair(const SmArgs &a, const SmTable &T,
                 SmCarry r;
                 carry_reset(r, base_bit ^ (uint32_t) (a.seed_e[nn] & 1));
                 known = carry_equal(s, r);
-            }                                                // OOKD_SEED_ANCHOR: its entry matches nothing
+            }
         } else {
             const uint32_t n_next = a.cnt_in[nn];            // entries that were complete before this round
             for (uint32_t i = 0; i < n_next; i++) {
@@ -1086,13 +1096,24 @@ __global__ void __launch_bounds__(32) sm_table_add_entry_kernel(const SmArgs a)
     const uint32_t c = a.first_chunk;
     const uint32_t n_here = a.cnt_out[c];
     SmCarry s = a.entry0;
-    for (uint32_t i = 0; i < n_here; i++) {
-        if (carry_equal(s, a.tab_entry[(u64) c * K + i])) { *a.start_slot = i; return; }
+    if (!a.entry_at_report) {
+        for (uint32_t i = 0; i < n_here; i++) {
+            if (carry_equal(s, a.tab_entry[(u64) c * K + i])) { *a.start_slot = i; return; }
+        }
+    } else {
+        // warm shard: chunk 0's pairs start in the history; the corrected state applies at the shard's first output
+        for (uint32_t i = 0; i < n_here; i++) {
+            if (carry_equal(s, a.mid_carry[i])) { *a.start_slot = i; return; }
+        }
     }
     if (n_here >= K) { atomicExch(a.overflow, 2u); return; }
     i64 start, end, lo;
     chunk_bounds(a, c, start, end, lo);
-    const u64 e = a.chunk_e[c];
+    u64 e = a.chunk_e[c];
+    if (a.entry_at_report) {
+        start = a.report_lo;
+        e = edge_lower_bound(a.edges, a.n_edges, (u64) start);
+    }
     const uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);
     SpanOut o;
     o.slots = a.slots + ((u64) c * K + n_here) * a.slot_cap;
@@ -1100,10 +1121,11 @@ __global__ void __launch_bounds__(32) sm_table_add_entry_kernel(const SmArgs a)
     o.n_msgs = 0;
     o.overflow = a.overflow;
     const SmCarry entry = s;
-    sm_run_span<false>(a, a.n_edges, T, s, start, end, e, tb, o, lo);
-    a.tab_entry[(u64) c * K + n_here] = entry;
+    if (start < end) sm_run_span<false>(a, a.n_edges, T, s, start, end, e, tb, o, lo);
+    a.tab_entry[(u64) c * K + n_here] = a.entry_at_report ? SmCarry{OOKD_TAB_INVALID, 0, 0, 0, {0, 0, 0, 0}} : entry;
     a.tab_exit[(u64) c * K + n_here] = s;
     a.tab_nmsg[(u64) c * K + n_here] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
+    if (a.entry_at_report) a.mid_carry[n_here] = entry;
     a.cnt_out[c] = n_here + 1;
     *a.start_slot = n_here;
 }
@@ -1223,7 +1245,7 @@ __device__ __forceinline__ void sm_walk_cta(const SmArgs &a)
         a.walk_status[1] = (done == a.n_chunks) ? 1u : 0u;
         if (done == a.n_chunks) {
             *a.final_exit = a.tab_exit[(u64) (a.n_chunks - 1) * K + a.chosen[a.n_chunks - 1]];
-            if (a.warm && a.first_chunk == 0) *a.final_entry = a.tab_exit[a.chosen[0]];
+            if (a.warm) *a.final_entry = a.mid_carry[a.chosen[0]];
         }
     }
     for (uint32_t c = threadIdx.x; c < a.n_chunks; c += blockDim.x) {
@@ -1281,7 +1303,7 @@ __global__ void __launch_bounds__(SM_WALK_NT) sm_walk_kernel(const SmArgs a, uin
             a.walk_status[0] = a.n_chunks;
             a.walk_status[1] = 1u;
             *a.final_exit = a.tab_exit[(u64) (a.n_chunks - 1) * K];
-            if (a.warm && a.first_chunk == 0) *a.final_entry = a.tab_exit[0];
+            if (a.warm) *a.final_entry = a.mid_carry[0];
         }
     } else {
         sm_walk_cta<4096>(a);
