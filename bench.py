@@ -331,7 +331,7 @@ def measure_c3(local_rank, peak):
     return out
 
 
-def measure_c5(rank, world, local_rank, peak, n_caps_total=256, log2n=24):
+def measure_c5(rank, world, local_rank, peak, n_caps_total=256, log2n=24, per=16):
     """BASELINE configs[4] (scaled to what one default run can synthesise): independent captures, devices alternating
     p3l-nexa2012 / unknown-remote1, authored fs64_fs8 filter, sigma in {0, 0.02, 0.05}, seeds = index; capture i is
     decoded by rank i mod world (no exchange at all)."""
@@ -356,7 +356,8 @@ def measure_c5(rank, world, local_rank, peak, n_caps_total=256, log2n=24):
                 device_ptr=d.data_ptr(), noise_terms=NOISE_TERMS)
         bufs.append(d)
     torch.cuda.synchronize()
-    per = 4                                                  # handles per device description: captures in flight
+    # `per` handles per device description = captures in flight per kind: a capture of 2^24 samples is 12 us of streaming
+    # followed by ~0.3 ms of latency-bound stages (edges, state machine), so throughput comes from overlapping many
     gpus = [B.Gpu(filter_stages=fir.stages, sm=devs[kind].sm_spec(), threshold=THR, samples_per_buffer=SPB,
                   device_id=local_rank) for kind in range(2) for _ in range(per)]
     caps = [((bufs[j].data_ptr(), n), (i % 2) * per + (j // 2) % per) for j, i in enumerate(mine)]

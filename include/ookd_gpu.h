@@ -168,11 +168,8 @@ struct ookd_gpu_config {
 };
 
 #define OOKD_FLAG_FORCE_GENERIC  1u          /* always use the shape-agnostic FIR kernels       */
-#define OOKD_FLAG_TILE_PER_CTA_SCREEN 4u     /* earliest forms, kept for cross-checking: one-tile-per-CTA screening
-                                                kernel and lane-per-output refine kernels instead of the persistent
-                                                TMA-staged screen and the group-per-thread refine                  */
-#define OOKD_FLAG_NO_TMA         8u          /* persistent screening kernel with register prefetch instead of the
-                                                TMA-staged default                                */
+#define OOKD_FLAG_NO_TMA         8u          /* screening kernel without tensor copies: every tile is staged with guarded
+                                                loads (the path tiles at the capture's ends and unaligned inputs take) */
 #define OOKD_FLAG_SYNC_TAIL      16u         /* edges / state machine with a host synchronisation between the
                                                 stages instead of the single-synchronisation default */
 #define OOKD_FLAG_SHARE_SMS      32u         /* pipelined use (several handles with a decode in flight on one
@@ -188,6 +185,11 @@ struct ookd_gpu_config {
 #define OOKD_FLAG_FMA_SCREEN    256u          /* start with FMA screening (fused multiply-add pass, rigorous rounding band,
                                                 exact recomputation inside the band) instead of the energy proofs; a
                                                 handle switches to it by itself when the energy proofs decide too little */
+#define OOKD_FLAG_NO_ADAPTIVE   512u          /* no per-decode choice between the energy proofs and FMA screening for short
+                                                captures (up to 2^26 outputs: a probe kernel looks at 256 windows and both
+                                                forms are enqueued, the one not chosen returns at once); like long captures,
+                                                they then use the energy proofs until those overflow the work list and FMA
+                                                screening from then on                                                  */
 #define OOKD_FLAG_NO_SCREEN      2u          /* no screening: the exact tiled kernels compute every output with the
                                                 reference's in-order MACs (same decisions, fp32-issue bound)        */
 
@@ -269,8 +271,9 @@ int  ookd_gpu_decode_end(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd_g
 /* Batch of independent captures (each one a whole file: the loop of
  * ookiedokie_rx(), src/ookiedokie.c:238-290, run once per capture).  Capture i
  * is decoded by handles[caps[i].handle] -- handles may differ in device
- * description, filter and CUDA device -- by one host thread per handle, each
- * walking its handle's captures in order.  Messages of all captures are written to msgs_out in capture order;
+ * description, filter and CUDA device -- with up to n_handles decodes in flight
+ * (a capture is enqueued on its handle as soon as the handle's previous capture
+ * has been collected), so give it several handles per device description.  Messages of all captures are written to msgs_out in capture order;
  * capture i owns msgs_out[msg_first[i] .. msg_first[i+1]).  If msgs_cap is too
  * small OOKD_ERR_OVERFLOW is returned and msg_first[n_caps] holds the number
  * of messages.  results (nullable) receives per-capture statistics (its msgs

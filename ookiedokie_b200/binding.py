@@ -20,13 +20,13 @@ K_INF = 0xFFFFFFFF
 
 FLAG_FORCE_GENERIC = 1
 FLAG_NO_SCREEN = 2
-FLAG_TILE_PER_CTA_SCREEN = 4
 FLAG_NO_TMA = 8
 FLAG_SYNC_TAIL = 16
 FLAG_SHARE_SMS = 32
 FLAG_NO_GRAPH = 64
 FLAG_FUSED_SM = 128
 FLAG_FMA_SCREEN = 256
+FLAG_NO_ADAPTIVE = 512
 
 # every symbol include/ookd_gpu.h declares
 EXPORTS = [

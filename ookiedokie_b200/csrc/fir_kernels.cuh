@@ -126,6 +126,49 @@ struct ScreenArgs {
     uint32_t n_tiles;        // tiles of this launch (persistent variant)
 };
 
+// Adaptive decodes (short captures): a probe kernel writes the screening form it chose for this decode next to the work
+// counter (work_count[OOKD_MODE_SLOT]); both forms are enqueued, and the ADAPT instantiation of the one that was not
+// chosen returns at once.  (Kept out of the parameter structs on purpose: two more fields in ScreenArgs cost the plain
+// screening kernel three registers and 4 % of its speed.)
+#define OOKD_MODE_ENERGY 1u
+#define OOKD_MODE_FMA    2u
+#define OOKD_MODE_SLOT   82        /* (344 - 16) / 4: scalars + 344, counted from the work counter at scalars + 16 */
+
+// Which screening form pays for THIS capture?  The energy proofs decide an output "off" when its window energy is below
+// K0; on an OOK capture most windows are silence, so if even the silence is above K0 (noise floor too high) they decide
+// almost nothing and every group would go to the exact kernel.  256 windows spread over the capture are enough to tell:
+// fewer than 40 % provably off => FMA screening.  One small CTA, no host round trip (the FIR kernels read the verdict).
+__global__ void __launch_bounds__(1024) screen_probe_kernel(const TiledArgs a, int dec, int window, uint32_t k0, uint32_t *mode)
+{
+    // 32 warps x 8 windows; lane i of a warp reads samples i, i + 32, ... of the window (coalesced)
+    __shared__ uint32_t s_cnt[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const i64 n_out = a.out_hi - a.out_lo;
+    uint32_t off = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const i64 o = a.out_lo + (n_out * (i64) (warp * 8 + q)) / 256;      // output whose window is sampled
+        const i64 newest = (o + 1) * dec - 1;
+        unsigned long long e = 0;
+        for (int i = (int) lane; i < window; i += 32) {
+            const i64 g = newest - i;
+            const uint32_t w = (g >= 0 && g >= a.in_base && g < a.in_valid_end) ? __ldg(a.in + (g - a.in_base)) : 0u;
+            const long long I = (short) (w & 0xFFFFu), Q = ((int) w) >> 16;
+            e += (unsigned long long) (I * I + Q * Q);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) e += __shfl_xor_sync(0xFFFFFFFFu, e, d);
+        off += (e < (unsigned long long) k0) ? 1u : 0u;
+    }
+    if (lane == 0) s_cnt[warp] = off;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int q = 0; q < 32; q++) tot += s_cnt[q];
+        *mode = (tot * 10 < 256 * 4) ? OOKD_MODE_FMA : OOKD_MODE_ENERGY;
+    }
+}
+
 __device__ __forceinline__ float sqrt_approx(float x)
 {
     float r;
@@ -165,7 +208,7 @@ __device__ __forceinline__ uint32_t fma_classify(float re, float im, float hi2, 
     return (p >= hi2) ? 1u : ((p < lo2) ? 0u : 2u);
 }
 
-template <int T, int R, bool FMA>
+template <int T, int R, bool FMA, bool ADAPT>
 __global__ void __launch_bounds__(256, 2)
 fir1_tiled_kernel(const ScreenArgs sa, const TapsParam<T> taps, const FmaBand band)
 {
@@ -180,6 +223,9 @@ fir1_tiled_kernel(const ScreenArgs sa, const TapsParam<T> taps, const FmaBand ba
     __shared__ float s_m2[NT / 32];
 
     const TiledArgs &a = sa.t;
+    if constexpr (ADAPT) {
+        if (sa.work_count[OOKD_MODE_SLOT] != OOKD_MODE_FMA) return;    // the probe chose the other screening form
+    }
     uint32_t n_tiles_here = gridDim.x;
     uint32_t stride = gridDim.x;
     uint32_t tile_it = blockIdx.x;
@@ -320,391 +366,16 @@ fir1_tiled_kernel(const ScreenArgs sa, const TapsParam<T> taps, const FmaBand ba
 //          If that lower bound, less the rounding allowance, clears the threshold, all 16
 //          outputs of the thread decide 1.
 //
-//    Groups of 8 outputs that neither test settles are recomputed with the exact in-order MACs
-//    (one output per lane, compacted through a shared-memory queue so lanes stay full, samples
-//    re-read through L1/L2) by fir1_refine_kernel from a global work list.  Decisions are therefore
+//    Groups of 8 outputs that neither test settles are recomputed with the exact in-order MACs by
+//    fir1_refine_group_kernel from a global work list.  Decisions are therefore
 //    bit-identical to the exact kernel for EVERY input; only the cost is data dependent.  Spans
 //    holding a sample outside the range the 32-bit sums are sized for are simply left undecided.
 //    If more groups are undecided than the work list holds (low-SNR captures), the host redoes the
 //    range with fir1_exact_tiled_kernel and stops screening on that handle.
 // =======================================================================================
-#ifndef OOKD_SCREEN_MINB
-#define OOKD_SCREEN_MINB 5
-#endif
-#ifndef OOKD_SCREEN_PERSIST_MINB
-#define OOKD_SCREEN_PERSIST_MINB 4
-#endif
-
-// prefix sums / sums / range guard of one 16-sample span
-__device__ __forceinline__ void screen_span_stats(const uint32_t (&w)[16], uint32_t (&pre)[16], int &sx, int &sy,
-                                                  uint32_t &guard)
-{
-    uint32_t run = 0;
-    int xs = 0, ys = 0;
-    guard = 0;
-#pragma unroll
-    for (int e = 0; e < 16; e++) {
-        const int I = (int) (short) (w[e] & 0xFFFFu);
-        const int Q = ((int) w[e]) >> 16;
-        const uint32_t q = (uint32_t) (I * I) + (uint32_t) (Q * Q);
-        guard |= q;
-        run += q;
-        pre[e] = run;
-        xs += I;
-        ys += Q;
-    }
-    sx = xs;
-    sy = ys;
-}
-
-template <int T>
-__global__ void __launch_bounds__(256, OOKD_SCREEN_MINB)
-fir1_screen_kernel(const ScreenArgs sa, const ScreenParams sp)
-{
-    static_assert(T == 32, "window = exactly two 16-sample thread spans");
-    constexpr int NT = 256, SPT = 16, L = NT * SPT;    // 4096 outputs per tile
-    constexpr int HT = 2;                              // history spans in front of the tile (32 samples)
-    __shared__ uint4 s_pre[(NT + HT) * 4];             // per span: 16 running prefix sums of |x|^2 (chunk-rotated)
-    __shared__ int2 s_xy[NT + HT];                     // per span: sum I, sum Q
-    __shared__ uint8_t s_flag[NT + HT];                // per span: some |x|^2 >= 2^25 (32-bit sums not guaranteed)
-
-    const TiledArgs &a = sa.t;
-    const uint32_t tile = blockIdx.x + sa.tile_offset;
-    const i64 o0 = a.out_lo + (i64) tile * L;
-    const i64 g0 = o0 - HT * SPT;
-    const bool fast = ((((uintptr_t) a.in) & 15) == 0) && (((g0 - a.in_base) & 3) == 0) && g0 >= a.in_base && g0 >= 0 &&
-                      (g0 + L + HT * SPT) <= a.in_valid_end;
-
-    // ---- pass over the raw words: running prefix of |x|^2, sums of I and Q, range guard ----
-    uint32_t pre[SPT], guard = 0;
-    int sx = 0, sy = 0;
-#pragma unroll
-    for (int pass = 0; pass < 2; pass++) {
-        int span;
-        if (pass == 0) {
-            span = threadIdx.x + HT;
-        } else {
-            if (threadIdx.x >= HT) break;
-            span = threadIdx.x;
-        }
-        const i64 g = g0 + (i64) span * SPT;
-        uint32_t w[SPT];
-        if (fast) {
-            const uint4 *src = (const uint4 *) (a.in + (g - a.in_base));
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                const uint4 x = __ldg(src + v);
-                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < SPT; e++) {
-                const i64 ge = g + e;
-                w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
-            }
-        }
-        uint32_t p[SPT], gd;
-        int xs, ys;
-        screen_span_stats(w, p, xs, ys, gd);
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            // rotate the four 16-byte chunks by (span >> 1) so that a warp's stores spread over all banks
-            s_pre[span * 4 + ((v + (span >> 1)) & 3)] = make_uint4(p[4 * v], p[4 * v + 1], p[4 * v + 2], p[4 * v + 3]);
-        }
-        s_xy[span] = make_int2(xs, ys);
-        s_flag[span] = (gd >> 25) ? 1 : 0;
-        if (pass == 0) {
-#pragma unroll
-            for (int e = 0; e < SPT; e++) pre[e] = p[e];
-            sx = xs; sy = ys; guard = gd;
-        }
-    }
-    __syncthreads();
-
-    // ---- decide the 16 outputs of this thread (two groups of 8) ----
-    const int span = threadIdx.x + HT;
-    uint32_t bits16 = 0;
-    bool undecided_lo = false, undecided_hi = false;
-    const i64 o = o0 + (i64) threadIdx.x * SPT;
-    const bool bad = (guard >> 25) || s_flag[span - 1] || s_flag[span - 2];
-    if (!bad) {
-        uint32_t p2[SPT];
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            const uint4 x = s_pre[(span - 2) * 4 + ((v + ((span - 2) >> 1)) & 3)];
-            p2[4 * v] = x.x; p2[4 * v + 1] = x.y; p2[4 * v + 2] = x.z; p2[4 * v + 3] = x.w;
-        }
-        const uint32_t tot1 = s_pre[(span - 1) * 4 + ((3 + ((span - 1) >> 1)) & 3)].w, tot2 = p2[SPT - 1];
-        const uint32_t base = tot2 + tot1;
-        // window of output j: samples (t-2, j+1) .. (t, j):  E_j = base + pre[j] - p2[j]   (exact in u32)
-        int dmax_lo = INT_MIN, dmax_hi = INT_MIN;
-#pragma unroll
-        for (int j = 0; j < SPT; j++) {
-            const int d = (int) (pre[j] - p2[j]);              // all sums < 2^31: signed difference is exact
-            if (j < 8) dmax_lo = max(dmax_lo, d); else dmax_hi = max(dmax_hi, d);
-        }
-        const bool off_lo = (uint32_t) ((int) base + dmax_lo) < sp.k0, off_hi = (uint32_t) ((int) base + dmax_hi) < sp.k0;
-        bool on = false;
-        if (!(off_lo && off_hi)) {
-            const int2 xy1 = s_xy[span - 1], xy2 = s_xy[span - 2];
-            const float X = (float) (sx + xy1.x + xy2.x), Y = (float) (sy + xy1.y + xy2.y);
-            const float Q = (float) (base + pre[SPT - 1]);
-            const float m2 = fmaf(X, X, Y * Y);
-            const float mu = sqrt_approx(m2) * sp.inv_n;
-            const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
-            const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
-            on = fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi;
-        }
-        if (on) {
-            bits16 = 0xFFFFu;
-        } else {
-            undecided_lo = !off_lo;
-            undecided_hi = !off_hi;
-        }
-    } else {
-        undecided_lo = undecided_hi = true;
-    }
-    const bool in_lo = o < a.out_hi, in_hi = o + 8 < a.out_hi;
-    if (in_lo) {
-        // undecided groups are overwritten by fir1_refine_kernel
-        const i64 byte = (o - a.bit_base) >> 3;              // even: 16 outputs per thread
-        if (in_hi) {
-            *(uint16_t *) (a.out_bits + byte) = (uint16_t) bits16;
-        } else {
-            a.out_bits[byte] = (uint8_t) bits16;
-        }
-    }
-    // ---- undecided groups -> global work list (warp-aggregated reservation, no CTA barrier) ----
-    const bool push_lo = undecided_lo && in_lo, push_hi = undecided_hi && in_hi;
-    const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, push_lo), m_hi = __ballot_sync(0xFFFFFFFFu, push_hi);
-    const uint32_t n_push = __popc(m_lo) + __popc(m_hi);
-    if (n_push) {
-        const int lane = threadIdx.x & 31;
-        uint32_t slot0 = 0;
-        if (lane == 0) slot0 = atomicAdd(sa.work_count, n_push);
-        slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
-        const uint32_t below = (1u << lane) - 1;
-        const uint32_t grp0 = (uint32_t) ((o - a.bit_base) >> 3);
-        if (push_lo) {
-            const uint32_t s = slot0 + __popc(m_lo & below);
-            if (s < sa.work_cap) sa.work_list[s] = grp0;
-        }
-        if (push_hi) {
-            const uint32_t s = slot0 + __popc(m_lo) + __popc(m_hi & below);
-            if (s < sa.work_cap) sa.work_list[s] = grp0 + 1;
-        }
-    }
-}
-
-// Persistent variant of fir1_screen_kernel: each CTA walks a contiguous range of tiles, requests the raw
-// words of tile i+1 (4 x LDG.128 per thread) before it processes tile i, and keeps the span statistics in
-// a two-tile ring in shared memory so that the last two spans of tile i are the history of tile i+1.
-// One CTA barrier per tile; no global-load latency on the critical path.
-template <int T>
-__global__ void __launch_bounds__(256, OOKD_SCREEN_PERSIST_MINB)
-fir1_screen_persist_kernel(const ScreenArgs sa, const ScreenParams sp)
-{
-    static_assert(T == 32, "window = exactly two 16-sample thread spans");
-    constexpr int NT = 256, SPT = 16, L = NT * SPT;
-    constexpr int RING = 2 * NT;
-    // Rows RING.. : the last two spans of each tile again, in a ring of THREE tiles.  Threads 0 and 1 read
-    // them after the barrier of tile i; a copy living in the two-tile ring would be overwritten by the
-    // stores of tile i+1, which no barrier separates from those reads.
-    constexpr int TAIL = RING, ROWS = RING + 3 * 2;
-    __shared__ uint4 s_pre[ROWS * 4];
-    __shared__ int2 s_xy[ROWS];
-    __shared__ uint8_t s_flag[ROWS];
-
-    const TiledArgs &a = sa.t;
-    const uint32_t per = (sa.n_tiles + gridDim.x - 1) / gridDim.x;
-    const uint32_t t_begin = sa.tile_offset + blockIdx.x * per;
-    const uint32_t t_end = min(sa.tile_offset + sa.n_tiles, t_begin + per);
-    if (t_begin >= t_end) return;
-
-    const bool ptr_ok = ((((uintptr_t) a.in) & 15) == 0);
-    auto load_span = [&](i64 g, bool fast, uint32_t (&w)[16]) {
-        if (fast) {
-            const uint4 *src = (const uint4 *) (a.in + (g - a.in_base));
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                const uint4 x = __ldg(src + v);
-                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < 16; e++) {
-                const i64 ge = g + e;
-                w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
-            }
-        }
-    };
-    auto tile_fast = [&](uint32_t tile) -> bool {
-        const i64 g0 = a.out_lo + (i64) tile * L;
-        return ptr_ok && (((g0 - a.in_base) & 3) == 0) && g0 >= a.in_base && g0 >= 0 && (g0 + L) <= a.in_valid_end;
-    };
-    auto store_span = [&](int rp, const uint32_t (&p)[16], int xs, int ys, uint32_t gd) {
-#pragma unroll
-        for (int v = 0; v < 4; v++) {
-            s_pre[rp * 4 + ((v + (rp >> 1)) & 3)] = make_uint4(p[4 * v], p[4 * v + 1], p[4 * v + 2], p[4 * v + 3]);
-        }
-        s_xy[rp] = make_int2(xs, ys);
-        s_flag[rp] = (gd >> 25) ? 1 : 0;
-    };
-
-    // history of the first tile: the two spans in front of it go to the end of the "previous" half of the ring
-    if (threadIdx.x < 2) {
-        const i64 g = a.out_lo + (i64) t_begin * L - 2 * SPT + (i64) threadIdx.x * SPT;
-        uint32_t w[16], p[16], gd;
-        int xs, ys;
-        load_span(g, false, w);
-        screen_span_stats(w, p, xs, ys, gd);
-        store_span(TAIL + 2 * 2 + threadIdx.x, p, xs, ys, gd);     // slot 2 = "previous" of slot 0
-    }
-
-    uint32_t w_cur[16], w_nxt[16];
-    load_span(a.out_lo + (i64) t_begin * L + (i64) threadIdx.x * SPT, tile_fast(t_begin), w_cur);
-
-    int slot = 0;                                   // (tile - t_begin) % 3
-    for (uint32_t tile = t_begin; tile < t_end; tile++) {
-        const int par = (int) (tile & 1);
-        const int prev_slot = (slot == 0) ? 2 : slot - 1;
-        const i64 o0 = a.out_lo + (i64) tile * L;
-        if (tile + 1 < t_end) {
-            load_span(o0 + L + (i64) threadIdx.x * SPT, tile_fast(tile + 1), w_nxt);
-        }
-        uint32_t pre[SPT], guard;
-        int sx, sy;
-        const int rp = par * NT + threadIdx.x;
-        screen_span_stats(w_cur, pre, sx, sy, guard);
-        store_span(rp, pre, sx, sy, guard);
-        if (threadIdx.x >= NT - 2) store_span(TAIL + 2 * slot + (threadIdx.x - (NT - 2)), pre, sx, sy, guard);
-        __syncthreads();     // rows of this half are next written two tiles (= two barriers) from now
-
-        const int r1 = (threadIdx.x >= 1) ? rp - 1 : TAIL + 2 * prev_slot + 1;
-        const int r2 = (threadIdx.x >= 2) ? rp - 2 : TAIL + 2 * prev_slot + (int) threadIdx.x;
-        uint32_t bits16 = 0;
-        bool undecided_lo = false, undecided_hi = false;
-        const i64 o = o0 + (i64) threadIdx.x * SPT;
-        const bool bad = (guard >> 25) || s_flag[r1] || s_flag[r2];
-        if (!bad) {
-            uint32_t p2[SPT];
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                const uint4 x = s_pre[r2 * 4 + ((v + (r2 >> 1)) & 3)];
-                p2[4 * v] = x.x; p2[4 * v + 1] = x.y; p2[4 * v + 2] = x.z; p2[4 * v + 3] = x.w;
-            }
-            const uint32_t tot1 = s_pre[r1 * 4 + ((3 + (r1 >> 1)) & 3)].w, tot2 = p2[SPT - 1];
-            const uint32_t base = tot2 + tot1;
-            int dmax_lo = INT_MIN, dmax_hi = INT_MIN;
-#pragma unroll
-            for (int j = 0; j < SPT; j++) {
-                const int d = (int) (pre[j] - p2[j]);          // all sums < 2^31: signed difference is exact
-                if (j < 8) dmax_lo = max(dmax_lo, d); else dmax_hi = max(dmax_hi, d);
-            }
-            const bool off_lo = (uint32_t) ((int) base + dmax_lo) < sp.k0, off_hi = (uint32_t) ((int) base + dmax_hi) < sp.k0;
-            bool on = false;
-            if (!(off_lo && off_hi)) {
-                const int2 xy1 = s_xy[r1], xy2 = s_xy[r2];
-                const float X = (float) (sx + xy1.x + xy2.x), Y = (float) (sy + xy1.y + xy2.y);
-                const float Q = (float) (base + pre[SPT - 1]);
-                const float m2 = fmaf(X, X, Y * Y);
-                const float mu = sqrt_approx(m2) * sp.inv_n;
-                const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
-                const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
-                on = fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi;
-            }
-            if (on) {
-                bits16 = 0xFFFFu;
-            } else {
-                undecided_lo = !off_lo;
-                undecided_hi = !off_hi;
-            }
-        } else {
-            undecided_lo = undecided_hi = true;
-        }
-        const bool in_lo = o < a.out_hi, in_hi = o + 8 < a.out_hi;
-        if (in_lo) {
-            const i64 byte = (o - a.bit_base) >> 3;
-            if (in_hi) {
-                *(uint16_t *) (a.out_bits + byte) = (uint16_t) bits16;
-            } else {
-                a.out_bits[byte] = (uint8_t) bits16;
-            }
-        }
-        const bool push_lo = undecided_lo && in_lo, push_hi = undecided_hi && in_hi;
-        const uint32_t m_lo = __ballot_sync(0xFFFFFFFFu, push_lo), m_hi = __ballot_sync(0xFFFFFFFFu, push_hi);
-        const uint32_t n_push = __popc(m_lo) + __popc(m_hi);
-        if (n_push) {
-            const int lane = threadIdx.x & 31;
-            uint32_t slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(sa.work_count, n_push);
-            slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
-            const uint32_t below = (1u << lane) - 1;
-            const uint32_t grp0 = (uint32_t) ((o - a.bit_base) >> 3);
-            if (push_lo) {
-                const uint32_t sl = slot0 + __popc(m_lo & below);
-                if (sl < sa.work_cap) sa.work_list[sl] = grp0;
-            }
-            if (push_hi) {
-                const uint32_t sl = slot0 + __popc(m_lo) + __popc(m_hi & below);
-                if (sl < sa.work_cap) sa.work_list[sl] = grp0 + 1;
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 16; e++) w_cur[e] = w_nxt[e];
-        slot = (slot == 2) ? 0 : slot + 1;
-    }
-}
-
-// Exact recomputation of the groups the screen left undecided: one output per lane (8 lanes per group),
-// samples re-read through L1/L2.  Grid-stride over the global work list, so lanes stay full whatever the
-// distribution of undecided groups over the capture.
-template <int T>
-__global__ void __launch_bounds__(256) fir1_refine_kernel(const ScreenArgs sa, const TapsParam<T> taps)
-{
-    const TiledArgs &a = sa.t;
-    const uint32_t n_groups = min(*sa.work_count, sa.work_cap);
-    const u64 n_items = ((u64) n_groups * 8 + 31) & ~31ull;
-    for (u64 item = (u64) blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (u64) gridDim.x * blockDim.x) {
-        const u64 qi = item >> 3;
-        const uint32_t j = (uint32_t) (item & 7);
-        bool bit = false;
-        uint32_t grp = 0;
-        if (qi < n_groups) {
-            grp = sa.work_list[qi];
-            const i64 n = a.bit_base + (i64) grp * 8 + j;    // output index == index of its newest sample
-            float re = 0.0f, im = 0.0f;
-            if (n - (T - 1) >= a.in_base && n - (T - 1) >= 0 && n < a.in_valid_end) {
-                const uint32_t *src = a.in + (n - a.in_base);   // whole window present: no per-tap checks
-#pragma unroll
-                for (int i = 0; i < T; i++) {
-                    const float2 x = sc16q11_to_float2(__ldg(src - i));
-                    re = mac_exact(re, taps.t[i], x.x);
-                    im = mac_exact(im, taps.t[i], x.y);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < T; i++) {
-                    const i64 g = n - i;
-                    const uint32_t w = (g >= 0 && g >= a.in_base && g < a.in_valid_end) ? __ldg(a.in + (g - a.in_base)) : 0u;
-                    const float2 x = sc16q11_to_float2(w);
-                    re = mac_exact(re, taps.t[i], x.x);
-                    im = mac_exact(im, taps.t[i], x.y);
-                }
-            }
-            bit = power_exact(re, im) >= a.pstar;
-        }
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);
-        if (qi < n_groups && j == 0) {
-            a.out_bits[grp] = (uint8_t) (ballot >> (threadIdx.x & 24));
-        }
-    }
-}
-
-// Same job, one THREAD per undecided group of 8 outputs: the 39 samples the group's windows cover are read
-// once (ten 16-byte loads when the input is 16-byte aligned), converted once and kept in registers; 8
-// outputs = 16 independent exact accumulator chains per thread.  ~3x fewer instructions per group than
-// the lane-per-output form above and no redundant loads.
+// Exact recomputation of the groups the screen left undecided: one THREAD per group of 8 outputs.  The 39 samples the
+// group's windows cover are read once (ten 16-byte loads when the input is 16-byte aligned), converted once and kept in
+// registers; 8 outputs = 16 independent exact accumulator chains per thread.
 template <int T>
 __global__ void __launch_bounds__(128) fir1_refine_group_kernel(const ScreenArgs sa, const TapsParam<T> taps)
 {
@@ -775,183 +446,6 @@ struct Taps2Param {
     const float *d_t1, *d_t2;       // the same taps in device memory (rolled-loop boundary path)
 };
 
-__global__ void __launch_bounds__(256, 5) fir2_screen_kernel(const ScreenArgs sa, const ScreenParams sp)
-{
-    constexpr int NT = 256, SPT = 16, LIN = NT * SPT;     // 4096 inputs = 1024 outputs per tile
-    constexpr int HT = 5;                                 // history spans in front of the tile (80 samples >= 77)
-    __shared__ uint4 s_a[NT + HT];                        // pre[1], pre[5], pre[9], pre[13]
-    __shared__ uint4 s_b[NT + HT];                        // total, sum I, sum Q, flag
-
-    const TiledArgs &a = sa.t;                            // out_lo / out_hi / bit_base in OUTPUT indices
-    const uint32_t tile = blockIdx.x + sa.tile_offset;
-    const i64 o0 = a.out_lo + (i64) tile * (LIN / 4);     // first output of the tile
-    const i64 g0 = o0 * 4 - HT * SPT;                     // first input of the first history span
-    const bool fast = ((((uintptr_t) a.in) & 15) == 0) && (((g0 - a.in_base) & 3) == 0) && g0 >= a.in_base && g0 >= 0 &&
-                      (g0 + LIN + HT * SPT) <= a.in_valid_end;
-
-    uint32_t pre[SPT], guard = 0;
-    int sx = 0, sy = 0;
-#pragma unroll
-    for (int pass = 0; pass < 2; pass++) {
-        int span;
-        if (pass == 0) {
-            span = threadIdx.x + HT;
-        } else {
-            if (threadIdx.x >= HT) break;
-            span = threadIdx.x;
-        }
-        const i64 g = g0 + (i64) span * SPT;
-        uint32_t w[SPT];
-        if (fast) {
-            const uint4 *src = (const uint4 *) (a.in + (g - a.in_base));
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                const uint4 x = __ldg(src + v);
-                w[4 * v] = x.x; w[4 * v + 1] = x.y; w[4 * v + 2] = x.z; w[4 * v + 3] = x.w;
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < SPT; e++) {
-                const i64 ge = g + e;
-                w[e] = (ge >= 0 && ge >= a.in_base && ge < a.in_valid_end) ? __ldg(a.in + (ge - a.in_base)) : 0u;
-            }
-        }
-        uint32_t p[SPT], gd;
-        int xs, ys;
-        screen_span_stats(w, p, xs, ys, gd);
-        s_a[span] = make_uint4(p[1], p[5], p[9], p[13]);
-        s_b[span] = make_uint4(p[15], (uint32_t) xs, (uint32_t) ys, (gd >> 25) ? 1u : 0u);
-        if (pass == 0) {
-#pragma unroll
-            for (int e = 0; e < SPT; e++) pre[e] = p[e];
-            sx = xs; sy = ys; guard = gd;
-        }
-    }
-    __syncthreads();
-
-    const int span = threadIdx.x + HT;
-    const uint4 b1 = s_b[span - 1], b2 = s_b[span - 2], b3 = s_b[span - 3], b4 = s_b[span - 4], b5 = s_b[span - 5];
-    const uint4 a4 = s_a[span - 4], a5 = s_a[span - 5];
-    uint32_t bits4 = 0, und = 0;                          // decisions / undecided flags of the 4 outputs
-    const bool bad = (guard >> 25) || b1.w || b2.w || b3.w || b4.w || b5.w;
-    if (!bad) {
-        const uint32_t mid3 = b3.x + b2.x + b1.x;         // spans s-3 .. s-1
-        const uint32_t mid4 = mid3 + b4.x;                // spans s-4 .. s-1
-        // newest sample at element 3, 7, 11: window starts at element 6, 10, 14 of span s-5
-        const uint32_t e0 = (b5.x - a5.y) + mid4 + pre[3];
-        const uint32_t e1 = (b5.x - a5.z) + mid4 + pre[7];
-        const uint32_t e2 = (b5.x - a5.w) + mid4 + pre[11];
-        // newest sample at element 15: window starts at element 2 of span s-4
-        const uint32_t e3 = (b4.x - a4.x) + mid3 + pre[15];
-        und = (e0 < sp.k0 ? 0u : 1u) | (e1 < sp.k0 ? 0u : 2u) | (e2 < sp.k0 ? 0u : 4u) | (e3 < sp.k0 ? 0u : 8u);
-        if (und) {
-            const float X = (float) (sx + (int) b1.y + (int) b2.y + (int) b3.y + (int) b4.y + (int) b5.y);
-            const float Y = (float) (sy + (int) b1.z + (int) b2.z + (int) b3.z + (int) b4.z + (int) b5.z);
-            const float Q = (float) (b5.x + mid4 + pre[15]);
-            const float m2 = fmaf(X, X, Y * Y);
-            const float mu = sqrt_approx(m2) * sp.inv_n;
-            const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
-            const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
-            if (fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi) {
-                bits4 = 0xF;
-                und = 0;
-            }
-        }
-    } else {
-        und = 0xF;
-    }
-    // two threads share a byte of decisions
-    const uint32_t other_bits = __shfl_down_sync(0xFFFFFFFFu, bits4, 1);
-    const uint32_t other_und = __shfl_down_sync(0xFFFFFFFFu, und, 1);
-    const i64 o = o0 + (i64) threadIdx.x * 4;             // first output of this thread
-    const bool even = (threadIdx.x & 1) == 0;
-    const bool in_range = even && o < a.out_hi;
-    const bool push = in_range && ((und | other_und) != 0);
-    if (in_range) {
-        a.out_bits[(o - a.bit_base) >> 3] = (uint8_t) (bits4 | (other_bits << 4));
-    }
-    const uint32_t m_push = __ballot_sync(0xFFFFFFFFu, push);
-    if (m_push) {
-        const int lane = threadIdx.x & 31;
-        uint32_t slot0 = 0;
-        if (lane == 0) slot0 = atomicAdd(sa.work_count, (uint32_t) __popc(m_push));
-        slot0 = __shfl_sync(0xFFFFFFFFu, slot0, 0);
-        if (push) {
-            const uint32_t sl = slot0 + __popc(m_push & ((1u << lane) - 1));
-            if (sl < sa.work_cap) sa.work_list[sl] = (uint32_t) ((o - a.bit_base) >> 3);
-        }
-    }
-}
-
-// Exact two-stage recomputation of one output per lane (8 lanes per undecided group).
-//   y[m]  = sum_{j<32} t2[j] * s[2m+1-j]          accumulated from j = 0   (src/fir.c:313-318, stage 2)
-//   s[u]  = sum_{i<16} t1[i] * x[2u+1-i]          accumulated from i = 0   (stage 1); s[u<0] = 0, x[g<0] = 0
-// A 16-sample register window slides down by two inputs per stage-1 output (fully unrolled).
-__global__ void __launch_bounds__(256) fir2_refine_kernel(const ScreenArgs sa, const Taps2Param taps)
-{
-    const TiledArgs &a = sa.t;
-    const uint32_t n_groups = min(*sa.work_count, sa.work_cap);
-    const u64 n_items = ((u64) n_groups * 8 + 31) & ~31ull;
-    for (u64 item = (u64) blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += (u64) gridDim.x * blockDim.x) {
-        const u64 qi = item >> 3;
-        const uint32_t jj = (uint32_t) (item & 7);
-        bool bit = false;
-        uint32_t grp = 0;
-        if (qi < n_groups) {
-            grp = sa.work_list[qi];
-            const i64 m = a.bit_base + (i64) grp * 8 + jj;
-            const i64 g_new = 4 * m + 3;                   // newest input of output m
-            float re = 0.0f, im = 0.0f;
-            if (g_new - 77 >= a.in_base && g_new - 77 >= 0 && g_new < a.in_valid_end) {
-                const uint32_t *src = a.in + (g_new - a.in_base);
-                float2 w[16];                              // w[k] = x[2u+1-k] for the current u
-#pragma unroll
-                for (int k = 0; k < 16; k++) w[k] = sc16q11_to_float2(__ldg(src - k));
-#pragma unroll
-                for (int j = 0; j < 32; j++) {             // u = 2m+1-j
-                    float sr = 0.0f, si = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        sr = mac_exact(sr, taps.t1[i], w[i].x);
-                        si = mac_exact(si, taps.t1[i], w[i].y);
-                    }
-                    re = mac_exact(re, taps.t2[j], sr);
-                    im = mac_exact(im, taps.t2[j], si);
-                    if (j < 31) {
-#pragma unroll
-                        for (int k = 0; k < 14; k++) w[k] = w[k + 2];
-                        w[14] = sc16q11_to_float2(__ldg(src - (2 * j + 16)));
-                        w[15] = sc16q11_to_float2(__ldg(src - (2 * j + 17)));
-                    }
-                }
-            } else {
-                for (int j = 0; j < 32; j++) {
-                    const i64 u = 2 * m + 1 - j;
-                    float sr = 0.0f, si = 0.0f;
-                    if (u >= 0) {
-                        for (int i = 0; i < 16; i++) {
-                            const i64 g = 2 * u + 1 - i;
-                            const uint32_t wv = (g >= 0 && g >= a.in_base && g < a.in_valid_end) ? __ldg(a.in + (g - a.in_base)) : 0u;
-                            const float2 x = sc16q11_to_float2(wv);
-                            const float t = __ldg(taps.d_t1 + i);
-                            sr = mac_exact(sr, t, x.x);
-                            si = mac_exact(si, t, x.y);
-                        }
-                    }
-                    const float t = __ldg(taps.d_t2 + j);
-                    re = mac_exact(re, t, sr);
-                    im = mac_exact(im, t, si);
-                }
-            }
-            bit = power_exact(re, im) >= a.pstar;
-        }
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, bit);
-        if (qi < n_groups && jj == 0) {
-            a.out_bits[grp] = (uint8_t) (ballot >> (threadIdx.x & 24));
-        }
-    }
-}
-
 // Tiled EXACT kernel for the two-stage shape (every output computed with the reference's in-order MACs): the path
 // for captures where the screen cannot decide anything (low SNR) and for OOKD_FLAG_NO_SCREEN.
 // CTA = 288 threads, tile = 512 final outputs = 2048 inputs.
@@ -963,13 +457,16 @@ __global__ void __launch_bounds__(256) fir2_refine_kernel(const ScreenArgs sa, c
 // ~77 instructions per input sample against the 64 the arithmetic itself needs.
 constexpr int F2X_NT = 288, F2X_M = 512, F2X_IN = 4 * F2X_M + 80, F2X_NS = 2 * F2X_M + 30;
 
-template <bool FMA>
+template <bool FMA, bool ADAPT>
 __global__ void __launch_bounds__(F2X_NT, 2) fir2_tiled_kernel(const ScreenArgs sa, const Taps2Param taps, const FmaBand band)
 {
     __shared__ float2 s_x[F2X_IN + F2X_IN / 8 + 8];        // (+8: the last phase-1 thread reads a few slots past its valid window)
     __shared__ float2 s_s[(F2X_NS + 3) / 4 * 5 + 1];
     __shared__ float s_m2[F2X_NT / 32];
     const TiledArgs &a = sa.t;
+    if constexpr (ADAPT) {
+        if (sa.work_count[OOKD_MODE_SLOT] != OOKD_MODE_FMA) return;     // the probe chose the other screening form
+    }
     const int t = (int) threadIdx.x;
     const i64 m0 = a.out_lo + (i64) blockIdx.x * F2X_M;       // first output of the tile (a.out_lo % 8 == a.bit_base % 8)
     const i64 g0 = 4 * m0 - 80;                               // first staged input

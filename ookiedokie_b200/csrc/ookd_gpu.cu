@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -59,14 +60,12 @@ struct ookd_gpu {
     uint32_t burst_rounds = 2;
     uint32_t flags = 0;
     bool screen = false;
-    bool persist = false;
-    bool tma = false;                 // TMA-staged screening kernel (screen_tma.cuh)
     bool screen2 = false;             // dec4 shape: screen + refine (else the exact tiled two-stage kernel)
-    int screen_regs = 64;             // register cap of the TMA screening kernel (64 / 56 / 48)
-    bool screen_v2 = true;            // span statistics through dp2a, sums of I / Q only for loud spans (OOKD_SCREEN_V2=0: first form)
     bool fma = false;                 // FMA screening (fused multiply-add pass + rigorous band, exact refine of the band):
                                       // what a handle switches to when the energy proofs decide too little (low SNR)
     bool fma_ok = false;              // ... and whether this handle's filter shape / threshold allow it
+    bool adaptive = false;            // both forms available: a probe kernel picks one per decode, on the device
+    bool adaptive_ok = false;         // ... for decodes short enough that enqueueing both forms costs next to nothing
     bool fused_sm = true;             // state-machine stage as ONE cooperative kernel (sm_fused_kernel)
     unsigned fused_grid_max = 0;      // CTAs of it that can be co-resident on this device
     unsigned n_sm = 148;
@@ -78,7 +77,7 @@ struct ookd_gpu {
 
     // workspaces
     DevBuf in, bits, inter[2], block_counts, edges, scalars, chunk_exit[2], chunk_ran, slots, slot_count,
-           slot_off, msgs_dev, dense_list, chunk_e, bound_pos, seed_pos, seed_e, seed_kind, edge_tmp, final_entry, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
+           sm_dbg, slot_off, msgs_dev, dense_list, chunk_e, bound_pos, seed_pos, seed_e, seed_kind, edge_tmp, final_entry, tab_entry, tab_exit, tab_nmsg, tab_cnt[2], tab_link, tab_chosen;
     uint32_t slot_cap = 8;
     bool tables_valid = false;       // entry/exit tables of the last decode can be extended by resolve
     int tab_cur = 0;
@@ -326,12 +325,10 @@ encode_tiled_fn tensor_map_encoder()
 
 typedef void (*screen_tma_kernel_t)(const CUtensorMap, const ScreenTmaArgs, const ScreenParams);
 
-screen_tma_kernel_t screen_tma_fn(int dec, int regs, bool v2)
+screen_tma_kernel_t screen_tma_fn(int dec, bool adapt)
 {
-#define OOKD_PICK(D, V) (regs <= 48 ? fir_screen_tma_kernel<D, 48, V> : regs <= 56 ? fir_screen_tma_kernel<D, 56, V> : fir_screen_tma_kernel<D, 64, V>)
-    if (dec == 1) return v2 ? OOKD_PICK(1, true) : OOKD_PICK(1, false);
-    return v2 ? OOKD_PICK(4, true) : OOKD_PICK(4, false);
-#undef OOKD_PICK
+    if (dec == 1) return adapt ? fir_screen_tma_kernel<1, true> : fir_screen_tma_kernel<1, false>;
+    return adapt ? fir_screen_tma_kernel<4, true> : fir_screen_tma_kernel<4, false>;
 }
 
 // OOKD_FLAG_SHARE_SMS: the persistent screening kernels of different handles on one device must not overlap
@@ -389,7 +386,8 @@ int launch_screen_tma(ookd_gpu *h, const ScreenArgs &sa, const ScreenParams &sp,
     const i64 n_rows = (in_valid_end - row0) / 32;
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    bool ok = (addr0 % 16 == 0) && n_rows >= STMA_L / 32 && n_rows < (1ll << 31) && tensor_map_encoder();
+    bool ok = (addr0 % 16 == 0) && n_rows >= STMA_L / 32 && n_rows < (1ll << 31) && tensor_map_encoder() &&
+              !(h->flags & OOKD_FLAG_NO_TMA);
     if (ok) {
         const cuuint64_t gdim[2] = {32, (cuuint64_t) n_rows};
         const cuuint64_t gstride[1] = {128};
@@ -414,7 +412,7 @@ int launch_screen_tma(ookd_gpu *h, const ScreenArgs &sa, const ScreenParams &sp,
     cudaEvent_t *tok = (share && use_token) ? screen_token(h->device) : nullptr;
     if (tok) CU(h, cudaStreamWaitEvent(h->s_compute, *tok, 0));
     const unsigned grid = (unsigned) (tiles < ctas ? tiles : ctas);
-    screen_tma_fn(dec, h->screen_regs, h->screen_v2)<<<grid, STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(tmap, ta, sp);
+    screen_tma_fn(dec, h->adaptive)<<<grid, STMA_NT, STMA_SMEM_BYTES, h->s_compute>>>(tmap, ta, sp);
     if (tok) CU(h, cudaEventRecord(*tok, h->s_compute));
     return OOKD_OK;
 }
@@ -436,30 +434,43 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
             ScreenParams sp;
             make_screen_params(h, sp);
             sa.n_tiles = (uint32_t) stiles;
-            if (h->tma) {
-                if ((rc = launch_screen_tma(h, sa, sp, d_in, in_base, in_valid_end, stiles, 1))) return rc;
-            } else if (h->persist) {
-                const u64 ctas = (u64) h->n_sm * OOKD_SCREEN_PERSIST_MINB;
-                fir1_screen_persist_kernel<32><<<(unsigned) (stiles < ctas ? stiles : ctas), 256, 0, h->s_compute>>>(sa, sp);
-            } else {
-                fir1_screen_kernel<32><<<(unsigned) stiles, 256, 0, h->s_compute>>>(sa, sp);
-            }
-        } else {
+            if ((rc = launch_screen_tma(h, sa, sp, d_in, in_base, in_valid_end, stiles, 1))) return rc;
+        }
+        if (!h->screen || h->adaptive) {
             ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
             sa.t.out_lo = o_begin; sa.t.out_hi = o_end;
             FmaBand band{};
-            if (h->fma) {
+            if (h->adaptive) h->launches++;
+            // (adaptive decodes are short: when the probe did not choose this form its CTAs return at once)
+            if (h->adaptive) {
                 make_fma_band(h, band);
-                fir1_tiled_kernel<32, TILE_R, true><<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, tp, band);
+                fir1_tiled_kernel<32, TILE_R, true, true><<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, tp, band);
+            } else if (h->fma) {
+                make_fma_band(h, band);
+                fir1_tiled_kernel<32, TILE_R, true, false><<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, tp, band);
             } else {
-                fir1_tiled_kernel<32, TILE_R, false><<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, tp, band);
+                fir1_tiled_kernel<32, TILE_R, false, false><<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, tp, band);
             }
         }
         h->launches++;
         CU(h, cudaGetLastError());
         return OOKD_OK;
     }
-    if (h->path == FIR_SCREEN_DEC4 && !h->screen2) {
+    if (h->path == FIR_SCREEN_DEC4 && h->screen2) {
+        constexpr int L2 = 1024;                                        // outputs per tile (4096 inputs)
+        const u64 tiles = (u64) (o_end - o_begin + L2 - 1) / L2;
+        ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
+        sa.t.out_hi = o_end;
+        sa.tile_offset = (uint32_t) ((u64) (o_begin - h->bit_base) / L2);
+        sa.n_tiles = (uint32_t) tiles;
+        ScreenParams sp;
+        make_screen_params_dec4(h, sp);
+        if ((rc = launch_screen_tma(h, sa, sp, d_in, in_base, in_valid_end, tiles, 4))) return rc;
+        h->launches++;
+        CU(h, cudaGetLastError());
+        if (!h->adaptive) return OOKD_OK;
+    }
+    if (h->path == FIR_SCREEN_DEC4) {
         Taps2Param tp;
         memcpy(tp.t1, h->stages[0].taps.data(), sizeof(tp.t1));
         memcpy(tp.t2, h->stages[1].taps.data(), sizeof(tp.t2));
@@ -469,29 +480,14 @@ int launch_fir(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_valid_end,
         sa.t.out_lo = o_begin; sa.t.out_hi = o_end;
         const u64 tiles = (u64) (o_end - o_begin + F2X_M - 1) / F2X_M;
         FmaBand band{};
-        if (h->fma) {
+        if (h->adaptive) {
             make_fma_band(h, band);
-            fir2_tiled_kernel<true><<<(unsigned) tiles, F2X_NT, 0, h->s_compute>>>(sa, tp, band);
+            fir2_tiled_kernel<true, true><<<(unsigned) tiles, F2X_NT, 0, h->s_compute>>>(sa, tp, band);
+        } else if (h->fma) {
+            make_fma_band(h, band);
+            fir2_tiled_kernel<true, false><<<(unsigned) tiles, F2X_NT, 0, h->s_compute>>>(sa, tp, band);
         } else {
-            fir2_tiled_kernel<false><<<(unsigned) tiles, F2X_NT, 0, h->s_compute>>>(sa, tp, band);
-        }
-        h->launches++;
-        CU(h, cudaGetLastError());
-        return OOKD_OK;
-    }
-    if (h->path == FIR_SCREEN_DEC4) {
-        constexpr int L2 = 1024;                                        // outputs per tile of fir2_screen_kernel
-        const u64 tiles = (u64) (o_end - o_begin + L2 - 1) / L2;
-        ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
-        sa.t.out_hi = o_end;
-        sa.tile_offset = (uint32_t) ((u64) (o_begin - h->bit_base) / L2);
-        sa.n_tiles = (uint32_t) tiles;
-        ScreenParams sp;
-        make_screen_params_dec4(h, sp);
-        if (h->tma) {
-            if ((rc = launch_screen_tma(h, sa, sp, d_in, in_base, in_valid_end, tiles, 4))) return rc;
-        } else {
-            fir2_screen_kernel<<<(unsigned) tiles, 256, 0, h->s_compute>>>(sa, sp);
+            fir2_tiled_kernel<false, false><<<(unsigned) tiles, F2X_NT, 0, h->s_compute>>>(sa, tp, band);
         }
         h->launches++;
         CU(h, cudaGetLastError());
@@ -511,11 +507,7 @@ int launch_fir_refine(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_val
         tp.d_t1 = h->stages[0].d_taps;
         tp.d_t2 = h->stages[1].d_taps;
         ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
-        if (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) {
-            fir2_refine_kernel<<<8 * h->n_sm, 256, 0, h->s_compute>>>(sa, tp);           // lane-per-output form
-        } else {
-            fir2_refine_group_kernel<<<16 * h->n_sm, 128, 0, h->s_compute>>>(sa, tp);
-        }
+        fir2_refine_group_kernel<<<16 * h->n_sm, 128, 0, h->s_compute>>>(sa, tp);
         h->launches++;
         CU(h, cudaGetLastError());
         return OOKD_OK;
@@ -524,11 +516,7 @@ int launch_fir_refine(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_val
     TapsParam<32> tp;
     memcpy(tp.t, h->stages[0].taps.data(), sizeof(tp.t));
     ScreenArgs sa = screen_args(h, d_in, in_base, in_valid_end);
-    if (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) {
-        fir1_refine_kernel<32><<<8 * h->n_sm, 256, 0, h->s_compute>>>(sa, tp);      // lane-per-output form
-    } else {
-        fir1_refine_group_kernel<32><<<16 * h->n_sm, 128, 0, h->s_compute>>>(sa, tp);
-    }
+    fir1_refine_group_kernel<32><<<16 * h->n_sm, 128, 0, h->s_compute>>>(sa, tp);
     h->launches++;
     CU(h, cudaGetLastError());
     return OOKD_OK;
@@ -542,6 +530,8 @@ int launch_fir_exact_all(ookd_gpu *h, const uint32_t *d_in, i64 in_base, i64 in_
 {
     h->screen = false;                                                  // no screening of any kind on this handle from now on
     h->screen2 = false;
+    h->adaptive = false;
+    h->adaptive_ok = false;
     h->fma = false;
     return launch_fir(h, d_in, in_base, in_valid_end, h->bit_base, h->out_hi);
 }
@@ -666,6 +656,7 @@ SmArgs base_sm_args(ookd_gpu *h, const SmCarry &entry0)
     a.warm = h->warm ? 1u : 0u;
     a.first_chunk = 0;
     a.report_lo = h->report_lo;
+    a.dbg = (unsigned long long *) h->sm_dbg.p;
     a.mid_carry = h->final_entry.p ? (SmCarry *) h->final_entry.p + 1 : nullptr;
     a.entry_at_report = 0;
     a.chunk_e = (u64 *) h->chunk_e.p;
@@ -1071,6 +1062,10 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     h->entry_used = entry0;
     h->n_edges = 0;
     h->base_bit = 0;
+    if (getenv("OOKD_DEBUG")) {
+        if ((rc = ensure(h, h->sm_dbg, sizeof(u64) * 4 * nc))) return rc;
+        CU(h, cudaMemsetAsync(h->sm_dbg.p, 0, sizeof(u64) * 4 * nc, h->s_compute));
+    }
     SmArgs a = fast_sm_args(h, entry0);
     int cur = 0;
     uint32_t rounds = 0;
@@ -1165,7 +1160,7 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     }
     }
     CU(h, cudaGetLastError());
-    CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 336, cudaMemcpyDeviceToHost, h->s_compute));
+    CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 352, cudaMemcpyDeviceToHost, h->s_compute));
     if (getenv("OOKD_DEBUG")) {
         CU(h, cudaMemcpyAsync((char *) h->h_scalars + 384, (char *) h->scalars.p + 384, 128, cudaMemcpyDeviceToHost, h->s_compute));
     }
@@ -1274,6 +1269,24 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
     // yet): keep the edges, anchors and tables and add rounds one at a time, each with its own link / walk /
     // gather and one synchronisation, instead of starting over on the synchronous path.
     if (h->fused_sm) rounds = *(const uint32_t *) (hs + 52);
+    if (h->sm_dbg.p && getenv("OOKD_DEBUG")) {
+        std::vector<u64> d(4 * (size_t) nc);
+        cudaMemcpy(d.data(), h->sm_dbg.p, sizeof(u64) * 4 * nc, cudaMemcpyDeviceToHost);
+        std::vector<uint32_t> idx(nc);
+        for (uint32_t i = 0; i < nc; i++) idx[i] = i;
+        std::sort(idx.begin(), idx.end(), [&](uint32_t x, uint32_t y) { return d[4 * x] > d[4 * y]; });
+        u64 tot_steps = 0, tot_cycles = 0;
+        for (uint32_t i = 0; i < nc; i++) { tot_steps += d[4 * i + 1]; tot_cycles += d[4 * i]; }
+        fprintf(stderr, "[ookd] seed round: %u chunks, mean %.0f cycles / %.1f steps per warp; slowest:", nc, (double) tot_cycles / nc,
+                (double) tot_steps / nc);
+        for (int q = 0; q < 6 && q < (int) nc; q++) {
+            const uint32_t c = idx[q];
+            fprintf(stderr, " [chunk %u: %llu cycles, %llu steps, %llu errors, %llu single-sample steps, %llu hops]", c,
+                    (unsigned long long) d[4 * c], (unsigned long long) d[4 * c + 1], (unsigned long long) (d[4 * c + 2] >> 32),
+                    (unsigned long long) (d[4 * c + 2] & 0xFFFFFFFFu), (unsigned long long) d[4 * c + 3]);
+        }
+        fprintf(stderr, "\n");
+    }
     if (h->fused_sm && getenv("OOKD_DEBUG")) {
         const long long *st = (const long long *) (hs + 384);
         auto us = [&](int i) { return (double) (st[1 + i] - st[0]) * 1e-3; };
@@ -1303,7 +1316,7 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
         h->launches += 5;
         CU(h, cudaGetLastError());
         // keep [0, 8) of the host mirror (edge total) -- the device copy still holds it
-        CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 336, cudaMemcpyDeviceToHost, h->s_compute));
+        CU(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 352, cudaMemcpyDeviceToHost, h->s_compute));
         if (n_copy) {
             CU(h, cudaMemcpyAsync(h->h_msgs_pin, h->msgs_dev.p, sizeof(SmMsg) * n_copy, cudaMemcpyDeviceToHost, h->s_compute));
         }
@@ -1393,7 +1406,7 @@ void ookd_gpu_destroy(ookd_gpu *h)
     if (h->d_tab) cudaFree(h->d_tab);
     DevBuf *all[] = {&h->in, &h->bits, &h->inter[0], &h->inter[1], &h->block_counts, &h->edges, &h->scalars,
                      &h->chunk_exit[0], &h->chunk_exit[1], &h->chunk_ran, &h->slots, &h->slot_count,
-                     &h->slot_off, &h->msgs_dev, &h->dense_list, &h->chunk_e, &h->bound_pos, &h->seed_pos, &h->seed_e, &h->seed_kind, &h->edge_tmp,
+                     &h->sm_dbg, &h->slot_off, &h->msgs_dev, &h->dense_list, &h->chunk_e, &h->bound_pos, &h->seed_pos, &h->seed_e, &h->seed_kind, &h->edge_tmp,
                      &h->final_entry, &h->tab_entry, &h->tab_exit, &h->tab_nmsg, &h->tab_cnt[0],
                      &h->tab_cnt[1], &h->tab_link, &h->tab_chosen};
     for (DevBuf *b : all) release(*b);
@@ -1519,19 +1532,13 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
         h->screen2 = !(h->flags & OOKD_FLAG_NO_SCREEN) && pstar_ok;
     }
     h->n_sm = (unsigned) prop.multiProcessorCount;
-    if (const char *e = getenv("OOKD_SCREEN_REGS")) h->screen_regs = atoi(e);
-    if (const char *e = getenv("OOKD_SCREEN_V2")) h->screen_v2 = atoi(e) != 0;
-    h->persist = (h->flags & OOKD_FLAG_TILE_PER_CTA_SCREEN) == 0;
-    h->tma = h->persist && !(h->flags & OOKD_FLAG_NO_TMA);       // both screened shapes (one stage 32/1, dec4)
-    if (h->tma) {
+    {
         for (int dec : {1, 4}) {
-            for (int regs : {48, 56, 64}) {
-                for (bool v2 : {false, true}) {
-                    if (cudaFuncSetAttribute(screen_tma_fn(dec, regs, v2), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             STMA_SMEM_BYTES) != cudaSuccess) {
-                        cudaGetLastError();
-                        h->tma = false;
-                    }
+            for (bool adapt : {false, true}) {
+                if (cudaFuncSetAttribute(screen_tma_fn(dec, adapt), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         STMA_SMEM_BYTES) != cudaSuccess) {
+                    cudaGetLastError();
+                    CREATE_FAIL(OOKD_ERR_CUDA);
                 }
             }
         }
@@ -1546,6 +1553,9 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
         h->screen2 = false;
         h->fma = true;
     }
+    // both forms at hand: a probe kernel chooses per decode (energy proofs where the noise floor lets them decide,
+    // the FMA pass elsewhere); both are enqueued, the one not chosen returns at once
+    h->adaptive_ok = h->fma_ok && !h->fma && (h->screen || h->screen2) && !(h->flags & OOKD_FLAG_NO_ADAPTIVE);
 
     // ---- state machine ----
     if (cfg->sm) {
@@ -1628,6 +1638,10 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     int rc;
     if ((rc = ensure(h, h->bits, (n_bits / 8 + 64 + 8) & ~7ull))) return rc;
 
+    // Short captures (batches of independent ones, of unknown nature each): the probe kernel chooses the screening form
+    // per decode.  Long ones: the probe and the wave of CTAs of the form not chosen would cost ~40 us per decode, so the
+    // handle keeps its current form and switches once, for good, if the energy proofs overflow the work list.
+    h->adaptive = h->adaptive_ok && (h->screen || h->screen2) && !h->fma && n_bits <= (1ull << 26);
     CU(h, cudaEventRecord(h->ev_t0, h->s_compute));
     if (h->screen || h->screen2 || h->fma) {
         // work list for undecided 8-output groups: room for 1/8 of all groups (beyond that the capture is
@@ -1642,6 +1656,19 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
 
     // ---- input staging + FIR/threshold ----
     const u64 n_have = halo_avail + n_samples;                 // samples present at iq
+    auto launch_probe = [&](const uint32_t *d_src, i64 o_hi_probe) -> int {
+        if (!h->adaptive || o_hi_probe <= h->bit_base) return OOKD_OK;
+        ScreenParams sp;
+        if (h->path == FIR_SCREEN_DEC4) make_screen_params_dec4(h, sp); else make_screen_params(h, sp);
+        TiledArgs pa{};
+        pa.in = d_src; pa.in_base = in_base; pa.in_valid_end = in_valid_end;
+        pa.out_lo = h->bit_base; pa.out_hi = o_hi_probe;
+        screen_probe_kernel<<<1, 1024, 0, h->s_compute>>>(pa, (int) h->total_dec, (int) h->halo_fir + 1, sp.k0,
+                                                         (uint32_t *) ((char *) h->scalars.p + 344));
+        h->launches++;
+        CU(h, cudaGetLastError());
+        return OOKD_OK;
+    };
     (void) n_out;
     const uint32_t *d_in = (const uint32_t *) iq;
     constexpr u64 TILE = SCREEN_L;                             // piece boundaries: whole tiles of either kernel
@@ -1664,6 +1691,12 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
             CU(h, cudaEventRecord(h->ev_piece[p], h->s_copy));
             if (h->path != FIR_GENERIC) {
                 CU(h, cudaStreamWaitEvent(h->s_compute, h->ev_piece[p], 0));
+                if (p == 0) {
+                    // the probe looks at the first piece only (the rest of the capture is still on its way)
+                    i64 o_probe = (i64) (((u64) in_base + s1) / D);
+                    if (o_probe > h->out_hi) o_probe = h->out_hi;
+                    if ((rc = launch_probe(d_in, o_probe))) return rc;
+                }
                 // outputs whose newest input has arrived, rounded down to whole tiles
                 i64 o_avail;
                 if (p + 1 == n_pieces) {
@@ -1681,6 +1714,7 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
             }
         }
         if (n_pieces == 0 && h->path != FIR_GENERIC) {
+            if ((rc = launch_probe(d_in, h->out_hi))) return rc;
             if ((rc = launch_fir(h, d_in, in_base, in_valid_end, h->bit_base, h->out_hi))) return rc;
         }
         if (h->path == FIR_GENERIC) {
@@ -1690,6 +1724,7 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
         }
     } else {
         if (h->path != FIR_GENERIC) {
+            if ((rc = launch_probe(d_in, h->out_hi))) return rc;
             if ((rc = launch_fir(h, d_in, in_base, in_valid_end, h->bit_base, h->out_hi))) return rc;
         } else {
             if ((rc = run_generic_chain(h, d_in, true, in_base, in_valid_end, h->bit_base, h->out_hi, nullptr,
@@ -1773,6 +1808,8 @@ static int decode_end_once(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd
             // multiply-adds, only those inside the rigorous rounding band recomputed exactly -- and redo the decisions.
             h->screen = false;
             h->screen2 = false;
+            h->adaptive = false;
+            h->adaptive_ok = false;
             h->fma = true;
             CU(h, cudaMemsetAsync((char *) h->scalars.p + 16, 0, 12, h->s_compute));
             if ((rc = launch_fir(h, d_in, in_base, in_valid_end, h->bit_base, h->out_hi))) return rc;
@@ -1813,6 +1850,11 @@ static int decode_end_once(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd
         res->host_syncs = h->stat_syncs;
         res->fir_mode = (h->path == FIR_GENERIC) ? OOKD_FIR_GENERIC
                         : (h->screen || h->screen2) ? OOKD_FIR_SCREEN : h->fma ? OOKD_FIR_FMA : OOKD_FIR_EXACT;
+        if (h->adaptive) {                                              // what the probe chose for this decode
+            uint32_t m = *(const uint32_t *) ((const char *) h->h_scalars + 344);     // (came back with the tail's scalars)
+            if (!fast_done) cudaMemcpy(&m, (const char *) h->scalars.p + 344, 4, cudaMemcpyDeviceToHost);
+            if (m == OOKD_MODE_FMA) res->fir_mode = OOKD_FIR_FMA;
+        }
     }
     return OOKD_OK;
 }
@@ -1828,10 +1870,12 @@ int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
 }
 
 // Independent captures: capture i is decoded whole (first sample 0, EOF padding) by
-// handles[caps[i].handle].  One host thread per handle walks that handle's captures in order (a decode of a small
-// capture is bound by the ~25 launches the host has to enqueue, so the enqueueing itself is what must run in
-// parallel); on the device the kernels of the different handles overlap, which hides the latency-bound stages
-// (edge scan, state-machine rounds) of one capture behind the streaming stages of the others.
+// handles[caps[i].handle].  ONE host thread keeps every handle busy: capture i is enqueued on its handle as soon as that
+// handle's previous capture has been collected (ookd_gpu_decode_begin / _end), so up to n_handles decodes are in flight
+// and the latency-bound stages of one capture (edge scan, state-machine rounds: ~0.15 ms of a 0.2 ms decode at 2^24
+// samples) hide behind the streaming stages of the others.  (One thread per handle, each waiting in its own
+// synchronisation, was measured to serialise: the waiting threads keep the runtime busy and the launches of the others
+// queue up behind them.)
 int ookd_gpu_batch_decode(ookd_gpu *const *handles, uint32_t n_handles, const struct ookd_capture *caps, uint32_t n_caps,
                           struct ookd_msg *msgs_out, uint64_t msgs_cap, uint64_t *msg_first, struct ookd_gpu_result *results)
 {
@@ -1841,32 +1885,34 @@ int ookd_gpu_batch_decode(ookd_gpu *const *handles, uint32_t n_handles, const st
     }
     std::vector<u64> counts(n_caps, 0);
     std::vector<std::vector<ookd_msg>> held(n_caps);
-    std::vector<int> status(n_handles, OOKD_OK);
-    auto worker = [&](uint32_t hi) {
-        for (uint32_t i = 0; i < n_caps; i++) {
-            if (caps[i].handle != hi) continue;
-            ookd_gpu_result r;
-            int rc = ookd_gpu_decode_begin(handles[hi], caps[i].iq, caps[i].iq_is_device_ptr, 0, caps[i].n_samples, 1, nullptr);
-            if (!rc) rc = ookd_gpu_decode_end(handles[hi], nullptr, &r);
-            if (rc) {
-                status[hi] = rc;
-                return;
-            }
-            counts[i] = r.n_msgs;
-            held[i].assign(r.msgs, r.msgs + r.n_msgs);      // the handle's list is reused by its next decode
-            if (results) {
-                results[i] = r;
-                results[i].msgs = nullptr;
-            }
+    std::vector<int64_t> in_flight(n_handles, -1);                     // capture a handle is busy with
+    int status = OOKD_OK;
+    auto collect = [&](uint32_t hi) -> int {
+        const int64_t i = in_flight[hi];
+        if (i < 0) return OOKD_OK;
+        in_flight[hi] = -1;
+        ookd_gpu_result r;
+        const int rc = ookd_gpu_decode_end(handles[hi], nullptr, &r);
+        if (rc) return rc;
+        counts[i] = r.n_msgs;
+        held[i].assign(r.msgs, r.msgs + r.n_msgs);                     // the handle's list is reused by its next decode
+        if (results) {
+            results[i] = r;
+            results[i].msgs = nullptr;
         }
+        return OOKD_OK;
     };
-    std::vector<std::thread> threads;
-    for (uint32_t hi = 1; hi < n_handles; hi++) threads.emplace_back(worker, hi);
-    worker(0);
-    for (auto &t : threads) t.join();
-    for (uint32_t hi = 0; hi < n_handles; hi++) {
-        if (status[hi]) return status[hi];
+    for (uint32_t i = 0; i < n_caps && !status; i++) {
+        const uint32_t hi = caps[i].handle;
+        if ((status = collect(hi))) break;
+        status = ookd_gpu_decode_begin(handles[hi], caps[i].iq, caps[i].iq_is_device_ptr, 0, caps[i].n_samples, 1, nullptr);
+        if (!status) in_flight[hi] = i;
     }
+    for (uint32_t hi = 0; hi < n_handles; hi++) {
+        const int rc = collect(hi);                                    // (also after an error: nothing stays in flight)
+        if (rc && !status) status = rc;
+    }
+    if (status) return status;
     u64 total = 0;
     for (uint32_t i = 0; i < n_caps; i++) {
         msg_first[i] = total;

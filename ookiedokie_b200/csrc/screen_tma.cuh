@@ -1,11 +1,10 @@
 // screen_tma.cuh -- production form of the screening kernels: fir_screen_tma_kernel<1> for the one-stage shape
 // (T = 32, decimation 1) and <4> for the two-stage 16/2 + 32/2 shape (fs128_fs16_dec4).
 //
-// Same decisions as fir1_screen_kernel / fir1_screen_persist_kernel (fir_kernels.cuh, section 3: the
-// Cauchy-Schwarz "off" proof on exact integer window energies, the mean/scatter "on" proof, everything
-// else to the exact refine kernel), different data movement.  ncu on the register-prefetching kernel
-// showed the LSU data pipe at 90 %: a thread owning 16 consecutive samples makes every LDG.128 of a
-// warp touch 16 cache lines.  Here the raw tile (4096 samples = 16 KiB) is brought in by ONE TMA
+// The proofs are those of fir_kernels.cuh, section 3 (Cauchy-Schwarz "off" proof on exact integer window energies, the
+// mean/scatter "on" proof, everything else to the exact refine kernel).  Data movement: a thread owning 16 consecutive
+// samples that loads them itself makes every LDG.128 of a warp touch 16 cache lines (the first, register-prefetching
+// form of this kernel had the LSU data pipe at 90 % and reached 0.64 of HBM peak).  Here the raw tile (4096 samples = 16 KiB) is brought in by ONE TMA
 // tensor copy per tile into a 3-stage shared-memory ring, with the 128-byte swizzle so that the
 // per-thread 64-byte rows are read (and their prefix sums written back IN PLACE) without bank
 // conflicts:
@@ -116,9 +115,9 @@ __device__ __forceinline__ int stma_chunk_off(int u, int v)
 
 // DEC = 1: one stage, 32 taps, decimation 1 (fs32_fs4, fs64_fs8): 16 outputs per thread, window = 2 spans back.
 // DEC = 4: two stages 16/2 + 32/2 (fs128_fs16_dec4): 4 outputs per thread, composite window of 78 inputs = 5 spans
-//          back (the proofs and the elements needed are those of fir2_screen_kernel, fir_kernels.cuh section 4).
+//          back (fir_kernels.cuh section 4).
 // Tiles, a.out_lo / out_hi / bit_base are in OUTPUT indices; a tile is 4096 INPUT samples = 4096 / DEC outputs.
-// ---- span statistics, second form (V2) ----
+// ---- span statistics ----
 // |x|^2 = I*I + Q*Q through two dp2a per sample: with I = 256 I_hi + I_lo (I_hi = I >> 8 signed, I_lo = I & 255 unsigned),
 //   lo += I*I_lo + Q*Q_lo   (dp2a.lo, signed halves x unsigned bytes),   hi += I*I_hi + Q*Q_hi   (dp2a.hi, signed x signed)
 // and the running prefix is lo + 256 hi -- PRMT + 2 IDP + 1 shift-add per sample instead of two extractions, two IMADs,
@@ -183,11 +182,12 @@ __device__ __forceinline__ void screen_span_stats_v2(const uint32_t (&w)[16], ui
     }
 }
 
-// MAXR: register cap per thread.  64 = all the registers four resident CTAs can have; 56 / 48 leave 8 K / 16 K
-// registers per SM free, so that the latency-bound tail kernels of the PREVIOUS window (exact refine, edges, state
-// machine) can be resident beside the four screening CTAs of the current one (pipelined windows, ookd_gpu.cu).
-template <int DEC, int MAXR, bool V2>
-__global__ void __maxnreg__(MAXR)
+// ADAPT: the decode is adaptive (short captures: a probe kernel chose between this form and FMA screening; both are
+// enqueued and the one not chosen returns at once).  A separate instantiation, so that the plain form's code is untouched.
+// (__maxnreg__(64) rather than __launch_bounds__(256, 4): same occupancy, but ptxas then keeps three more values in
+// registers and the kernel measures 4 % faster)
+template <int DEC, bool ADAPT>
+__global__ void __maxnreg__(64)
 fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaArgs ta, const ScreenParams sp)
 {
     static_assert(DEC == 1 || DEC == 4, "shapes with a screening proof");
@@ -202,6 +202,9 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
     const uint32_t t_begin = sa.tile_offset + blockIdx.x * per;
     const uint32_t t_end = min(sa.tile_offset + sa.n_tiles, t_begin + per);
     if (t_begin >= t_end) return;
+    if constexpr (ADAPT) {
+        if (sa.work_count[OOKD_MODE_SLOT] != OOKD_MODE_ENERGY) return;   // the probe chose the other screening form
+    }
 
     const uint32_t body0 = smem_u32(smem_raw);
     // The 128-byte swizzle of the tensor copy assumes 1024-byte aligned bodies.  The dynamic shared-memory window
@@ -254,17 +257,12 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
         if (t_begin + 1 < t_end && tile_fast(t_begin + 1)) issue(t_begin + 1, 1);
     }
     if (u < HT) {
-        uint32_t w[16], p[16], gd;
+        uint32_t w[16], p[16];
         int xs, ys;
         load_span_slow(tile_in0(t_begin) - HT * SPT + (i64) u * SPT, w);
-        if constexpr (V2) {
-            uint32_t tot;
-            screen_span_stats_v2(w, p, xs, ys, tot, sp.k0);
-            p[15] = tot;
-        } else {
-            screen_span_stats(w, p, xs, ys, gd);
-            if (gd >> 25) p[15] = 0xFFFFFFFFu;
-        }
+        uint32_t tot;
+        screen_span_stats_v2(w, p, xs, ys, tot, sp.k0);
+        p[15] = tot;
         store_row(0, u - HT, p, xs, ys);
     }
 
@@ -295,13 +293,7 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
         }
         uint32_t pre[SPT], tot_own;                                         // tot_own bit 31 = "span out of range"
         int sx, sy;
-        if constexpr (V2) {
-            screen_span_stats_v2(w, pre, sx, sy, tot_own, sp.k0);
-        } else {
-            uint32_t guard;
-            screen_span_stats(w, pre, sx, sy, guard);
-            tot_own = (guard >> 25) ? 0xFFFFFFFFu : pre[15];
-        }
+        screen_span_stats_v2(w, pre, sx, sy, tot_own, sp.k0);
         {
             uint32_t p[16];
 #pragma unroll
@@ -355,7 +347,7 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
                     const float V = fmaxf(fmaf(-m2, sp.inv_n, Q), 0.0f) + 1e-5f * Q;
                     const float bc = fmaf(sp.t2, sqrt_approx(V), sp.cg * sqrt_approx(Q));
                     on = fmaf(mu, sp.g_lo, -bc) * 0.99999f > sp.theta_hi;
-                    if (V2 && (sx == OOKD_XY_QUIET || x1 == OOKD_XY_QUIET || x2 == OOKD_XY_QUIET)) on = false;
+                    if (sx == OOKD_XY_QUIET || x1 == OOKD_XY_QUIET || x2 == OOKD_XY_QUIET) on = false;
                 }
                 if (on) {
                     bits16 = 0xFFFFu;
@@ -415,7 +407,7 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
                 und = (e0 < sp.k0 ? 0u : 1u) | (e1 < sp.k0 ? 0u : 2u) | (e2 < sp.k0 ? 0u : 4u) | (e3 < sp.k0 ? 0u : 8u);
                 if (und) {
                     int X = sx, Y = sy;
-                    bool quiet = V2 && sx == OOKD_XY_QUIET;
+                    bool quiet = sx == OOKD_XY_QUIET;
 #pragma unroll
                     for (int k = 1; k <= 5; k++) {
                         int xk, yk;
@@ -423,7 +415,7 @@ fir_screen_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ScreenTmaA
                                      : "r"(xy0 + (s * STMA_XY_ROWS + u - k + HT) * 8));
                         X += xk;
                         Y += yk;
-                        quiet = quiet || (V2 && xk == OOKD_XY_QUIET);
+                        quiet = quiet || (xk == OOKD_XY_QUIET);
                     }
                     const float Xf = (float) X, Yf = (float) Y;
                     const float Q = (float) (t5 + mid4 + pre[15]);

@@ -87,6 +87,7 @@ struct SmArgs {
     i64 report_lo;            // warm: the shard's first output.  Chunk 0 starts one chunk of history earlier and runs THROUGH
                               // it up to chunk 1's anchor; every run of chunk 0 records its state there in mid_carry[slot]
     SmCarry  *mid_carry;      // [tab_k]
+    unsigned long long *dbg;  // null, or [n_chunks * 4] per seed warp: cycles, steps, errors << 32 | singles, hops (OOKD_DEBUG)
     uint32_t entry_at_report; // resolve of a warm shard: entry0 is the state AT report_lo; the pair added to chunk 0 starts there
     u64 *chunk_e;             // [n_chunks] index of the first edge at or after each chunk's start (sm_anchor_kernel)
     // Boundaries moved to anchors (sm_anchor_kernel): chunk c covers [bound_pos[c], bound_pos[c+1]).
@@ -291,6 +292,7 @@ struct SpanOut {
     uint32_t cap;
     uint32_t n_msgs;
     uint32_t *overflow;       // null => count only (probe runs)
+    uint32_t steps = 0, errs = 0, singles = 0;   // diagnostics (OOKD_DEBUG): loop iterations, ERRORs, single-sample steps
 };
 
 __device__ __forceinline__ void sm_emit(SpanOut &o, const SmCarry &s, i64 pos)
@@ -579,6 +581,23 @@ struct WarpEdges {
         cur = fetch(e + lane);
         nxt = fetch(e + 32 + lane);
     }
+    // Index of the first edge at or after e whose offset is >= nb (the next buffer's first output after an ERROR).
+    // Dropped buffers come in runs (a broken message raises an ERROR in almost every buffer it touches), so the answer
+    // is almost always among the 64 edges already held in registers: one or two ballots instead of a chain of
+    // dependent loads per dropped buffer.
+    __device__ __forceinline__ u64 first_at_or_after(u64 e, uint32_t nb, u64 nb64)
+    {
+        if (e - ebase < 64) {
+            const bool in1 = (ebase + lane) >= e && cur < nb;            // (0xFFFFFFFF = no such edge: never below nb)
+            const bool in2 = (ebase + 32 + lane) >= e && nxt < nb;
+            const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, in1), m2 = __ballot_sync(0xFFFFFFFFu, in2);
+            const uint32_t last = __shfl_sync(0xFFFFFFFFu, nxt, 31);
+            if (last >= nb) return e + (u64) (__popc(m1) + __popc(m2));  // the window reaches past nb (or past the last edge)
+            const u64 from = ebase + 64;                                  // everything held is below nb: search on from there
+            return from + edge_lower_bound_near(edges + from, n_edges - from, nb64);
+        }
+        return e + edge_lower_bound_near(edges + e, n_edges - e, nb64);
+    }
     // offset of edge e (e >= ebase); slides the window when e has left the current batch
     __device__ __forceinline__ uint32_t at(u64 e)
     {
@@ -614,7 +633,7 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
         if (more) nb64 = end64;
         const uint32_t nb = (uint32_t) (nb64 - chunk_lo);
         if (next_edge < nb) {
-            const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb64);
+            const u64 e2 = E.first_at_or_after(e, nb, (u64) nb64);
             tb ^= (uint32_t) ((e2 - e) & 1);
             e = e2;
             next_edge = E.at(e);
@@ -625,10 +644,13 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
 
     while (pos < end) {
         const bool at_edge = (next_edge == pos);
+        o.steps++;
         if (s.state == 0 || s.prev != tb) {
             // single-sample path: RESET (evaluated twice) and the first sample after a dropped buffer tail
             const uint32_t b = at_edge ? (tb ^ 1u) : tb;
+            o.singles++;
             const int r = warp_sm_step(W, s, b);
+            if (r < 0) o.errs++;
             if (at_edge) {
                 tb ^= 1u;
                 e++;
@@ -647,7 +669,7 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
                 const uint32_t nb = (uint32_t) (nb64 - chunk_lo);
                 if (nb > pos) {
                     if (next_edge < nb) {
-                        const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb64);
+                        const u64 e2 = E.first_at_or_after(e, nb, (u64) nb64);
                         tb ^= (uint32_t) ((e2 - e) & 1);
                         e = e2;
                         next_edge = E.at(e);
@@ -737,6 +759,7 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
         } else {
             r = -1;
             s.state = 0;
+            o.errs++;
         }
         s.k = 0;
         s.prev = b;
@@ -755,7 +778,7 @@ __device__ __forceinline__ void warp_sm_run_span(const SmArgs &a, const u64 n_ed
             const uint32_t nb = (uint32_t) (nb64 - chunk_lo);
             if (nb > pos) {
                 if (next_edge < nb) {
-                    const u64 e2 = e + edge_lower_bound_near(a.edges + e, n_edges - e, (u64) nb64);
+                    const u64 e2 = E.first_at_or_after(e, nb, (u64) nb64);
                     tb ^= (uint32_t) ((e2 - e) & 1);
                     e = e2;
                     next_edge = E.at(e);
@@ -986,6 +1009,7 @@ __device__ __forceinline__ void sm_round_pair(const SmArgs &a, const SmTable &T,
     // holds (e.g. a string of messages lost to dropped buffers) is then repaired in ONE round -- its cost is the
     // chain itself -- instead of one round, link and walk per chunk.
     uint32_t cc = c;
+    const long long t_dbg = a.dbg ? clock64() : 0;
     for (int hop = 0;; hop++) {
         SpanOut o;
         o.slots = a.slots + ((u64) cc * K + slot) * a.slot_cap;
@@ -1016,6 +1040,12 @@ __device__ __forceinline__ void sm_round_pair(const SmArgs &a, const SmTable &T,
             a.tab_entry[(u64) cc * K + slot] = entry;
             a.tab_exit[(u64) cc * K + slot] = s;
             a.tab_nmsg[(u64) cc * K + slot] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
+            if (a.dbg && a.round == 0) {
+                a.dbg[(u64) c * 4 + 0] = (unsigned long long) (clock64() - t_dbg);
+                a.dbg[(u64) c * 4 + 1] += o.steps;
+                a.dbg[(u64) c * 4 + 2] += ((unsigned long long) o.errs << 32) | o.singles;
+                a.dbg[(u64) c * 4 + 3] = (unsigned long long) hop + 1;
+            }
         }
         if (!warp_ok || hop >= 16 || cc + 1 >= a.n_chunks) return;
         // (all lanes hold the same carry; memory reads below are uniform)

@@ -135,7 +135,7 @@ def test_screen_decisions_equal_exact(filt, levels, sigma, thr, full):
     iq = _piecewise_capture(rng, 300001 if "dec4" in filt else 300000, levels, sigma, full_range=full)
     stages = O.load_filter(filt)
     ref = O.rx(iq, stages, None, threshold_=thr, samples_per_buffer=8192, want_bits=True)
-    for flags in (0, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_FORCE_GENERIC, B.FLAG_FMA_SCREEN):
+    for flags in (0, B.FLAG_NO_TMA, B.FLAG_NO_SCREEN, B.FLAG_FORCE_GENERIC, B.FLAG_FMA_SCREEN):
         g = B.Gpu(filter_stages=stages, threshold=thr, samples_per_buffer=8192, flags=flags)
         got = g.decode(iq)
         assert np.array_equal(g.bits(), ref["bits"]), (flags, got["refined_blocks"], got["refined_tiles"])
@@ -156,7 +156,9 @@ def test_screen_actually_screens(filt, dec):
 
 
 def test_screen_overflow_falls_back_to_exact_and_stays_correct():
-    # everything near the threshold: the work list overflows, the handle switches to the exact kernels
+    # everything near the threshold: the energy proofs decide nothing.  By default the probe kernel sees that and the
+    # decode uses FMA screening from the start; without it (OOKD_FLAG_NO_ADAPTIVE) the work list overflows once and
+    # the handle switches to FMA screening for good.  Decisions equal the oracle's either way.
     rng = np.random.default_rng(2)
     iq = _piecewise_capture(rng, 1 << 21, [0.1], 30.0)
     for filt in ("fs32_fs4", "fs128_fs16_dec4"):
@@ -164,20 +166,24 @@ def test_screen_overflow_falls_back_to_exact_and_stays_correct():
         ref = O.rx(iq, stages, None, threshold_=0.1, samples_per_buffer=8192, want_bits=True)
         g = B.Gpu(filter_stages=stages, threshold=0.1)
         first = g.decode(iq)
+        assert first["fir_mode"] == 2 and first["refined_tiles"] == 0
+        assert np.array_equal(g.bits(), ref["bits"])
+        # levels sitting on the threshold: the rounding band really is visited, but by few groups
+        assert 0 < first["refined_blocks"] < 0.05 * (1 << 21) / 8
+        g = B.Gpu(filter_stages=stages, threshold=0.1, flags=B.FLAG_NO_ADAPTIVE)
+        first = g.decode(iq)
         # the list holds 1/8 of all groups + 64 Ki: 2^21 fs32_fs4 outputs overflow it, 2^19 dec4 outputs do not
         assert first["refined_tiles"] == (1 if filt == "fs32_fs4" else 0)
         assert np.array_equal(g.bits(), ref["bits"])
         again = g.decode(iq)                      # after an overflow: FMA screening from the start
         assert again["refined_tiles"] == 0 and np.array_equal(g.bits(), ref["bits"])
         assert again["fir_mode"] == (2 if filt == "fs32_fs4" else 1)
-        if filt == "fs32_fs4":                    # levels sitting on the threshold: the rounding band really is visited
-            assert 0 < again["refined_blocks"] < 0.05 * (1 << 21) / 8
 
 
 @pytest.mark.parametrize("filt,log2n", [("fs32_fs4", 28), ("fs128_fs16_dec4", 27)])
 def test_large_capture_paths_agree_and_are_deterministic(filt, log2n):
     """2^27..2^28 samples synthesised on the device: the persistent TMA-staged screening kernel (many tiles per CTA,
-    where a shared-memory ring is reused), the tile-per-CTA screen and the exact tiled kernel must give identical
+    where a shared-memory ring is reused), the FMA screen, the guarded-load path and the exact tiled kernel must give identical
     edge lists and messages, run after run (a ring reuse race only shows at this scale)."""
     import torch
     from ookiedokie_b200 import host as H
@@ -194,7 +200,7 @@ def test_large_capture_paths_agree_and_are_deterministic(filt, log2n):
             device_ptr=d_iq.data_ptr())
     torch.cuda.synchronize()
     ref = None
-    for flags, reps in [(B.FLAG_NO_SCREEN, 1), (B.FLAG_TILE_PER_CTA_SCREEN, 1), (B.FLAG_NO_TMA, 1), (0, 4)]:
+    for flags, reps in [(B.FLAG_NO_SCREEN, 1), (B.FLAG_FMA_SCREEN, 1), (B.FLAG_NO_TMA, 1), (0, 4)]:
         g = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=0.1, samples_per_buffer=8192, flags=flags)
         g.want_list = False
         for _ in range(reps):
@@ -242,7 +248,7 @@ def test_batch_of_independent_captures_matches_oracle():
 
 @pytest.mark.parametrize("devname,filt", [("p3l-nexa2012", "fs32_fs4"), ("unknown-remote1", "fs128_fs16_dec4")])
 def test_every_code_path_gives_the_same_decode(devname, filt):
-    """Flags select alternative kernels / host paths (TMA vs register-prefetch vs tile-per-CTA screening, exact
+    """Flags select alternative kernels / host paths (tensor-copy vs guarded-load screening, FMA screening, exact
     kernel, synchronous tail, shared SMs, generic FIR): edges and messages must be identical, and equal to the oracle."""
     dev = O.load_device(devname)
     fields = util.nexa_fields if "nexa" in devname else util.remote_fields
@@ -250,7 +256,7 @@ def test_every_code_path_gives_the_same_decode(devname, filt):
                                glitches=((9000, 100),))
     stages = O.load_filter(filt)
     ref = O.rx(iq, stages, dev, samples_per_buffer=8192, want_bits=True)
-    for flags in (0, B.FLAG_SYNC_TAIL, B.FLAG_NO_TMA, B.FLAG_TILE_PER_CTA_SCREEN, B.FLAG_NO_SCREEN, B.FLAG_SHARE_SMS, B.FLAG_FMA_SCREEN,
+    for flags in (0, B.FLAG_SYNC_TAIL, B.FLAG_NO_TMA, B.FLAG_NO_SCREEN, B.FLAG_SHARE_SMS, B.FLAG_FMA_SCREEN, B.FLAG_NO_ADAPTIVE,
                   B.FLAG_FORCE_GENERIC, B.FLAG_NO_TMA | B.FLAG_SYNC_TAIL, B.FLAG_NO_GRAPH, B.FLAG_FUSED_SM,
                   B.FLAG_FUSED_SM | B.FLAG_NO_GRAPH):
         for chunk_buffers in (0, 5):

@@ -108,7 +108,7 @@ def test_c3_lowsnr_1000_messages_vs_oracle():
     for rep in range(2):                                           # (second decode: after the screen's verdict on the first)
         got = g.decode(iq)
         _compare(g, got, ref, rep)
-    assert got["fir_mode"] == 2                                    # the handle has switched to FMA screening by itself
+    assert got["fir_mode"] == 2                                    # the probe kernel chose FMA screening by itself
     print(f"C3: {len(ref['msgs'])}/{len(sent)} messages, {len(ref['edges'])} edges, sm_rounds {got['sm_rounds']}, "
           f"refined_tiles {got['refined_tiles']}, refined groups {got['refined_blocks']}")
 
