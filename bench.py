@@ -400,7 +400,9 @@ def main():
     ap.add_argument("--ref-samples", type=int, default=1 << 25, help="prefix per step of --impl reference")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-configs", action="store_true", help="skip the extra configs block (C3 low SNR, C5 batch)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra configs block (C3 low SNR, C5 batch, C4 at N > 1)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the 2^33-samples-per-GPU continuous capture (N > 1)")
+    ap.add_argument("--c4-samples", type=int, default=1 << 33, help="samples per GPU of that capture")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--chunk-buffers", type=int, default=0)
     ap.add_argument("--share", action="store_true", help="OOKD_FLAG_SHARE_SMS on the handles (three screening CTAs per SM)")
@@ -515,7 +517,7 @@ def main():
         out = last_gpu._result(res)
         return out, out["msgs_raw"], acc
 
-    def run_steps_multi(iq_arg, n_steps, depth=1):
+    def run_steps_multi(iq_arg, n_steps, depth=1, first=first, n=n):
         """world > 1: every step is a complete decode incl. the cross-rank stitch (ookiedokie_b200/shard.py)."""
         st = S.PipelinedStitcher(rank, world)
         acc = [0, 0.0, 0.0, 0.0, 0]
@@ -726,6 +728,36 @@ def main():
             if world == 1:
                 configs["c3_lowsnr_remote1_dec4"] = measure_c3(local_rank, peak)
             configs["c5_batch_mixed_fs64_fs8"] = measure_c5(rank, world, local_rank, peak)
+            if world > 1 and not args.no_c4:
+                # BASELINE configs[3]: one continuous capture of world x 2^33 samples (256 GiB at 8 GPUs), 32 GiB time shard
+                # per GPU with FIR halo and cross-shard state-machine carry; same recipe and stitch as the headline
+                n4 = args.c4_samples
+                first4 = rank * n4
+                ha4 = min(halo, first4)
+                tog4, n_tx4 = build_toggles(dev, world * n4)
+                d4 = torch.empty(((ha4 + n4) * 2,), dtype=torch.int16, device="cuda")
+                B.synth(ha4 + n4, tog4, i_on, q_on, noise_scale(), SEED, first_sample=first4 - ha4, device_id=local_rank,
+                        device_ptr=d4.data_ptr(), noise_terms=NOISE_TERMS)
+                torch.cuda.synchronize()
+                arg4 = (d4.data_ptr(), ha4 + n4)
+                run_steps_multi(arg4, 2, 1, first4, n4)
+                barrier()
+                t40 = time.perf_counter()
+                res4, msgs4, _ = run_steps_multi(arg4, 3, 1, first4, n4)
+                barrier()
+                dt4 = (time.perf_counter() - t40) / 3
+                t4 = torch.tensor([dt4], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+                dt4 = float(t4.item())
+                configs["c4_continuous_time_sharded"] = {
+                    "workload": f"one continuous capture of {world} x 2^{n4.bit_length() - 1} samples ({world * n4 * 4 / 2**30:.0f} GiB), "
+                                f"{DEVICE_NAME} + {FILTER_NAME}, one {n4 * 4 / 2**30:.0f} GiB time shard per GPU (FIR halo, carry stitch)",
+                    "ms_per_step": 1e3 * dt4, "value": world * n4 / dt4 / 1e6, "unit": UNIT,
+                    "hbm_frac_job": 4.0 * n4 / dt4 / 1e9 / peak,
+                    "messages_decoded": int(len(msgs4)) if msgs4 is not None else None,
+                    "messages_transmitted_upper_bound": n_tx4}
+                del d4
+                torch.cuda.empty_cache()
         except Exception as e:                               # the headline line must survive a failure here
             configs["error"] = f"{type(e).__name__}: {str(e)[:200]}"
 

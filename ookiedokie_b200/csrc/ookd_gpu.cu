@@ -57,7 +57,8 @@ struct ookd_gpu {
     float threshold = 0.1f, pstar = 0.0f;
     uint32_t spb = 8192;
     uint32_t chunk_buffers = 64;
-    uint32_t burst_rounds = 2;
+    uint32_t burst_rounds = 1;
+    bool burst_fixed = false;         // sm_burst_rounds given in the configuration: no adaptation
     uint32_t flags = 0;
     bool screen = false;
     bool screen2 = false;             // dec4 shape: screen + refine (else the exact tiled two-stage kernel)
@@ -975,7 +976,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
 // Rounds enqueued blindly behind the edge pass.  Round 0 resolves the chain when every chunk is entered idle at its
 // anchor; round 1 repairs the chunks entered in another state and runs on through cascades of them.  A round that
 // is not needed costs ~9 us (three kernels that return at once), a missing one costs a synchronisation.
-constexpr uint32_t FAST_BURST_ROUNDS = 2;
+constexpr uint32_t FAST_BURST_ROUNDS = 1;
 
 // arguments of the state-machine kernels on the single-synchronisation path (edge count / base bit from the
 // device-side header)
@@ -1294,6 +1295,9 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
                         "round %.1f, barrier %.1f, links %.1f, barrier %.1f, walk+scan %.1f, barrier %.1f, end %.1f; %u round(s), %u chunks\n",
                 us(0), us(1), us(2), us(8), us(9), us(3), us(4), us(5), us(7), rounds, nc);
     }
+    if (!h->fused_sm && !h->burst_fixed && overflow == 0 && walk_complete != 1 && h->burst_rounds < 2) {
+        h->burst_rounds = 2;      // this kind of capture needs the repair round: enqueue it blindly from now on
+    }
     while (!h->fused_sm && overflow == 0 && walk_complete != 1 && rounds < 16) {
         SmArgs a = fast_sm_args(h, h->pend.e0);
         a.round = rounds;
@@ -1448,6 +1452,7 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     h->chunk_buffers = cfg->sm_chunk_buffers ? cfg->sm_chunk_buffers : 64;
     h->warmup = cfg->sm_warmup != 0;
     h->burst_rounds = cfg->sm_burst_rounds ? (cfg->sm_burst_rounds < 16 ? cfg->sm_burst_rounds : 16) : FAST_BURST_ROUNDS;
+    h->burst_fixed = cfg->sm_burst_rounds != 0;
 
 #define CREATE_FAIL(code)                                                                        \
     do { ookd_gpu_destroy(h); return (code); } while (0)

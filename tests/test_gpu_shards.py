@@ -232,3 +232,56 @@ def test_one_glitch_loses_every_message_like_the_reference():
         m = B.MultiGpu([0, 0, 0], filter_stages=stages, sm=sm, samples_per_buffer=4096)
         got_m, _ = m.decode(iq)
         assert got_m["msgs"] == ref["msgs"] and np.array_equal(m.edges()[1], ref["edges"])
+
+
+def test_c4_shard_of_2pow33_samples():
+    """BASELINE configs[3] per-GPU size: a 2^33-sample (32 GiB) shard of the benchmark recipe on one GPU.  The decode of the
+    whole shard must equal (a) the oracle on a 2^27-sample prefix and (b) the same samples decoded as eight consecutive
+    2^30-sample shards chained through the state-machine carry (shard-count invariance: 64-bit positions, tile / row /
+    chunk counters beyond 2^31 samples)."""
+    import torch
+    from ookiedokie_b200 import host as H
+    free, total = torch.cuda.mem_get_info()
+    if free < 60 * 2**30:
+        pytest.skip("needs ~45 GiB of free device memory")
+    n = 1 << 33
+    fir = H.Fir("fs32_fs4")
+    hdev = H.Device("p3l-nexa2012", util.FS)
+    msgs = [hdev.message({"Channel": str(1 + i % 3), "Temperature (C)": f"{-20.0 + 0.1 * ((i * 37) % 900):.1f}"})
+            for i in range(n // 380000 + 8)]
+    tog, total_len = hdev.toggles(msgs, 12000)
+    assert total_len >= n
+    d_iq = torch.empty((n * 2,), dtype=torch.int16, device="cuda")
+    B.synth(n, np.ascontiguousarray(tog), 1488, 1253, O.noise_scale_for_sigma(0.02, 12), 0x00C0FFEE, device_id=0,
+            device_ptr=d_iq.data_ptr(), noise_terms=12)
+    torch.cuda.synchronize()
+    g = B.Gpu(filter_stages=fir.stages, sm=hdev.sm_spec(), threshold=0.1, samples_per_buffer=8192)
+    g.want_list = False
+    whole, exit_whole = g.decode_shard((d_iq.data_ptr(), n), 0, n, True, None)
+    fb, edges = g.edges()
+    assert len(whole["msgs_raw"]) > 19000 and int(whole["msgs_raw"]["out_sample"][-1]) > (1 << 32)
+    assert int(edges[-1]) > (1 << 32) and np.all(np.diff(edges.astype(np.int64)) > 0)
+    # (a) oracle on the first 2^27 samples
+    npre = 1 << 27
+    iq = d_iq[:2 * npre].cpu().numpy().reshape(-1, 2)
+    odev = O.load_device("p3l-nexa2012")
+    ref = O.rx(iq, O.load_filter("fs32_fs4"), odev, samples_per_buffer=8192)
+    k = len(ref["msgs"])
+    got_pre = B.msgs_to_tuples(whole["msgs_raw"][:k], 5)
+    # (a message completing in the prefix's last buffers could differ only through the prefix's zero padding: none does)
+    assert [tuple(m) for m in got_pre] == [tuple(m) for m in ref["msgs"]]
+    ne = len(ref["edges"])
+    assert np.array_equal(edges[:ne], ref["edges"])
+    # (b) eight shards of 2^30 chained through the carry
+    per = 1 << 30
+    halo = g.halo
+    carry, parts, eparts = None, [], []
+    for i in range(8):
+        first = i * per
+        h = min(halo, first)
+        res, carry = g.decode_shard((d_iq.data_ptr() + 4 * (first - h), h + per), first, per, i == 7, carry)
+        parts.append(res["msgs_raw"].copy())
+        eparts.append(g.edges()[1].copy())
+    assert np.array_equal(np.concatenate(parts), whole["msgs_raw"])
+    assert np.array_equal(np.concatenate(eparts), edges)
+    assert carry == exit_whole
