@@ -1034,11 +1034,15 @@ int decode_tail_fast_enqueue(ookd_gpu *h, u64 n_bits, SmCarry entry0)
     while (n_copy < h->last_n_msgs + h->last_n_msgs / 4 + 512) n_copy *= 2;   // a power of two (stable graph key)
     if (n_copy > msg_cap) n_copy = msg_cap;
     if (h->h_msgs_pin_cap < n_copy) {
+        // (re)allocating pinned memory synchronises the device and takes ~1 ms: size it once for what the geometry can
+        // produce (up to 64 Ki messages = 3 MiB) instead of following the speculative count up in steps
+        u64 want = msg_cap < (1ull << 16) ? msg_cap : (1ull << 16);
+        if (want < n_copy) want = n_copy;
         if (h->h_msgs_pin) cudaFreeHost(h->h_msgs_pin);
         h->h_msgs_pin = nullptr;
         h->h_msgs_pin_cap = 0;
-        CU(h, cudaHostAlloc((void **) &h->h_msgs_pin, sizeof(SmMsg) * n_copy, cudaHostAllocDefault));
-        h->h_msgs_pin_cap = n_copy;
+        CU(h, cudaHostAlloc((void **) &h->h_msgs_pin, sizeof(SmMsg) * want, cudaHostAllocDefault));
+        h->h_msgs_pin_cap = want;
     }
 
     // ---- edge pass: tile-local extraction, scan of the tile counts, flatten ----
