@@ -1291,6 +1291,19 @@ int decode_tail_fast_finish(ookd_gpu *h, ookd_sm_carry *exit_, ookd_gpu_result *
                     (unsigned long long) (d[4 * c + 2] & 0xFFFFFFFFu), (unsigned long long) d[4 * c + 3]);
         }
         fprintf(stderr, "\n");
+        // where the slowest warps ran on: the exit their chunk's seed pair produced against the idle state assumed at anchors
+        std::vector<SmCarry> ex((size_t) nc * TAB_K);
+        std::vector<uint8_t> kinds(nc);
+        cudaMemcpy(ex.data(), h->tab_exit.p, sizeof(SmCarry) * (size_t) nc * TAB_K, cudaMemcpyDeviceToHost);
+        cudaMemcpy(kinds.data(), h->seed_kind.p, nc, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[ookd] idle state assumed at anchors: state %u k %u bits %u prev %u\n", h->canon.state, h->canon.k,
+                h->canon.num_bits, h->canon.prev);
+        for (int q = 0; q < 5 && q < (int) nc; q++) {
+            const uint32_t c = idx[q];
+            const SmCarry &e = ex[(size_t) c * TAB_K];
+            fprintf(stderr, "[ookd]   chunk %u seed exit: state %u k %u bits %u prev %u; next chunk's seed kind %u\n", c, e.state, e.k,
+                    e.num_bits, e.prev, c + 1 < nc ? kinds[c + 1] : 99u);
+        }
     }
     if (h->fused_sm && getenv("OOKD_DEBUG")) {
         const long long *st = (const long long *) (hs + 384);

@@ -23,21 +23,25 @@ for n, v in seq:
     cur.append((n, v))
 if cur:
     steps.append(cur)
-print(f"{len(steps)} decode steps in the list")
-dev_step = steps[1] if len(steps) > 1 else steps[0]
-tot = sum(v for _, v in dev_step)
-print("-- device-resident step --")
-for n, v in dev_step:
-    print(f"{v / 1000:9.1f} us  {100 * v / tot:5.1f} %  {n}")
-print(f"{tot / 1000:9.1f} us  total")
-if len(steps) > 2:
+print(f"{len(steps)} decode steps in the list (kernels per step: {[len(x) for x in steps]})")
+single = [x for x in steps if sum(1 for n, _ in x if 'fir_screen' in n or 'exact_tiled' in n) == 1 and len(x) > 3]
+multi = [x for x in steps if sum(1 for n, _ in x if 'fir_screen' in n or 'exact_tiled' in n) > 1]
+if single:
+    single.sort(key=lambda x: sum(v for _, v in x))
+    dev_step = single[len(single) // 2]                 # median device-resident step
+    tot = sum(v for _, v in dev_step)
+    print("-- device-resident step (median of %d) --" % len(single))
+    for n, v in dev_step:
+        print(f"{v / 1000:9.1f} us  {100 * v / tot:5.1f} %  {n}")
+    print(f"{tot / 1000:9.1f} us  total (serialised, cold-cache launches under ncu: shares, not absolute times)")
+if multi:
     agg = collections.OrderedDict()
-    for n, v in steps[-1]:
+    for n, v in multi[0]:
         a = agg.setdefault(n, [0, 0.0])
         a[0] += 1
         a[1] += v
     tot = sum(a[1] for a in agg.values())
-    print("-- host-input (e2e) step, aggregated --")
+    print("-- host-input (e2e) step, aggregated (the launch list may be cut by ncu -c) --")
     for n, (c, v) in agg.items():
         print(f"{v / 1000:9.1f} us  {100 * v / tot:5.1f} %  x{c:<3d} {n}")
     print(f"{tot / 1000:9.1f} us  total")
