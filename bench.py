@@ -407,6 +407,8 @@ def main():
     ap.add_argument("--c4-samples", type=int, default=1 << 33, help="samples per GPU of that capture")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--chunk-buffers", type=int, default=0)
+    ap.add_argument("--sub-windows", type=int, default=3,
+                    help="ookd_gpu_config.sub_windows of the handles: K > 1 cuts every decode into K time shards on the same GPU")
     ap.add_argument("--share", action="store_true", help="OOKD_FLAG_SHARE_SMS on the handles (three screening CTAs per SM)")
     ap.add_argument("--pipeline", type=int, default=1,
                     help="decodes in flight per GPU in the MAIN timed region (handles used round robin); the default 1 "
@@ -451,7 +453,8 @@ def main():
     n_handles = max(depth, args.pipelined_depth, args.e2e_depth, 3 if world > 1 else 1)
     flags = args.flags | (B.FLAG_SHARE_SMS if args.share else 0)
     gpus = [B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
-                  flags=flags, sm_chunk_buffers=args.chunk_buffers, sm_warmup=1 if world > 1 else 0)
+                  flags=flags, sm_chunk_buffers=args.chunk_buffers, sm_warmup=1 if world > 1 else 0,
+                  sub_windows=args.sub_windows)
             for _ in range(n_handles)]
     gpu = gpus[0]
     n = args.samples
@@ -689,7 +692,7 @@ def main():
         if reference_binary() is not None:
             v, rows, ref_rows, ref_fb, ref_edges = run_reference_cpu(cpu_prefix, want_parity=True)
             pg = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
-                       flags=flags)
+                       flags=flags, sub_windows=args.sub_windows)         # (the configuration that was timed)
             got = pg.decode((d_iq.data_ptr(), nc))
             fb, edges = pg.edges()
             gpu_rows, cur_buf = [], None
@@ -715,7 +718,7 @@ def main():
             r = O.rx(cpu_prefix, O.load_filter(FILTER_NAME), odev, threshold_=THR, samples_per_buffer=SPB, samplerate=FS)
             v = nc / (time.perf_counter() - t0) / 1e6
             pg = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
-                       flags=flags)
+                       flags=flags, sub_windows=args.sub_windows)
             got = pg.decode((d_iq.data_ptr(), nc))
             fb, edges = pg.edges()
             assert fb == r["first_bit"] and np.array_equal(edges, r["edges"]), "edges differ from the oracle's"
@@ -786,6 +789,7 @@ def main():
             "config": {"workload": workload_name(n), "samples_per_gpu": n, "device": DEVICE_NAME, "filter": FILTER_NAME,
                        "parallelism": f"time-shards x{world}" if world > 1 else "single shard",
                        "pipeline_depth": depth,
+                       "sub_windows": args.sub_windows,      # > 1: each decode is cut into that many time shards on its own GPU
                        "stitch": (S.stitch_description() if world > 1 else "n/a"),
                        "stitch_resolves": n_resolves,        # shard decodes whose state machine had to be re-run (warm-up + main + pipelined regions, all ranks)
                        "l2": "input shard (4 B/sample) larger than L2; no flush needed",
@@ -799,9 +803,14 @@ def main():
                          "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
                          "peak_source": peak_src,
                          "kernel": "fir_screen_tma_kernel<1> (SC16Q11 -> window energies -> threshold decisions), "
-                                   "4 B/sample algorithmic, one launch per step",
-                         "kernel_ms_per_launch": screen_ms_per_launch,
-                         "job_gbs": job_gbs / world, "job_frac": job_gbs / world / peak},
+                                   "4 B/sample algorithmic, " +
+                                   (f"{args.sub_windows} launches per step (one per sub-window, samples/{args.sub_windows} each), timed as one "
+                                    "CUDA-event span from the first one's start to the last one's end: the tails of the earlier "
+                                    "sub-windows run inside that span" if args.sub_windows > 1 else "one launch per step"),
+                         "launches_per_step": max(1, args.sub_windows),
+                         "kernel_ms_per_launch": screen_ms_per_launch / max(1, args.sub_windows),
+                         "kernel_ms_per_step": screen_ms_per_launch,
+                         "job_gbs": job_gbs, "job_frac": job_gbs / peak},          # per GPU (n = samples per GPU)
             "clocks": clocks, "gpu_launches": launches,
         }
         if pipelined:

@@ -165,6 +165,12 @@ struct ookd_gpu_config {
                                                 (2: the seed round and one repair round, which chases cascades).  A round that turns out not to be needed costs ~9 us, a missing
                                                 one a host synchronisation: raise it where the slowest of many shards
                                                 sets the pace (multi-GPU)                                            */
+    uint32_t sub_windows;                    /* K >= 2: a decode long enough for it is cut into K time shards decoded by K
+                                                internal handles on the SAME device, enqueued back to back (FIR halo, warm
+                                                entry and carry stitch as between GPUs): sub-window j's latency-bound tail
+                                                (refine, edges, state machine) runs while sub-window j+1 streams.  Results
+                                                are identical; ookd_gpu_bits / ookd_gpu_filtered_sc16q11 are not available
+                                                after a decode that was cut (OOKD_ERR_STATE).  Implies sm_warmup.  0, 1: off */
 };
 
 #define OOKD_FLAG_FORCE_GENERIC  1u          /* always use the shape-agnostic FIR kernels       */
@@ -312,6 +318,17 @@ int  ookd_gpu_multi_shard_range(const ookd_gpu_multi *m, uint64_t first_sample, 
 int  ookd_gpu_multi_decode(ookd_gpu_multi *m, const void *iq, int iq_is_device_ptrs, uint64_t first_sample,
                            uint64_t n_samples, int last, const struct ookd_sm_carry *entry,
                            struct ookd_sm_carry *exit_, struct ookd_gpu_result *res);
+/* The same in two halves, from the calling thread: _begin enqueues every shard, _end waits for them in order, stitches
+ * and gathers; _resolve corrects the entry state of the window of the last decode (shard 0 re-runs its state-machine
+ * stage, later shards only if their entry changes with it).  iq_mode: 0 / 1 as iq_is_device_ptrs above, 2 = ONE device
+ * pointer to the window, for handles that share a device (gpu_ids all equal: the shards are then SUB-WINDOWS of a capture
+ * resident on that device -- the screening kernel of sub-window j+1 runs while the latency-bound tail of sub-window j
+ * does; a handle created with ookd_gpu_config.sub_windows > 1 runs exactly this underneath). */
+int  ookd_gpu_multi_decode_begin(ookd_gpu_multi *m, const void *iq, int iq_mode, uint64_t first_sample, uint64_t n_samples,
+                                 int last, const struct ookd_sm_carry *entry);
+int  ookd_gpu_multi_decode_end(ookd_gpu_multi *m, struct ookd_sm_carry *exit_, struct ookd_gpu_result *res);
+int  ookd_gpu_multi_resolve(ookd_gpu_multi *m, const struct ookd_sm_carry *entry, struct ookd_sm_carry *exit_,
+                            struct ookd_gpu_result *res);
 int  ookd_gpu_multi_edges(ookd_gpu_multi *m, const uint64_t **edges, uint64_t *n_edges, uint32_t *first_bit);
 
 uint32_t ookd_gpu_halo(const ookd_gpu *h);               /* input samples of FIR history  */

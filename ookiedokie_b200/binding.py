@@ -41,6 +41,7 @@ EXPORTS = [
     "ookd_gpu_multi_create", "ookd_gpu_multi_destroy", "ookd_gpu_multi_halo", "ookd_gpu_multi_n_gpus",
     "ookd_gpu_multi_handle", "ookd_gpu_multi_shards_used", "ookd_gpu_multi_last_error", "ookd_gpu_multi_shard_range",
     "ookd_gpu_multi_decode", "ookd_gpu_multi_edges",
+    "ookd_gpu_multi_decode_begin", "ookd_gpu_multi_decode_end", "ookd_gpu_multi_resolve",
 ]
 
 
@@ -121,7 +122,8 @@ class SmCarry(C.Structure):
 class GpuConfig(C.Structure):
     _fields_ = [("filter", C.POINTER(FilterDesc)), ("sm", C.POINTER(SmDesc)), ("threshold", C.c_float),
                 ("samples_per_buffer", C.c_uint32), ("device_id", C.c_int32), ("flags", C.c_uint32),
-                ("sm_chunk_buffers", C.c_uint32), ("sm_warmup", C.c_uint32), ("sm_burst_rounds", C.c_uint32)]
+                ("sm_chunk_buffers", C.c_uint32), ("sm_warmup", C.c_uint32), ("sm_burst_rounds", C.c_uint32),
+                ("sub_windows", C.c_uint32)]
 
 
 class GpuResult(C.Structure):
@@ -335,7 +337,7 @@ class Gpu:
     """One ookd_gpu handle."""
 
     def __init__(self, filter_stages=None, sm=None, threshold=0.1, samples_per_buffer=8192, device_id=-1,
-                 flags=0, sm_chunk_buffers=0, sm_warmup=0, sm_burst_rounds=0):
+                 flags=0, sm_chunk_buffers=0, sm_warmup=0, sm_burst_rounds=0, sub_windows=0):
         L = lib()
         cfg = GpuConfig()
         self._keep = []
@@ -357,6 +359,7 @@ class Gpu:
         cfg.sm_chunk_buffers = sm_chunk_buffers
         cfg.sm_warmup = sm_warmup
         cfg.sm_burst_rounds = sm_burst_rounds
+        cfg.sub_windows = sub_windows
         self.h = C.c_void_p()
         rc = L.ookd_gpu_create(C.byref(self.h), C.byref(cfg))
         if rc != 0:

@@ -45,6 +45,10 @@ enum FirPath { FIR_GENERIC = 0, FIR_TILED_1STAGE_32, FIR_SCREEN_DEC4 };
 struct ookd_gpu {
     int device = 0;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    ookd_gpu_multi *sub = nullptr;    // cfg.sub_windows > 1: K internal handles on this device, long decodes are cut into K time shards
+    uint32_t sub_k = 0;
+    bool sub_active = false;          // the decode in flight was handed to `sub`
+    bool sub_last = false;            // ... and so was the last completed one (edges / resolve are answered by `sub`)
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_s1 = nullptr;
     std::vector<cudaEvent_t> ev_piece;
 
@@ -1418,6 +1422,8 @@ const char *ookd_gpu_last_error(const ookd_gpu *h)
 void ookd_gpu_destroy(ookd_gpu *h)
 {
     if (!h) return;
+    if (h->sub) ookd_gpu_multi_destroy(h->sub);
+    h->sub = nullptr;
     cudaSetDevice(h->device);
     if (h->s_compute) cudaStreamSynchronize(h->s_compute);
     if (h->s_copy) cudaStreamSynchronize(h->s_copy);
@@ -1467,7 +1473,7 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
     h->spb = cfg->samples_per_buffer;
     h->flags = cfg->flags;
     h->chunk_buffers = cfg->sm_chunk_buffers ? cfg->sm_chunk_buffers : 64;
-    h->warmup = cfg->sm_warmup != 0;
+    h->warmup = cfg->sm_warmup != 0 || (cfg->sub_windows > 1 && cfg->sm);
     h->burst_rounds = cfg->sm_burst_rounds ? (cfg->sm_burst_rounds < 16 ? cfg->sm_burst_rounds : 16) : FAST_BURST_ROUNDS;
     h->burst_fixed = cfg->sm_burst_rounds != 0;
 
@@ -1603,6 +1609,19 @@ int ookd_gpu_create(ookd_gpu **out, const struct ookd_gpu_config *cfg)
         carry_to_dev(idle, h->canon);
         h->have_sm = true;
     }
+    if (cfg->sub_windows > 1 && cfg->sm) {
+        // sub-windows: K more handles on this device (same configuration, warm entry), driven through ookd_multi.cpp
+        const uint32_t K = cfg->sub_windows < 16 ? cfg->sub_windows : 16;
+        ookd_gpu_config c = *cfg;
+        c.sub_windows = 0;
+        c.device_id = dev;
+        int32_t ids[16];
+        for (uint32_t k = 0; k < K; k++) ids[k] = dev;
+        const int rc = ookd_gpu_multi_create(&h->sub, &c, ids, K);
+        if (rc != OOKD_OK) CREATE_FAIL(rc);
+        if (ookd_gpu_multi_halo(h->sub) != h->halo) CREATE_FAIL(OOKD_ERR_STATE);     // (same formula: cannot happen)
+        h->sub_k = K;
+    }
 #undef CUC
 #undef CREATE_FAIL
     *out = h;
@@ -1622,9 +1641,22 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
                           uint64_t n_samples, int last, const struct ookd_sm_carry *entry)
 {
     if (!h) return OOKD_ERR_ARG;
-    if (h->pend.active) return fail(h, OOKD_ERR_STATE, "decode_begin: the previous decode has not been ended");
+    if (h->pend.active || h->sub_active) return fail(h, OOKD_ERR_STATE, "decode_begin: the previous decode has not been ended");
     if (!iq && n_samples) return fail(h, OOKD_ERR_ARG, "null input");
     CU(h, cudaSetDevice(h->device));
+    if (h->sub) {
+        // cut into sub_k time shards when each of them is at least as long as the history it reads (else: one piece)
+        const u64 al = (u64) h->spb / gcd64(h->spb, h->total_dec) * h->total_dec;
+        const u64 per = ((n_samples + al - 1) / al + h->sub_k - 1) / h->sub_k * al;
+        h->sub_last = false;
+        if (per >= h->halo && n_samples > per) {
+            const int rc = ookd_gpu_multi_decode_begin(h->sub, iq, iq_is_device_ptr ? 2 : 0, first_sample, n_samples, last, entry);
+            if (rc) return fail(h, rc, "sub-windows: %s", ookd_gpu_multi_last_error(h->sub));
+            h->have_last = false;
+            h->sub_active = true;
+            return OOKD_OK;
+        }
+    }
     h->have_last = false;
     h->tables_valid = false;
     h->h_edges_valid = false;
@@ -1789,6 +1821,13 @@ static int decode_end_once(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd
 int ookd_gpu_decode_end(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd_gpu_result *res)
 {
     if (!h) return OOKD_ERR_ARG;
+    if (h->sub_active) {
+        h->sub_active = false;
+        const int rc = ookd_gpu_multi_decode_end(h->sub, exit_, res);
+        if (rc) return fail(h, rc, "sub-windows: %s", ookd_gpu_multi_last_error(h->sub));
+        h->sub_last = true;
+        return OOKD_OK;
+    }
     if (!h->pend.active) return fail(h, OOKD_ERR_STATE, "decode_end without decode_begin");
     const bool was_warm = h->warm;
     int rc = decode_end_once(h, exit_, res);
@@ -1881,6 +1920,21 @@ static int decode_end_once(ookd_gpu *h, struct ookd_sm_carry *exit_, struct ookd
     return OOKD_OK;
 }
 
+// (internal, for ookd_multi.cpp; not in the header) CUDA-event spans over the sub-windows of one capture on one device:
+// from the first handle's stage start to the last handle's screening end / FIR end / last kernel.
+int ookd_gpu_internal_spans(const ookd_gpu *first, const ookd_gpu *last_h, float *screen_ms, float *fir_ms, float *kernel_ms)
+{
+    if (!first || !last_h || first->device != last_h->device) return OOKD_ERR_ARG;
+    if (cudaSetDevice(first->device) != cudaSuccess) return OOKD_ERR_CUDA;
+    if (cudaEventElapsedTime(screen_ms, first->ev_f0, last_h->ev_s1) != cudaSuccess ||
+        cudaEventElapsedTime(fir_ms, first->ev_f0, last_h->ev_f1) != cudaSuccess ||
+        cudaEventElapsedTime(kernel_ms, first->ev_t0, last_h->ev_t1) != cudaSuccess) {
+        cudaGetLastError();
+        return OOKD_ERR_CUDA;
+    }
+    return OOKD_OK;
+}
+
 int ookd_gpu_decode_shard(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, uint64_t first_sample,
                           uint64_t n_samples, int last, const struct ookd_sm_carry *entry,
                           struct ookd_sm_carry *exit_, struct ookd_gpu_result *res)
@@ -1958,6 +2012,10 @@ int ookd_gpu_resolve(ookd_gpu *h, const struct ookd_sm_carry *entry, struct ookd
                      struct ookd_gpu_result *res)
 {
     if (!h || !entry) return OOKD_ERR_ARG;
+    if (h->sub_last) {
+        const int rc = ookd_gpu_multi_resolve(h->sub, entry, exit_, res);
+        return rc ? fail(h, rc, "sub-windows: %s", ookd_gpu_multi_last_error(h->sub)) : OOKD_OK;
+    }
     if (!h->have_last) return fail(h, OOKD_ERR_STATE, "resolve without a preceding decode");
     CU(h, cudaSetDevice(h->device));
     SmCarry e0{};
@@ -1982,6 +2040,10 @@ int ookd_gpu_resolve(ookd_gpu *h, const struct ookd_sm_carry *entry, struct ookd
 int ookd_gpu_edges(ookd_gpu *h, const uint64_t **edges, uint64_t *n_edges, uint32_t *first_bit)
 {
     if (!h || !edges || !n_edges) return OOKD_ERR_ARG;
+    if (h->sub_last) {
+        const int rc = ookd_gpu_multi_edges(h->sub, edges, n_edges, first_bit);
+        return rc ? fail(h, rc, "sub-windows: %s", ookd_gpu_multi_last_error(h->sub)) : OOKD_OK;
+    }
     if (!h->have_last) return fail(h, OOKD_ERR_STATE, "no decode yet");
     CU(h, cudaSetDevice(h->device));
     if (!h->h_edges_valid) {
@@ -2014,6 +2076,7 @@ int ookd_gpu_edges(ookd_gpu *h, const uint64_t **edges, uint64_t *n_edges, uint3
 int ookd_gpu_bits(ookd_gpu *h, uint8_t *bits_out, uint64_t max_out, uint64_t *n_out)
 {
     if (!h || !n_out) return OOKD_ERR_ARG;
+    if (h->sub_last) return fail(h, OOKD_ERR_STATE, "decisions are not kept in one piece after a decode cut into sub-windows");
     if (!h->have_last) return fail(h, OOKD_ERR_STATE, "no decode yet");
     CU(h, cudaSetDevice(h->device));
     const u64 n = (u64) (h->out_hi - h->report_lo);
@@ -2076,6 +2139,7 @@ int ookd_gpu_filtered(ookd_gpu *h, const int16_t *iq, uint64_t n_samples, int iq
 int ookd_gpu_filtered_sc16q11(ookd_gpu *h, int16_t *out_host, uint64_t max_out, uint64_t *n_out)
 {
     if (!h || !n_out) return OOKD_ERR_ARG;
+    if (h->sub_last) return fail(h, OOKD_ERR_STATE, "filtered_sc16q11: not available after a decode cut into sub-windows");
     if (!h->have_last || h->pend.active) return fail(h, OOKD_ERR_STATE, "filtered_sc16q11: no completed decode");
     CU(h, cudaSetDevice(h->device));
     const u64 n = (u64) (h->out_hi - h->report_lo);

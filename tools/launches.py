@@ -1,6 +1,7 @@
-"""Summarise an ncu --csv launch list (gpu__time_duration.sum) of bench.py: one decode step = the launches from one
-FIR / threshold launch (or run of them) up to the next.  Prints the second step (shard resident in HBM) launch by launch and
-the last step (host input: one screening launch per 64 MiB piece) aggregated by kernel."""
+"""Summarise an ncu --csv launch list (gpu__time_duration.sum) of bench.py: one decode (or one sub-window of a decode) =
+the launches from one FIR / threshold launch (or run of them) up to the next.  Prints the median such group (input
+resident in HBM) launch by launch, with `launches.py list.csv K` also one whole step of K sub-windows aggregated by kernel,
+and the last host-input step (one screening launch per 64 MiB piece) aggregated by kernel."""
 import collections
 import csv
 import sys
@@ -34,6 +35,22 @@ if single:
     for n, v in dev_step:
         print(f"{v / 1000:9.1f} us  {100 * v / tot:5.1f} %  {n}")
     print(f"{tot / 1000:9.1f} us  total (serialised, cold-cache launches under ncu: shares, not absolute times)")
+    K = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    if K > 1 and len(single) >= K:
+        # under ncu the launches are serialised in host order: the K sub-windows of a step follow each other
+        order = [x for x in steps if x in single]
+        step = order[-K:] if len(order) % K == 0 else order[:K]
+        agg = collections.OrderedDict()
+        for grp in step:
+            for n, v in grp:
+                a = agg.setdefault(n, [0, 0.0])
+                a[0] += 1
+                a[1] += v
+        tot = sum(a[1] for a in agg.values())
+        print(f"-- one device-resident step = {K} sub-windows, aggregated by kernel --")
+        for n, (c, v) in agg.items():
+            print(f"{v / 1000:9.1f} us  {100 * v / tot:5.1f} %  x{c:<3d} {n}")
+        print(f"{tot / 1000:9.1f} us  total of {sum(a[0] for a in agg.values())} launches (serialised under ncu; live, the tails of sub-windows 1..K-1 overlap the next screens)")
 if multi:
     agg = collections.OrderedDict()
     for n, v in multi[0]:
