@@ -874,7 +874,7 @@ int run_state_machine(ookd_gpu *h, SmCarry entry0, ookd_sm_carry *exit_, ookd_gp
             CU(h, cudaGetLastError());
             rounds = 1;
         } else {
-            fill_u32_kernel<<<(nc + 255) / 256, 256, 0, h->s_compute>>>((uint32_t *) h->tab_cnt[0].p, nc, 1u);     // slot 0 = the seed
+            seed_count_kernel<<<(nc + 255) / 256, 256, 0, h->s_compute>>>((const uint8_t *) h->seed_kind.p, (uint32_t *) h->tab_cnt[0].p, nc);   // slot 0 = the seed
         }
         for (;;) {
             // round 0 (seeds) and round 1 (predecessors' exits) back to back, later rounds one at a time;
@@ -1646,8 +1646,8 @@ int ookd_gpu_decode_begin(ookd_gpu *h, const int16_t *iq, int iq_is_device_ptr, 
     CU(h, cudaSetDevice(h->device));
     if (h->sub) {
         // cut into sub_k time shards when each of them is at least as long as the history it reads (else: one piece)
-        const u64 al = (u64) h->spb / gcd64(h->spb, h->total_dec) * h->total_dec;
-        const u64 per = ((n_samples + al - 1) / al + h->sub_k - 1) / h->sub_k * al;
+        uint64_t sf0 = 0, per = 0;
+        ookd_gpu_multi_shard_range(h->sub, first_sample, n_samples, 0, &sf0, &per);
         h->sub_last = false;
         if (per >= h->halo && n_samples > per) {
             const int rc = ookd_gpu_multi_decode_begin(h->sub, iq, iq_is_device_ptr ? 2 : 0, first_sample, n_samples, last, entry);

@@ -100,7 +100,11 @@ struct SmArgs {
 
 #define OOKD_SEED_TRUE      0   /* the shard's true entry (chunk 0)                                             */
 #define OOKD_SEED_CANON     1   /* idle machine at the chunk's anchor; the chunk's boundary IS the anchor        */
-#define OOKD_SEED_RESET     3   /* no anchor: RESET at the chunk's first sample                                  */
+#define OOKD_SEED_IDLE      2   /* no transition in the chunk, carrier off: idle machine at its first sample (silence)   */
+#define OOKD_SEED_RESET     3   /* no anchor (chunk 0 of a warm shard; carrier on throughout): RESET at the first sample */
+#define OOKD_SEED_NONE      4   /* transitions but no anchor: the chunk continues a burst that began earlier.  A guess at
+                                 * its first sample would land mid-message and drag its garbage through the following
+                                 * chunks; the run that arrives from the chunk in front adds this chunk's pair instead    */
 
 __device__ __forceinline__ i64 first_output_of_buffer(const SmArgs &a, u64 b)
 {
@@ -842,10 +846,11 @@ __device__ __forceinline__ void carry_reset(SmCarry &s, uint32_t prev)
     const u64 n_edges = (a).hdr ? (a).hdr->n_edges : (a).n_edges;                               \
     const uint32_t base_bit = (a).hdr ? (a).hdr->base_bit : (a).base_bit;
 
-__global__ void fill_u32_kernel(uint32_t *p, uint32_t n, uint32_t v)
+// pairs a chunk has before round 0: its seed's, unless it has none (OOKD_SEED_NONE = 4, below)
+__global__ void seed_count_kernel(const uint8_t *kind, uint32_t *cnt, uint32_t n)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
+    if (i < n) cnt[i] = (kind[i] == 4) ? 0u : 1u;
 }
 
 // Anchors, once per decode.  One warp per chunk: the chunk's first "anchor" is the first rising edge from which
@@ -920,8 +925,12 @@ __device__ __forceinline__ void sm_anchor_chunk(const SmArgs &a, const SmTable &
         kind = OOKD_SEED_CANON;
         bound = seed;
         bound_e = seed_e;
+    } else if (c == 0) {
+        kind = OOKD_SEED_RESET;                              // (warm shard: somebody has to start the chain)
+    } else if (e < n_edges && a.edges[e] < (u64) end) {
+        kind = OOKD_SEED_NONE;
     } else {
-        kind = OOKD_SEED_RESET;
+        kind = (tb == 0) ? OOKD_SEED_IDLE : OOKD_SEED_RESET;
     }
     a.bound_pos[c] = bound;
     a.chunk_e[c] = bound_e;
@@ -938,7 +947,7 @@ __global__ void __launch_bounds__(32) sm_anchor_kernel(const SmArgs a)
     if (c >= a.n_chunks) return;
     load_table(T, a.tab);
     sm_anchor_chunk(a, T, c, threadIdx.x & 31, n_edges, base_bit);
-    if (threadIdx.x == 0 && a.cnt_out) a.cnt_out[c] = 1u;    // every chunk starts with one pair: its seed (slot 0)
+    if (threadIdx.x == 0 && a.cnt_out) a.cnt_out[c] = (a.seed_kind[c] == OOKD_SEED_NONE) ? 0u : 1u;   // the seed's pair (slot 0)
 }
 
 // One WARP per (chunk, slot): the work is a chain of dependent steps, so what matters is latency, not lanes; giving
@@ -965,6 +974,7 @@ __device__ __forceinline__ void sm_round_pair(const SmArgs &a, const SmTable &T,
         // one speculative seed per chunk, prepared by sm_anchor_chunk
         if (!warp_ok && lane != 0) return;
         const uint32_t kind = a.seed_kind[c];
+        if (kind == OOKD_SEED_NONE) return;
         pos = a.seed_pos[c];
         e = a.seed_e[c];
         tb = base_bit ^ (uint32_t) (e & 1);
@@ -972,7 +982,7 @@ __device__ __forceinline__ void sm_round_pair(const SmArgs &a, const SmTable &T,
             s = a.entry_ptr ? *a.entry_ptr : a.entry0;
             if (s.state < T.num_states && s.k > T.states[s.state].ksat) s.k = T.states[s.state].ksat;
             entry = s;
-        } else if (kind == OOKD_SEED_CANON) {
+        } else if (kind == OOKD_SEED_CANON || kind == OOKD_SEED_IDLE) {
             s = a.canon;
             entry = s;
         } else {
@@ -1054,7 +1064,7 @@ __device__ __forceinline__ void sm_round_pair(const SmArgs &a, const SmTable &T,
         if (a.round == 0) {
             // the only entry chunk nn has (or is getting right now, from its own warp) is its seed
             const uint32_t kind = a.seed_kind[nn];
-            if (kind == OOKD_SEED_CANON) {
+            if (kind == OOKD_SEED_CANON || kind == OOKD_SEED_IDLE) {
                 known = carry_equal(s, a.canon);
             } else if (kind == OOKD_SEED_RESET) {
                 SmCarry r;
@@ -1464,8 +1474,9 @@ __global__ void __launch_bounds__(SM_FUSED_NT) sm_fused_kernel(const SmFusedArgs
     for (uint32_t c = gw; c < nc; c += n_gw) {
         sm_anchor_chunk(a, T, c, lane, n_edges, base_bit);
         if (lane == 0) {
-            f.cnt_alloc[c] = 1u;
-            f.cnt_done[c] = 1u;
+            const uint32_t n0 = (a.seed_kind[c] == OOKD_SEED_NONE) ? 0u : 1u;
+            f.cnt_alloc[c] = n0;
+            f.cnt_done[c] = n0;
         }
     }
     STAMP(0);
