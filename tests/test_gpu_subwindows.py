@@ -135,3 +135,31 @@ def test_subwindows_at_scale_equal_the_undivided_decode():
         assert np.array_equal(sub.edges()[1], wedges)
     plain.close()
     sub.close()
+
+
+@pytest.mark.parametrize("chunk_buffers", [8, 16])
+def test_silence_and_bursts_longer_than_a_chunk_resolve_in_the_seed_round(chunk_buffers):
+    """Seeds of chunks without a message start (sm_kernels.cuh: OOKD_SEED_IDLE / _NONE): long silences (tens of chunks
+    without a transition) and messages spanning several chunks (a nexa message is 0.2 s = 5..10 chunks here) must come out
+    as the reference's, without repair rounds (one host synchronisation, the seed round only)."""
+    dev = O.load_device("p3l-nexa2012")
+    stages = O.load_filter("fs32_fs4")
+    msgs = [O.message_bytes(dev, util.nexa_fields(i)) for i in range(4)]
+    tog, total = O.toggles_from_messages(dev, msgs, util.FS, 3000000)         # a second of silence in front
+    tog = np.array(tog, dtype=np.uint64)
+    gap = 4000000
+    cut = len(tog) // 2 // 2 * 2
+    tog = np.concatenate([tog[:cut], tog[cut:] + np.uint64(gap)])            # ... more between messages 2 and 3
+    total += gap + 2000000                                                    # ... and behind
+    i_on, q_on = O.on_level(0.9, 0.3)
+    iq = O.synth(total, tog, i_on, q_on, O.noise_scale_for_sigma(0.01), 5)
+    spb = 8192
+    ref = O.rx(iq, stages, dev, samples_per_buffer=spb)
+    assert len(ref["msgs"]) == 4
+    g = B.Gpu(filter_stages=stages, sm=util.sm_spec(dev, stages), samples_per_buffer=spb, sm_chunk_buffers=chunk_buffers)
+    for rep in range(2):
+        got = g.decode(iq)
+        assert got["msgs"] == ref["msgs"]
+        assert np.array_equal(g.edges()[1], ref["edges"])
+        assert got["sm_rounds"] == 1 and got["host_syncs"] == 1, (got["sm_rounds"], got["host_syncs"])
+    g.close()
