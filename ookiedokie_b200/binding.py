@@ -621,7 +621,8 @@ def batch_decode(gpus, captures, msgs_cap=None):
     handles = (C.c_void_p * len(gpus))(*[g.h for g in gpus])
     first = (C.c_uint64 * (n + 1))()
     results = (GpuResult * max(n, 1))()
-    cap = int(msgs_cap) if msgs_cap is not None else 4096
+    # (a list that does not fit costs a SECOND decode of the whole batch: start with room for 256 messages per capture)
+    cap = int(msgs_cap) if msgs_cap is not None else max(4096, 256 * n)
     while True:
         out = np.zeros(cap, dtype=MSG_DTYPE)
         rc = lib().ookd_gpu_batch_decode(handles, len(gpus), caps, n, out.ctypes.data, cap, first, results)
