@@ -285,3 +285,19 @@ def test_c4_shard_of_2pow33_samples():
     assert np.array_equal(np.concatenate(parts), whole["msgs_raw"])
     assert np.array_equal(np.concatenate(eparts), edges)
     assert carry == exit_whole
+
+
+def test_multi_gpu_api_and_cli_on_distinct_devices():
+    """The same on >= 2 real GPUs (one host thread per device, device-resident shards on their own GPUs, the CLI's
+    --gpus 2 / --gpu-ids 1,0 against one GPU): tools/multi_2gpu_check.py.  Skipped on one-GPU boxes."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "multi_2gpu_check.py")], cwd=root, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok CLI" in r.stdout
