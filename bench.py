@@ -360,9 +360,17 @@ def measure_c5(rank, world, local_rank, peak, n_caps_total=256, log2n=24, per=16
     torch.cuda.synchronize()
     # `per` handles per device description = captures in flight per kind: a capture of 2^24 samples is 12 us of streaming
     # followed by ~0.3 ms of latency-bound stages (edges, state machine), so throughput comes from overlapping many
+    kinds = sorted(set(i % 2 for i in mine))                 # (with an even number of ranks a rank holds one kind only)
+    per_kind = 2 * per // max(1, len(kinds))
     gpus = [B.Gpu(filter_stages=fir.stages, sm=devs[kind].sm_spec(), threshold=THR, samples_per_buffer=SPB,
-                  device_id=local_rank) for kind in range(2) for _ in range(per)]
-    caps = [((bufs[j].data_ptr(), n), (i % 2) * per + (j // 2) % per) for j, i in enumerate(mine)]
+                  device_id=local_rank) for kind in kinds for _ in range(per_kind)]
+    # capture -> handle: round robin over the handles of its kind
+    seen = {k: 0 for k in kinds}
+    caps = []
+    for j, i in enumerate(mine):
+        kind = i % 2
+        caps.append(((bufs[j].data_ptr(), n), kinds.index(kind) * per_kind + seen[kind] % per_kind))
+        seen[kind] += 1
     B.batch_decode(gpus, caps[:2 * per])                     # warm-up (workspace allocation)
     B.batch_decode(gpus, caps[:2 * per])                     # (and once more: the speculative message copies settle)
     torch.cuda.synchronize()
