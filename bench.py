@@ -285,7 +285,7 @@ def pin_to_gpu_numa(local_rank):
 FP32_ISSUE_PER_S = 148 * 128 * 1.965e9                       # fp32 lanes x clock (MEASURED_PEAKS.json sm_max_mhz)
 
 
-def measure_c3(local_rank, peak):
+def measure_c3(local_rank, peak, sub_windows=0):
     """BASELINE configs[2]: unknown-remote1 through fs128_fs16_dec4 on a low-SNR capture (amp 0.30, near-Gaussian noise
     sigma 0.10): nothing can be screened, the exact two-stage kernel computes every output (fp32-issue bound)."""
     import numpy as np
@@ -305,7 +305,8 @@ def measure_c3(local_rank, peak):
     B.synth(n, np.ascontiguousarray(tog), i_on, q_on, noise_scale(0.10), 7, device_id=local_rank, device_ptr=d.data_ptr(),
             noise_terms=NOISE_TERMS)
     torch.cuda.synchronize()
-    g = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank)
+    g = B.Gpu(filter_stages=fir.stages, sm=dev.sm_spec(), threshold=THR, samples_per_buffer=SPB, device_id=local_rank,
+              sub_windows=sub_windows)
     g.want_list = False
     first = g.decode((d.data_ptr(), n))                      # (the screen's verdict: work list overflow -> exact kernels)
     g.decode((d.data_ptr(), n))
