@@ -163,3 +163,38 @@ def test_silence_and_bursts_longer_than_a_chunk_resolve_in_the_seed_round(chunk_
         assert np.array_equal(g.edges()[1], ref["edges"])
         assert got["sm_rounds"] == 1 and got["host_syncs"] == 1, (got["sm_rounds"], got["host_syncs"])
     g.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_subwindow_fuzz(seed):
+    """Seeded random shapes: device, filter, samples per buffer, chunk size, K, noise level, glitch bursts that make the
+    reference lose messages (strings of dropped buffers across sub-window boundaries); messages, transitions and the exit
+    state must be the oracle's / the undivided decode's."""
+    rng = np.random.default_rng(1000 + seed)
+    devname = ["p3l-nexa2012", "unknown-remote1"][int(rng.integers(2))]
+    filt = ["fs32_fs4", "fs128_fs16_dec4", "fs64_fs8"][int(rng.integers(3))]
+    spb = [1001, 4096, 8192][int(rng.integers(3))]
+    k = int(rng.integers(2, 7))
+    cb = int(rng.integers(2, 9))
+    sigma = float(rng.choice([0.0, 0.02, 0.04, 0.06]))
+    dev = O.load_device(devname)
+    fields = util.nexa_fields if "nexa" in devname else util.remote_fields
+    n_msgs = int(rng.integers(8, 14))
+    iq0, _, tog = util.capture(dev, n_msgs, sigma=0.0, amplitude=0.8, phase=0.4, seed=seed, fields=fields)
+    glitches = tuple((int(rng.integers(1000, len(iq0) - 2000)), int(rng.integers(20, 400))) for _ in range(int(rng.integers(0, 5))))
+    iq, _, _ = util.capture(dev, n_msgs, sigma=sigma, amplitude=float(rng.uniform(0.5, 0.95)), phase=float(rng.uniform(0, 6.28)),
+                            seed=seed, fields=fields, glitches=glitches)
+    stages = O.load_filter(filt)
+    sm = util.sm_spec(dev, stages)
+    ref = O.rx(iq, stages, dev, samples_per_buffer=spb)
+    plain = B.Gpu(filter_stages=stages, sm=sm, samples_per_buffer=spb, sm_chunk_buffers=cb)
+    sub = B.Gpu(filter_stages=stages, sm=sm, samples_per_buffer=spb, sm_chunk_buffers=cb, sub_windows=k)
+    want, wexit = plain.decode_shard(iq, 0, len(iq), True)
+    assert want["msgs"] == ref["msgs"]
+    for rep in range(2):
+        got, gexit = sub.decode_shard(iq, 0, len(iq), True)
+        assert got["msgs"] == ref["msgs"], (devname, filt, spb, k, cb, sigma, glitches)
+        assert gexit == wexit
+        assert np.array_equal(sub.edges()[1], ref["edges"])
+    plain.close()
+    sub.close()
