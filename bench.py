@@ -561,21 +561,32 @@ def main():
             nh = min(3, len(gpus))
             if L.ookd_gpu_decode_begin(gpus[0].h, p, is_dev, first, n, int(last), None):
                 raise SystemExit(f"decode_begin failed: {L.ookd_gpu_last_error(gpus[0].h).decode()}")
+            prof = [0.0, 0.0, 0.0] if os.environ.get("OOKD_BENCH_PROFILE") else None
             for i in range(n_steps):
                 g = gpus[i % nh]
+                tp0 = time.perf_counter()
                 if L.ookd_gpu_decode_end(g.h, C.byref(ex), C.byref(res)):                # waits for step i
                     raise SystemExit(f"decode_end failed: {L.ookd_gpu_last_error(g.h).decode()}")
+                tp1 = time.perf_counter()
                 if nh < 3:
                     st.confirm_pending()                      # (with two handles step i-1 must be settled before its handle is reused)
                 if i + 1 < n_steps:
                     g2 = gpus[(i + 1) % nh]
                     if L.ookd_gpu_decode_begin(g2.h, p, is_dev, first, n, int(last), None):
                         raise SystemExit(f"decode_begin failed: {L.ookd_gpu_last_error(g2.h).decode()}")
+                tp2 = time.perf_counter()
                 runner = S.GpuShardRunner(g, iq_arg, first, n, last)
                 decoded = (g._result(res), ex.astuple())
                 runner._acc(decoded[0])
                 st.confirm_pending()
                 finish(runner, decoded)
+                if prof is not None:
+                    prof[0] += tp1 - tp0
+                    prof[1] += tp2 - tp1
+                    prof[2] += time.perf_counter() - tp2
+            if prof is not None and n_steps >= 10:
+                print(f"[bench] rank {rank}: per step: in decode_end {1e6 * prof[0] / n_steps:.0f} us, decode_begin {1e6 * prof[1] / n_steps:.0f} us, "
+                      f"result + stitch {1e6 * prof[2] / n_steps:.0f} us; kernel span {acc[3] / n_steps:.3f} ms", file=sys.stderr)
         else:
             pending = []
             for i in range(n_steps):

@@ -1129,30 +1129,32 @@ __global__ void __launch_bounds__(32 * SM_ROUND_WARPS) sm_table_round_kernel(con
 // so just chunk 0 gains a pair (unless it already has this entry) and the walk restarts from it.
 __global__ void __launch_bounds__(32) sm_table_add_entry_kernel(const SmArgs a)
 {
+    // One WARP (uniform control flow; lane 0 writes): the span is a chain of dependent steps, and the warp-cooperative
+    // evaluator takes a third of the time per step of the per-thread one -- this kernel is the latency of a resolve.
     __shared__ SmTable T;
     load_table(T, a.tab);
-    if (threadIdx.x != 0) return;
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t K = a.tab_k;
     const uint32_t c = a.first_chunk;
     const uint32_t n_here = a.cnt_out[c];
     SmCarry s = a.entry0;
     if (!a.entry_at_report) {
         for (uint32_t i = 0; i < n_here; i++) {
-            if (carry_equal(s, a.tab_entry[(u64) c * K + i])) { *a.start_slot = i; return; }
+            if (carry_equal(s, a.tab_entry[(u64) c * K + i])) { if (lane == 0) *a.start_slot = i; return; }
         }
     } else {
         // warm shard: chunk 0's pairs start in the history; the corrected state applies at the shard's first output
         for (uint32_t i = 0; i < n_here; i++) {
-            if (carry_equal(s, a.mid_carry[i])) { *a.start_slot = i; return; }
+            if (carry_equal(s, a.mid_carry[i])) { if (lane == 0) *a.start_slot = i; return; }
         }
     }
-    if (n_here >= K) { atomicExch(a.overflow, 2u); return; }
+    if (n_here >= K) { if (lane == 0) atomicExch(a.overflow, 2u); return; }
     i64 start, end, lo;
     chunk_bounds(a, c, start, end, lo);
     u64 e = a.chunk_e[c];
     if (a.entry_at_report) {
         start = a.report_lo;
-        e = edge_lower_bound(a.edges, a.n_edges, (u64) start);
+        e = warp_edge_lower_bound(a.edges, a.n_edges, (u64) start, lane);
     }
     const uint32_t tb = a.base_bit ^ (uint32_t) (e & 1);
     SpanOut o;
@@ -1161,7 +1163,17 @@ __global__ void __launch_bounds__(32) sm_table_add_entry_kernel(const SmArgs a)
     o.n_msgs = 0;
     o.overflow = a.overflow;
     const SmCarry entry = s;
-    if (start < end) sm_run_span<false>(a, a.n_edges, T, s, start, end, e, tb, o, lo);
+    const bool warp_ok = warp_sm_supported(a.tab) && (end - lo) < (1ll << 31);
+    if (start < end) {
+        if (warp_ok) {
+            WarpSm W;
+            warp_sm_load(W, &T, lane);
+            warp_sm_run_span(a, a.n_edges, W, s, start, end, e, tb, o, lo, lane);
+        } else if (lane == 0) {
+            sm_run_span<false>(a, a.n_edges, T, s, start, end, e, tb, o, lo);
+        }
+    }
+    if (lane != 0) return;
     a.tab_entry[(u64) c * K + n_here] = a.entry_at_report ? SmCarry{OOKD_TAB_INVALID, 0, 0, 0, {0, 0, 0, 0}} : entry;
     a.tab_exit[(u64) c * K + n_here] = s;
     a.tab_nmsg[(u64) c * K + n_here] = (o.n_msgs < o.cap) ? o.n_msgs : o.cap;
